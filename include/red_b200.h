@@ -1,0 +1,216 @@
+/* red_b200.h - C ABI of the B200-native RED matcher (libred_b200.so).
+
+   This is the drop-in boundary for RED's data-parallel hot path: executing a
+   compiled, minimized, serialized DFA (the reference's `Executable`) over
+   batches of byte strings and over long byte streams, on sm_100a.
+
+   Everything here is plain C: pointers, sizes, ints.  No C++/torch types.
+   "device pointer" means a pointer into the HBM of the program's GPU (e.g. a
+   cudaMalloc'd buffer or a torch tensor's data_ptr()); "stream" is a
+   cudaStream_t passed as void* (NULL = the default stream).
+
+   Reference interfaces each entry point stands in for
+   (paths relative to /root/reference/quol/red):
+
+     red_b200_program_upload      Executable(const CopyTag&, string_view)
+                                    include/Executable.h:47, validate() at
+                                    lib/Executable.cpp:159, checkHeader() at
+                                    lib/Serializer.cpp:270
+     red_b200_match               match(exec, ptr, len, style) and
+                                  check/scan/search siblings
+                                    include/Matcher.h:74-94
+     red_b200_match_batch_*       the per-line loop over the same calls that a
+                                  RED user writes (tools/thr_red.cpp,
+                                  tools/big_red.cpp); no batch call exists in
+                                  the reference
+     red_b200_match_stream_*      match(exec, ptr, len, style) on one very long
+                                  text  include/Matcher.h:79
+     red_b200_compile             Parser::addAs + compileToSerialized
+                                    include/Parser.h:98, include/Compile.h:30
+
+   Style and verb numbers are the reference's (include/Matcher.h:62-69).
+   All functions return 0 on success or a negative RED_B200_E* code; the text
+   of the last error on the calling thread is red_b200_last_error().
+   There is no CPU fallback: without a usable sm_100 device every compute entry
+   point fails with RED_B200_ENODEVICE.
+ */
+
+#ifndef RED_B200_H
+#define RED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RED_B200_ABI_VERSION 1
+
+/* match styles: Matcher.h:62-69 */
+enum {
+  RED_B200_STY_INSTANT = 1,
+  RED_B200_STY_FIRST   = 2,
+  RED_B200_STY_TANGENT = 3,
+  RED_B200_STY_LAST    = 4,
+  RED_B200_STY_FULL    = 5
+};
+
+/* verbs: Matcher.h:9-13.  check = match without positions;
+   scan = search without positions. */
+enum {
+  RED_B200_VERB_CHECK  = 0,
+  RED_B200_VERB_MATCH  = 1,
+  RED_B200_VERB_SCAN   = 2,
+  RED_B200_VERB_SEARCH = 3
+};
+
+/* error codes; the class mirrors the reference's exceptions (Except.h) */
+enum {
+  RED_B200_OK         =  0,
+  RED_B200_EAPI       = -1,  /* RedExceptApi: bad argument / bad program   */
+  RED_B200_EEXEC      = -2,  /* RedExceptExec: unsupported style or verb   */
+  RED_B200_ELIMIT     = -3,  /* RedExceptLimit: too big                    */
+  RED_B200_EPARSE     = -4,  /* RedExceptParse: malformed regex            */
+  RED_B200_ECUDA      = -5,  /* a CUDA call failed                         */
+  RED_B200_ENODEVICE  = -6,  /* no sm_100 GPU visible: no CPU fallback     */
+  RED_B200_EINTERNAL  = -7
+};
+
+/* Outcome: include/Outcome.h:33-37 */
+typedef struct {
+  int32_t  result;
+  uint64_t start;
+  uint64_t end;
+} red_b200_outcome;
+
+typedef struct red_b200_program red_b200_program;
+
+/* where the kernels keep the transition table */
+enum {
+  RED_B200_TABLE_SMEM_U16   = 1, /* shared memory, 2-byte entries            */
+  RED_B200_TABLE_GLOBAL_U32 = 2  /* L2-resident global table, 4-byte entries */
+};
+
+typedef struct {
+  uint32_t abi_version;
+  uint32_t format;        /* serialized value width: 1, 2 or 4              */
+  uint32_t state_count;
+  uint32_t class_count;   /* byte equivalence classes = maxChar + 1         */
+  uint32_t leader_len;
+  uint32_t table_mode;    /* RED_B200_TABLE_*                               */
+  uint32_t row_stride;    /* entries per row in the device table            */
+  uint32_t accepting_states;
+  uint32_t pure_dead_states;
+  uint32_t max_result;
+  uint64_t table_bytes;   /* device transition table size                   */
+  int32_t  device;
+  int32_t  sm_count;
+} red_b200_program_info;
+
+const char *red_b200_last_error(void);
+int red_b200_abi_version(void);
+
+/* number of usable (compute capability 10.x) devices; 0 if none */
+int red_b200_device_count(void);
+
+/* Validate a serialized DFA exactly as the reference does (magic, version,
+   FNV-1a checksum, format) plus bounds checks the GPU needs, re-lay it out for
+   the kernels and upload it to `device`.  The serialized bytes are not kept. */
+int red_b200_program_upload(const void *serialized, size_t len, int device,
+                            red_b200_program **out);
+void red_b200_program_free(red_b200_program *prog);
+int red_b200_program_get_info(const red_b200_program *prog,
+                              red_b200_program_info *info);
+
+/* Host-only validation; returns NULL when good, else the reference's wording
+   of the complaint (checkHeader, lib/Serializer.cpp:270). */
+const char *red_b200_check_header(const void *serialized, size_t len);
+
+/* ---- batch of byte strings (lines) ------------------------------------ */
+
+/* Line i is text[starts[i] .. starts[i]+lens[i]).  Per line the result id,
+   and (verbs match/search) where the match started/ended, exactly as
+   Outcome would hold them; results of 0 come with start = end = 0.
+   match_starts / match_ends may be NULL when not wanted.
+   All pointers are device pointers; the call is asynchronous on `stream`. */
+int red_b200_match_batch_device(const red_b200_program *prog,
+                                const uint8_t *d_text,
+                                const uint64_t *d_starts,
+                                const uint32_t *d_lens,
+                                uint64_t n_lines, int verb, int style,
+                                int32_t *d_results,
+                                uint32_t *d_match_starts,
+                                uint32_t *d_match_ends,
+                                void *stream);
+
+/* Same with host buffers: text and index go to the GPU, results come back;
+   copies are chunked and overlapped with the kernels.  Synchronous. */
+int red_b200_match_batch_host(const red_b200_program *prog,
+                              const uint8_t *text, uint64_t text_len,
+                              const uint64_t *starts, const uint32_t *lens,
+                              uint64_t n_lines, int verb, int style,
+                              int32_t *results, uint32_t *match_starts,
+                              uint32_t *match_ends);
+
+/* One text, host memory: the reference's match()/check()/scan()/search().
+   Long texts take the chunked stream path. */
+int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
+                   int verb, int style, red_b200_outcome *out);
+
+/* ---- line index and match compaction ----------------------------------- */
+
+/* Split d_text[0..text_len) at `delim` bytes: writes the start offset and the
+   length (delimiter excluded) of every line; a trailing piece without a
+   delimiter counts as a line.  *n_lines_out gets the count (host memory).
+   Capacity is in lines; RED_B200_ELIMIT if it would overflow.  Synchronous on
+   `stream` (it has to return the count). */
+int red_b200_split_lines_device(const uint8_t *d_text, uint64_t text_len,
+                                uint8_t delim, uint64_t capacity,
+                                uint64_t *d_starts, uint32_t *d_lens,
+                                uint64_t *n_lines_out, int device,
+                                void *stream);
+
+/* Warp-ballot compaction of the matching lines: writes the indices of lines
+   with result > 0 in increasing order to d_indices (capacity n_lines) and the
+   count to *d_count (device, uint64).  Asynchronous on `stream`. */
+int red_b200_compact_matches_device(const int32_t *d_results, uint64_t n_lines,
+                                    uint64_t *d_indices, uint64_t *d_count,
+                                    int device, void *stream);
+
+/* ---- one long byte stream ---------------------------------------------- */
+
+/* match()/check() of one long device-resident text: the text is cut into
+   chunks, every chunk is run from every DFA state that can be live at its
+   start (all states, pruned as they converge), and the chunk state maps are
+   stitched with a parallel prefix composition.  Synchronous on `stream`. */
+int red_b200_match_stream_device(const red_b200_program *prog,
+                                 const uint8_t *d_text, uint64_t len,
+                                 int verb, int style, red_b200_outcome *out,
+                                 void *stream);
+
+/* ---- host side: regex -> serialized DFA (RED's compile pipeline) -------- */
+
+/* languages: Parser.h:43-49; flags: Consts.h:14-18; formats: Serializer.h:37 */
+enum { RED_B200_LANG_RAW = 1, RED_B200_LANG_AUTO = 2, RED_B200_LANG_GLOB = 3,
+       RED_B200_LANG_EXACT = 4 };
+enum { RED_B200_F_IGNORE_CASE = 1, RED_B200_F_LOOSE_START = 2,
+       RED_B200_F_LOOSE_END = 4 };
+enum { RED_B200_FMT_1 = 1, RED_B200_FMT_2 = 2, RED_B200_FMT_4 = 4,
+       RED_B200_FMT_AUTO = 255 };
+
+/* Parse n patterns, build the NFA, determinize, minimize and serialize into
+   the reference's REDA format (loadable by the reference's Executable as
+   well).  *out is malloc'd; release with red_b200_free().  max_states = 0
+   means no budget (Budget.h). */
+int red_b200_compile(int n, const char *const *patterns,
+                     const uint64_t *pattern_lens, const int32_t *results,
+                     const uint32_t *flags, const int32_t *langs, int format,
+                     uint64_t max_states, void **out, uint64_t *out_len);
+void red_b200_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RED_B200_H */

@@ -1,0 +1,614 @@
+/* capi.cu - the C ABI of libred_b200.so (include/red_b200.h).
+
+   Host-side plumbing only: argument checks with the reference's error
+   classes, program upload, launches, and the chunked host<->device pipeline
+   of the *_host entry points.  There is no CPU execution path in this file:
+   if no sm_100 device is present the compute entry points fail. */
+
+#include "../../include/red_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "compile/compile.h"
+#include "device_program.h"
+#include "program.h"
+#include "stream.h"
+
+using namespace red_b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t err, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(err);
+  return RED_B200_ECUDA;
+}
+
+#define CUDA_TRY(expr)                                   \
+  do {                                                   \
+    cudaError_t e_ = (expr);                             \
+    if (e_ != cudaSuccess)                               \
+      return cuda_fail(e_, #expr);                       \
+  } while (0)
+
+bool usable_device(int dev) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return false;
+  return prop.major == 10;  // sm_100a code only
+}
+
+bool valid_style(int style) { return (style >= 1) && (style <= 5); }
+bool valid_verb(int verb) { return (verb >= 0) && (verb <= 3); }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess)
+      prev = -1;
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+
+} // anonymous
+
+struct red_b200_program {
+  int device = 0;
+  LaunchGeometry geo{};
+  DeviceImage img;      // host copy (tables cleared after upload)
+  ParsedProgram parsed; // kept small: tables cleared after upload
+  ProgramDev dev{};
+  bool smemTable = false;
+  uint32_t format = 0;
+  uint32_t leaderLen = 0;
+  uint64_t tableBytes = 0;
+  void *dTable = nullptr;
+  void *dCls = nullptr;
+  void *dResults = nullptr;
+  void *dLeader = nullptr;
+  BatchTuning tune;
+  std::mutex mu;        // guards the lazily created host pipeline
+  struct HostPipe *pipe = nullptr;
+  long launches = 0;    // kernels launched through this program (for bench)
+};
+
+/* Pinned staging + device buffers for the *_host entry points: two slots so
+   that the copy-in of chunk i+1 overlaps the kernel of chunk i and the
+   copy-out of chunk i-1. */
+struct HostPipe {
+  static constexpr int kSlots = 2;
+  size_t textCap = 0, lineCap = 0;
+  cudaStream_t stream[kSlots]{};
+  cudaEvent_t done[kSlots]{};
+  uint8_t *dText[kSlots]{};
+  uint64_t *dStarts[kSlots]{};
+  uint32_t *dLens[kSlots]{};
+  int32_t *dRes[kSlots]{};
+  uint32_t *dMs[kSlots]{};
+  uint32_t *dMe[kSlots]{};
+  uint64_t *hStarts[kSlots]{};  // pinned: chunk-relative starts
+
+  void release() {
+    for (int s = 0; s < kSlots; ++s) {
+      if (stream[s]) cudaStreamDestroy(stream[s]);
+      if (done[s]) cudaEventDestroy(done[s]);
+      cudaFree(dText[s]); cudaFree(dStarts[s]); cudaFree(dLens[s]);
+      cudaFree(dRes[s]); cudaFree(dMs[s]); cudaFree(dMe[s]);
+      if (hStarts[s]) cudaFreeHost(hStarts[s]);
+    }
+  }
+};
+
+extern "C" {
+
+const char *red_b200_last_error(void) { return g_err.c_str(); }
+
+int red_b200_abi_version(void) { return RED_B200_ABI_VERSION; }
+
+int red_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int good = 0;
+  for (int d = 0; d < n; ++d)
+    if (usable_device(d))
+      ++good;
+  return good;
+}
+
+const char *red_b200_check_header(const void *serialized, size_t len) {
+  return check_header(serialized, len);
+}
+
+int red_b200_program_upload(const void *serialized, size_t len, int device,
+                            red_b200_program **out) {
+  if (!out)
+    return fail(RED_B200_EAPI, "null output pointer");
+  *out = nullptr;
+  if (!serialized || (len == 0))
+    return fail(RED_B200_EAPI, "serialized dfa is empty");
+
+  auto prog = new red_b200_program;
+  std::string why;
+  if (!parse_program(serialized, len, prog->parsed, why)) {
+    delete prog;
+    return fail(RED_B200_EAPI, why);
+  }
+  if (static_cast<uint64_t>(prog->parsed.stateCount) *
+          prog->parsed.classCount > 0xffffffffull) {
+    delete prog;
+    return fail(RED_B200_ELIMIT, "dfa too big for device table");
+  }
+
+  int ndev = 0;
+  if ((cudaGetDeviceCount(&ndev) != cudaSuccess) || (ndev == 0)) {
+    cudaGetLastError();
+    delete prog;
+    return fail(RED_B200_ENODEVICE,
+                "no CUDA device visible; red_b200 has no CPU fallback");
+  }
+  if ((device < 0) || (device >= ndev) || !usable_device(device)) {
+    delete prog;
+    return fail(RED_B200_ENODEVICE,
+                "device is not an sm_100 GPU; red_b200 has no CPU fallback");
+  }
+  prog->device = device;
+  DeviceGuard guard(device);
+
+  cudaDeviceProp prop;
+  cudaError_t err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess) {
+    delete prog;
+    return cuda_fail(err, "cudaGetDeviceProperties");
+  }
+  prog->geo.smCount = prop.multiProcessorCount;
+  prog->geo.maxSmemOptin = static_cast<int>(prop.sharedMemPerBlockOptin);
+
+  // leave room for the class table and a little slack
+  size_t budget = prop.sharedMemPerBlockOptin - 1024;
+  if (const char *env = getenv("RED_B200_SMEM_TABLE_LIMIT"))
+    budget = std::min<size_t>(budget, strtoull(env, nullptr, 0));
+  build_image(prog->parsed, budget, prog->img);
+  DeviceImage &img = prog->img;
+  prog->smemTable = (img.mode == kTableSmemU16);
+  prog->format = prog->parsed.format;
+  prog->leaderLen = prog->parsed.leaderLen;
+
+  const void *tab = prog->smemTable
+      ? static_cast<const void *>(img.table16.data())
+      : static_cast<const void *>(img.table32.data());
+  size_t tabBytes = img.tableBytes();
+  size_t padded = (tabBytes + 15) & ~size_t(15);
+  prog->tableBytes = tabBytes;
+
+  auto cleanup = [&](cudaError_t e, const char *what) {
+    cudaFree(prog->dTable); cudaFree(prog->dCls); cudaFree(prog->dResults);
+    cudaFree(prog->dLeader);
+    delete prog;
+    return cuda_fail(e, what);
+  };
+  if ((err = cudaMalloc(&prog->dTable, padded)) != cudaSuccess)
+    return cleanup(err, "cudaMalloc(table)");
+  if ((err = cudaMemset(prog->dTable, 0, padded)) != cudaSuccess)
+    return cleanup(err, "cudaMemset(table)");
+  if ((err = cudaMemcpy(prog->dTable, tab, tabBytes, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cleanup(err, "cudaMemcpy(table)");
+  if ((err = cudaMalloc(&prog->dCls, 512)) != cudaSuccess)
+    return cleanup(err, "cudaMalloc(cls)");
+  if ((err = cudaMemcpy(prog->dCls, img.clsOffset.data(), 512, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cleanup(err, "cudaMemcpy(cls)");
+  if ((err = cudaMalloc(&prog->dResults, img.results.size() * 4)) != cudaSuccess)
+    return cleanup(err, "cudaMalloc(results)");
+  if ((err = cudaMemcpy(prog->dResults, img.results.data(), img.results.size() * 4,
+                        cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cleanup(err, "cudaMemcpy(results)");
+
+  {
+    // the leader in the same pre-scaled class space as clsOffset
+    std::vector<uint16_t> lead(std::max<size_t>(1, img.leader.size()), 0);
+    uint32_t entryBytes = prog->smemTable ? 2 : 4;
+    for (size_t ii = 0; ii < img.leader.size(); ++ii)
+      lead[ii] = static_cast<uint16_t>(img.leader[ii] * entryBytes);
+    if ((err = cudaMalloc(&prog->dLeader, lead.size() * 2)) != cudaSuccess)
+      return cleanup(err, "cudaMalloc(leader)");
+    if ((err = cudaMemcpy(prog->dLeader, lead.data(), lead.size() * 2,
+                          cudaMemcpyHostToDevice)) != cudaSuccess)
+      return cleanup(err, "cudaMemcpy(leader)");
+  }
+
+  ProgramDev &pd = prog->dev;
+  pd.leader = static_cast<const uint16_t *>(prog->dLeader);
+  pd.leaderLen = static_cast<uint32_t>(img.leader.size());
+  pd.leaderV = img.leaderV;
+  pd.clsOffset = static_cast<const uint16_t *>(prog->dCls);
+  pd.table = prog->dTable;
+  pd.results = static_cast<const int32_t *>(prog->dResults);
+  pd.tableBytes = static_cast<uint32_t>(padded);
+  pd.unitShift = img.unitShift;
+  pd.initV = img.initV;
+  pd.acceptV = img.acceptV;
+  pd.pureV = img.pureV;
+  pd.vPerState = img.vPerState;
+  pd.clsMaxOffset = *std::max_element(img.clsOffset.begin(), img.clsOffset.end());
+  pd.initResult = img.initResult;
+
+  // the host copies of the big tables are no longer needed
+  std::vector<uint16_t>().swap(img.table16);
+  std::vector<uint32_t>().swap(img.table32);
+  std::vector<uint32_t>().swap(prog->parsed.next);
+
+  if (const char *env = getenv("RED_B200_THREADS"))
+    prog->tune.threads = atoi(env);
+  if (const char *env = getenv("RED_B200_CTAS_PER_SM"))
+    prog->tune.ctasPerSm = atoi(env);
+  if (const char *env = getenv("RED_B200_SIMPLE_WALK"))
+    prog->tune.simpleWalk = atoi(env) != 0;
+
+  *out = prog;
+  return RED_B200_OK;
+}
+
+void red_b200_program_free(red_b200_program *prog) {
+  if (!prog)
+    return;
+  DeviceGuard guard(prog->device);
+  if (prog->pipe) {
+    prog->pipe->release();
+    delete prog->pipe;
+  }
+  cudaFree(prog->dTable);
+  cudaFree(prog->dCls);
+  cudaFree(prog->dResults);
+  cudaFree(prog->dLeader);
+  delete prog;
+}
+
+int red_b200_program_get_info(const red_b200_program *prog,
+                              red_b200_program_info *info) {
+  if (!prog || !info)
+    return fail(RED_B200_EAPI, "null argument");
+  memset(info, 0, sizeof(*info));
+  info->abi_version = RED_B200_ABI_VERSION;
+  info->format = prog->format;
+  info->state_count = prog->img.stateCount;
+  info->class_count = prog->img.classCount;
+  info->leader_len = prog->leaderLen;
+  info->table_mode = prog->smemTable ? RED_B200_TABLE_SMEM_U16
+                                     : RED_B200_TABLE_GLOBAL_U32;
+  info->row_stride = prog->img.rowStride;
+  info->accepting_states = prog->img.acceptCount;
+  info->pure_dead_states = prog->img.pureCount;
+  info->max_result = static_cast<uint32_t>(prog->img.maxResult);
+  info->table_bytes = prog->tableBytes;
+  info->device = prog->device;
+  info->sm_count = prog->geo.smCount;
+  return RED_B200_OK;
+}
+
+/* kernels launched through this program so far (bench.py's gpu_launches) */
+long red_b200_program_launch_count(const red_b200_program *prog) {
+  return prog ? prog->launches : 0;
+}
+
+static int launch_batch(red_b200_program *prog, const BatchArgs &args,
+                        int verb, int style, cudaStream_t stream) {
+  int launches = 0;
+  cudaError_t err;
+  if ((verb == RED_B200_VERB_CHECK) || (verb == RED_B200_VERB_MATCH)) {
+    BatchArgs a = args;
+    a.checkLeader = (verb == RED_B200_VERB_CHECK) && (prog->dev.leaderLen > 0);
+    err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
+                                prog->geo, prog->tune, stream, &launches);
+  }
+  else
+    err = launch_batch_sliding(prog->dev, prog->smemTable, args, style,
+                               verb == RED_B200_VERB_SEARCH, prog->geo, stream,
+                               &launches);
+  if (err != cudaSuccess)
+    return cuda_fail(err, "batch kernel launch");
+  prog->launches += launches;
+  return RED_B200_OK;
+}
+
+int red_b200_match_batch_device(const red_b200_program *cprog,
+                                const uint8_t *d_text,
+                                const uint64_t *d_starts,
+                                const uint32_t *d_lens, uint64_t n_lines,
+                                int verb, int style, int32_t *d_results,
+                                uint32_t *d_match_starts,
+                                uint32_t *d_match_ends, void *stream) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if (!valid_style(style))
+    return fail(RED_B200_EEXEC, "unsupported style");
+  if (!valid_verb(verb))
+    return fail(RED_B200_EEXEC, "unsupported verb");
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!d_text || !d_starts || !d_lens || !d_results)
+    return fail(RED_B200_EAPI, "null buffer");
+  BatchArgs args;
+  args.text = d_text;
+  args.starts = d_starts;
+  args.lens = d_lens;
+  args.nLines = n_lines;
+  args.results = d_results;
+  // check/scan report no positions (Matcher.h:74-77, 84-87)
+  bool positions = (verb == RED_B200_VERB_MATCH) || (verb == RED_B200_VERB_SEARCH);
+  args.matchStarts = positions ? d_match_starts : nullptr;
+  args.matchEnds = positions ? d_match_ends : nullptr;
+  DeviceGuard guard(prog->device);
+  return launch_batch(prog, args, verb, style, static_cast<cudaStream_t>(stream));
+}
+
+static int ensure_pipe(red_b200_program *prog, size_t textCap, size_t lineCap) {
+  HostPipe *pp = prog->pipe;
+  if (pp && (pp->textCap >= textCap) && (pp->lineCap >= lineCap))
+    return RED_B200_OK;
+  if (pp) {
+    pp->release();
+    delete pp;
+    prog->pipe = nullptr;
+  }
+  pp = new HostPipe;
+  pp->textCap = textCap;
+  pp->lineCap = lineCap;
+  prog->pipe = pp;
+  for (int s = 0; s < HostPipe::kSlots; ++s) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&pp->stream[s], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&pp->done[s], cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&pp->dText[s], textCap + 64));
+    CUDA_TRY(cudaMalloc(&pp->dStarts[s], lineCap * 8));
+    CUDA_TRY(cudaMalloc(&pp->dLens[s], lineCap * 4));
+    CUDA_TRY(cudaMalloc(&pp->dRes[s], lineCap * 4));
+    CUDA_TRY(cudaMalloc(&pp->dMs[s], lineCap * 4));
+    CUDA_TRY(cudaMalloc(&pp->dMe[s], lineCap * 4));
+    CUDA_TRY(cudaMallocHost(&pp->hStarts[s], lineCap * 8));
+  }
+  return RED_B200_OK;
+}
+
+int red_b200_match_batch_host(const red_b200_program *cprog,
+                              const uint8_t *text, uint64_t text_len,
+                              const uint64_t *starts, const uint32_t *lens,
+                              uint64_t n_lines, int verb, int style,
+                              int32_t *results, uint32_t *match_starts,
+                              uint32_t *match_ends) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if (!valid_style(style))
+    return fail(RED_B200_EEXEC, "unsupported style");
+  if (!valid_verb(verb))
+    return fail(RED_B200_EEXEC, "unsupported verb");
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!text || !starts || !lens || !results)
+    return fail(RED_B200_EAPI, "null buffer");
+  bool positions = (verb == RED_B200_VERB_MATCH) || (verb == RED_B200_VERB_SEARCH);
+  if (!positions) {
+    match_starts = nullptr;
+    match_ends = nullptr;
+  }
+
+  std::lock_guard<std::mutex> lock(prog->mu);
+  DeviceGuard guard(prog->device);
+
+  /* Cut the batch into chunks of consecutive lines whose bytes form one
+     span of the text (lines are normally in text order; a batch that is not
+     is still correct, its spans just get longer).  Chunk targets: ~64 MiB of
+     text or 1 Mi lines, whichever comes first. */
+  size_t textTarget = 64u << 20;
+  size_t lineTarget = 1u << 20;
+  if (const char *env = getenv("RED_B200_HOST_CHUNK_BYTES"))
+    textTarget = std::max<size_t>(1 << 16, strtoull(env, nullptr, 0));
+
+  struct Chunk { uint64_t first, count, lo, hi; };
+  std::vector<Chunk> chunks;
+  {
+    uint64_t ii = 0;
+    while (ii < n_lines) {
+      Chunk c{ii, 0, starts[ii], starts[ii] + lens[ii]};
+      while (ii < n_lines) {
+        uint64_t lo = std::min(c.lo, starts[ii]);
+        uint64_t hi = std::max(c.hi, starts[ii] + lens[ii]);
+        if (hi > text_len)
+          return fail(RED_B200_EAPI, "line extends past end of text");
+        if (c.count && (((hi - lo) > textTarget) || (c.count >= lineTarget)))
+          break;
+        c.lo = lo; c.hi = hi; ++c.count; ++ii;
+      }
+      chunks.push_back(c);
+    }
+  }
+  size_t maxText = 0, maxLines = 0;
+  for (const Chunk &c : chunks) {
+    maxText = std::max<size_t>(maxText, c.hi - c.lo);
+    maxLines = std::max<size_t>(maxLines, c.count);
+  }
+  int rc = ensure_pipe(prog, maxText, maxLines);
+  if (rc != RED_B200_OK)
+    return rc;
+  HostPipe *pp = prog->pipe;
+
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk &c = chunks[ci];
+    int s = static_cast<int>(ci % HostPipe::kSlots);
+    cudaStream_t st = pp->stream[s];
+    // slot free? (its previous copy-out finished)
+    CUDA_TRY(cudaEventSynchronize(pp->done[s]));
+    // the device copy keeps the span's alignment modulo 16
+    uint64_t lo16 = c.lo & ~uint64_t(15);
+    for (uint64_t k = 0; k < c.count; ++k)
+      pp->hStarts[s][k] = starts[c.first + k] - lo16;
+    CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (c.lo - lo16), text + c.lo,
+                             c.hi - c.lo, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], pp->hStarts[s], c.count * 8,
+                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + c.first, c.count * 4,
+                             cudaMemcpyHostToDevice, st));
+    BatchArgs args;
+    args.text = pp->dText[s];
+    args.starts = pp->dStarts[s];
+    args.lens = pp->dLens[s];
+    args.nLines = c.count;
+    args.results = pp->dRes[s];
+    args.matchStarts = match_starts ? pp->dMs[s] : nullptr;
+    args.matchEnds = match_ends ? pp->dMe[s] : nullptr;
+    rc = launch_batch(prog, args, verb, style, st);
+    if (rc != RED_B200_OK)
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(results + c.first, pp->dRes[s], c.count * 4,
+                             cudaMemcpyDeviceToHost, st));
+    if (match_starts)
+      CUDA_TRY(cudaMemcpyAsync(match_starts + c.first, pp->dMs[s], c.count * 4,
+                               cudaMemcpyDeviceToHost, st));
+    if (match_ends)
+      CUDA_TRY(cudaMemcpyAsync(match_ends + c.first, pp->dMe[s], c.count * 4,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(pp->done[s], st));
+  }
+  for (int s = 0; s < HostPipe::kSlots; ++s)
+    CUDA_TRY(cudaStreamSynchronize(pp->stream[s]));
+  return RED_B200_OK;
+}
+
+int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
+                   int verb, int style, red_b200_outcome *out) {
+  if (!prog || !out)
+    return fail(RED_B200_EAPI, "null argument");
+  if (!valid_style(style))
+    return fail(RED_B200_EEXEC, "unsupported style");
+  if (!valid_verb(verb))
+    return fail(RED_B200_EEXEC, "unsupported verb");
+  if (len >= (1ull << 31))
+    return fail(RED_B200_ELIMIT, "text too long for red_b200_match; use the stream entry point");
+  uint64_t start0 = 0;
+  uint32_t len32 = static_cast<uint32_t>(len);
+  int32_t res = 0;
+  uint32_t ms = 0, me = 0;
+  static const uint8_t empty[1] = {0};
+  const uint8_t *t = len ? static_cast<const uint8_t *>(text) : empty;
+  if (len && !text)
+    return fail(RED_B200_EAPI, "null text");
+  int rc = red_b200_match_batch_host(prog, t, len, &start0, &len32, 1, verb,
+                                     style, &res, &ms, &me);
+  if (rc != RED_B200_OK)
+    return rc;
+  out->result = res;
+  out->start = ms;
+  out->end = me;
+  return RED_B200_OK;
+}
+
+int red_b200_split_lines_device(const uint8_t *d_text, uint64_t text_len,
+                                uint8_t delim, uint64_t capacity,
+                                uint64_t *d_starts, uint32_t *d_lens,
+                                uint64_t *n_lines_out, int device,
+                                void *stream) {
+  if (!n_lines_out)
+    return fail(RED_B200_EAPI, "null argument");
+  if (text_len && (!d_text || !d_starts || !d_lens))
+    return fail(RED_B200_EAPI, "null buffer");
+  if (!usable_device(device))
+    return fail(RED_B200_ENODEVICE, "device is not an sm_100 GPU; red_b200 has no CPU fallback");
+  DeviceGuard guard(device);
+  std::string why;
+  int rc = split_lines(d_text, text_len, delim, capacity, d_starts, d_lens,
+                       n_lines_out, static_cast<cudaStream_t>(stream), why);
+  if (rc != RED_B200_OK)
+    return fail(rc, why);
+  return RED_B200_OK;
+}
+
+int red_b200_compact_matches_device(const int32_t *d_results, uint64_t n_lines,
+                                    uint64_t *d_indices, uint64_t *d_count,
+                                    int device, void *stream) {
+  if (!d_count || (n_lines && (!d_results || !d_indices)))
+    return fail(RED_B200_EAPI, "null buffer");
+  if (!usable_device(device))
+    return fail(RED_B200_ENODEVICE, "device is not an sm_100 GPU; red_b200 has no CPU fallback");
+  DeviceGuard guard(device);
+  std::string why;
+  int rc = compact_matches(d_results, n_lines, d_indices, d_count,
+                           static_cast<cudaStream_t>(stream), why);
+  if (rc != RED_B200_OK)
+    return fail(rc, why);
+  return RED_B200_OK;
+}
+
+int red_b200_match_stream_device(const red_b200_program *cprog,
+                                 const uint8_t *d_text, uint64_t len,
+                                 int verb, int style, red_b200_outcome *out,
+                                 void *stream) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog || !out)
+    return fail(RED_B200_EAPI, "null argument");
+  if (!valid_style(style))
+    return fail(RED_B200_EEXEC, "unsupported style");
+  if ((verb != RED_B200_VERB_CHECK) && (verb != RED_B200_VERB_MATCH))
+    return fail(RED_B200_EEXEC, "stream path supports check and match");
+  if (len && !d_text)
+    return fail(RED_B200_EAPI, "null text");
+  DeviceGuard guard(prog->device);
+  std::string why;
+  int launches = 0;
+  int rc = match_stream(prog->dev, prog->smemTable, prog->img, prog->geo,
+                        d_text, len, style, out,
+                        static_cast<cudaStream_t>(stream), &launches, why);
+  prog->launches += launches;
+  if (rc != RED_B200_OK)
+    return fail(rc, why);
+  if (verb == RED_B200_VERB_CHECK) {
+    out->start = 0;
+    out->end = 0;
+  }
+  return RED_B200_OK;
+}
+
+int red_b200_compile(int n, const char *const *patterns,
+                     const uint64_t *pattern_lens, const int32_t *results,
+                     const uint32_t *flags, const int32_t *langs, int format,
+                     uint64_t max_states, void **out, uint64_t *out_len) {
+  if (!out || !out_len || (n < 0) ||
+      (n && (!patterns || !pattern_lens || !results || !flags || !langs)))
+    return fail(RED_B200_EAPI, "null argument");
+  std::string buf, why;
+  int rc = compile_patterns(n, patterns, pattern_lens, results, flags, langs,
+                            format, max_states, buf, why);
+  if (rc != RED_B200_OK)
+    return fail(rc, why);
+  void *mem = malloc(buf.size() ? buf.size() : 1);
+  if (!mem)
+    return fail(RED_B200_ELIMIT, "out of memory");
+  memcpy(mem, buf.data(), buf.size());
+  *out = mem;
+  *out_len = buf.size();
+  return RED_B200_OK;
+}
+
+void red_b200_free(void *p) { free(p); }
+
+} // extern "C"

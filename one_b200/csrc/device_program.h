@@ -1,0 +1,66 @@
+/* device_program.h - what the kernels see of an uploaded program, and the
+   launch entry points implemented in kernels.cu. */
+
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace red_b200 {
+
+// Passed to kernels by value.  All pointers are device pointers.
+struct ProgramDev {
+  const uint16_t *clsOffset;  // [256] byte -> class * entryBytes
+  const void *table;          // u16 (smem mode) or u32 (global mode) entries
+  const int32_t *results;     // [stateCount], by renumbered state index
+  const uint16_t *leader;     // [leaderLen] required prefix, as class offsets
+  uint32_t leaderLen;
+  uint32_t leaderV;           // state reached after the leader
+  uint32_t tableBytes;
+  uint32_t unitShift;   // smem mode: row entry index = v << unitShift
+  uint32_t initV;
+  uint32_t acceptV;     // acceptV <= v < pureV : accepting
+  uint32_t pureV;       // v >= pureV          : pure dead end
+  uint32_t vPerState;
+  uint32_t clsMaxOffset;  // largest value in clsOffset
+  int32_t initResult;
+};
+
+struct BatchArgs {
+  const uint8_t *text;
+  const uint64_t *starts;
+  const uint32_t *lens;
+  uint64_t nLines;
+  int32_t *results;
+  uint32_t *matchStarts;  // may be null
+  uint32_t *matchEnds;    // may be null
+  bool checkLeader = false;  // verb check on a program that has a leader
+};
+
+struct LaunchGeometry {
+  int smCount;
+  int maxSmemOptin;  // bytes
+};
+
+// tuning knobs, overridable for sweeps (bench.py --tune)
+struct BatchTuning {
+  int threads = 0;      // 0 = pick
+  int ctasPerSm = 0;    // 0 = pick
+  bool simpleWalk = false;  // per-byte decisions only (A/B baseline)
+};
+
+// verbs check/match (anchored walk).  smemTable selects the table mode.
+cudaError_t launch_batch_anchored(const ProgramDev &pd, bool smemTable,
+                                  const BatchArgs &args, int style,
+                                  const LaunchGeometry &geo,
+                                  const BatchTuning &tune, cudaStream_t stream,
+                                  int *launches);
+
+// verbs scan/search (sliding start position)
+cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
+                                 const BatchArgs &args, int style,
+                                 bool wantPositions,
+                                 const LaunchGeometry &geo,
+                                 cudaStream_t stream, int *launches);
+
+} // namespace red_b200

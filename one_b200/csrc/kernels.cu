@@ -1,0 +1,522 @@
+/* kernels.cu - sm_100a kernels that execute an uploaded RED program over a
+   batch of byte strings (one lane per line).
+
+   What is computed per line is exactly matchCore / checkCore of the reference
+   (include/Matcher.h:363-495): walk the DFA from the initial state, one byte
+   at a time, and stop according to the style.  How it is computed differs:
+
+     * the table is the re-laid-out image of program.h: one step is
+           v = T[(v << K) + clsOffset[byte]]
+       two shared-memory loads, the first of which does not depend on v;
+     * "did anything happen at this byte" is one compare, v >= limit, where
+       limit = acceptV normally, and 0 once a First/Tangent walk has seen an
+       accepting state (then every further state needs a decision);
+     * results are looked up only when the walk ends;
+     * text is read 16 bytes at a time per lane through the read-only path,
+       with the next chunk requested before the current one is walked.
+
+   Styles as template parameters: 1 instant, 2 first, 3 tangent, 4 last,
+   5 full (Matcher.h:62-69).
+ */
+
+#include "device_program.h"
+
+#include <algorithm>
+
+namespace red_b200 {
+
+namespace {
+
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr int kMaxThreads = 1024;
+
+enum { STY_INSTANT = 1, STY_FIRST = 2, STY_TANGENT = 3, STY_LAST = 4,
+       STY_FULL = 5 };
+
+// ---- table accessors ------------------------------------------------------
+
+// u16 entries in shared memory; K = unitShift + 1 (byte offset of row = v<<K)
+template <int K> struct SmemTable {
+  const unsigned char *base;
+  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
+    return *reinterpret_cast<const uint16_t *>(base + ((v << K) + co));
+  }
+};
+
+// u32 entries in global memory (L1/L2 resident); byte offset of row = v * 4
+struct GlobalTable {
+  const unsigned char *base;
+  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
+    return __ldg(reinterpret_cast<const uint32_t *>(
+        base + ((static_cast<size_t>(v) << 2) + co)));
+  }
+};
+
+// ---- the walk -------------------------------------------------------------
+
+template <int STYLE, bool WANT_START> struct Walk {
+  uint32_t v;       // current state
+  uint32_t limit;   // states >= limit need a decision
+  uint32_t accV;    // last accepting state seen (kNone: none)
+  uint32_t mstart;  // where the initial state was last left
+  uint32_t mend;    // one past the last accepting position
+
+  __device__ __forceinline__ void begin(const ProgramDev &pd) {
+    v = pd.initV;
+    // a Full walk only ever has to notice pure dead ends (to stop early)
+    limit = (STYLE == STY_FULL) ? pd.pureV : pd.acceptV;
+    accV = kNone;
+    mstart = 0;
+    mend = 0;
+  }
+
+  // out-of-line part of a step; true = the walk is over
+  __device__ __forceinline__ bool special(const ProgramDev &pd, uint32_t pos) {
+    if (v >= pd.pureV)
+      return true;  // pure dead end: Matcher.h:405/478
+    if (STYLE == STY_FULL)
+      return false;
+    if (v >= pd.acceptV) {
+      if (STYLE == STY_FIRST) {
+        // stop when the result changes (Matcher.h:455-460)
+        if ((accV != kNone) && (v != accV) &&
+            (pd.results[v / pd.vPerState] != pd.results[accV / pd.vPerState]))
+          return true;
+      }
+      accV = v;
+      mend = pos + 1;
+      if (STYLE == STY_INSTANT)
+        return true;
+      if ((STYLE == STY_FIRST) || (STYLE == STY_TANGENT))
+        limit = 0;  // from now on the first rejecting state ends the walk
+      return false;
+    }
+    // ordinary rejecting state after an accept (First/Tangent only)
+    return true;
+  }
+
+  template <class Tab>
+  __device__ __forceinline__ bool step(const ProgramDev &pd, const Tab &tab,
+                                       uint32_t co, uint32_t pos) {
+    uint32_t nv = tab.next(v, co);
+    if (WANT_START) {
+      if ((v == pd.initV) && (nv != pd.initV))
+        mstart = pos;
+    }
+    v = nv;
+    if (v >= limit)
+      return special(pd, pos);
+    return false;
+  }
+
+  __device__ __forceinline__ void finish(const ProgramDev &pd, uint32_t len,
+                                         int32_t &result, uint32_t &start,
+                                         uint32_t &end) const {
+    int32_t cur = ((v >= pd.acceptV) && (v < pd.pureV))
+                      ? pd.results[v / pd.vPerState] : 0;
+    int32_t prev = 0;
+    if ((STYLE != STY_FULL) && (STYLE != STY_INSTANT) && (accV != kNone))
+      prev = pd.results[accV / pd.vPerState];
+    result = (prev > 0) ? prev : cur;
+    uint32_t e = (STYLE == STY_FULL) ? len : mend;
+    start = (result > 0) ? mstart : 0;
+    end = (result > 0) ? e : 0;
+  }
+};
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int j) {
+  return __byte_perm(w, 0, 0x4440 | j);
+}
+
+__device__ __forceinline__ uint32_t word_of(const uint4 &q, int i) {
+  return (i == 0) ? q.x : (i == 1) ? q.y : (i == 2) ? q.z : q.w;
+}
+
+/* One line, anchored.  p need not be aligned: the walk reads the aligned
+   16-byte blocks that cover [p, p+len) and skips the bytes outside.  The
+   blocks before/after the line share a 16-byte block with valid bytes, so the
+   over-read stays inside the allocation granule of any CUDA allocation. */
+template <int STYLE, bool WANT_START, bool FAST, class Tab, class ClsT>
+__device__ __forceinline__ void
+walk_line(const ProgramDev &pd, const Tab &tab, const ClsT *cls,
+          const uint8_t *p, uint32_t len, uint32_t v0, int32_t &result,
+          uint32_t &start, uint32_t &end) {
+  Walk<STYLE, WANT_START> wk;
+  wk.begin(pd);
+  wk.v = v0;
+
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+  const uint32_t skip = static_cast<uint32_t>(addr & 15);
+  const uint4 *blk = reinterpret_cast<const uint4 *>(addr - skip);
+  const uint32_t total = skip + len;  // bytes from blk[0] to the line's end
+  const uint32_t nblk = (total + 15) >> 4;
+
+  if (len != 0) {
+    uint4 cur = __ldg(blk);
+    for (uint32_t k = 0; k < nblk; ++k) {
+      uint4 nxt = cur;
+      if (k + 1 < nblk)
+        nxt = __ldg(blk + k + 1);
+      const uint32_t pos0 = k * 16 - skip;  // line position of byte 0 (mod 2^32)
+      const uint32_t lo = (k == 0) ? skip : 0;
+      const uint32_t hi = min(16u, total - k * 16);
+      if ((lo == 0) && (hi == 16)) {
+        if (FAST) {
+          // Walk the 16 bytes without looking at what each state means; only
+          // remember whether any of them would have needed a decision.  If
+          // none did (the common case) the chunk is done.  Otherwise rewind
+          // and take the careful steps below.
+          Walk<STYLE, WANT_START> sv = wk;
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t b = byte_of(word_of(cur, j >> 2), j & 3);
+            uint32_t nv = tab.next(wk.v, cls[b]);
+            if (WANT_START) {
+              if ((wk.v == pd.initV) && (nv != pd.initV))
+                wk.mstart = pos0 + j;
+            }
+            wk.v = nv;
+            any |= (nv >= wk.limit);
+          }
+          if (!any) {
+            cur = nxt;
+            continue;
+          }
+          wk = sv;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          uint32_t b = byte_of(word_of(cur, j >> 2), j & 3);
+          if (wk.step(pd, tab, cls[b], pos0 + j))
+            goto done;
+        }
+      }
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((j >= lo) && (j < hi)) {
+            uint32_t b = byte_of(word_of(cur, j >> 2), j & 3);
+            if (wk.step(pd, tab, cls[b], pos0 + j))
+              goto done;
+          }
+        }
+      }
+      cur = nxt;
+    }
+  }
+done:
+  wk.finish(pd, len, result, start, end);
+}
+
+// ---- kernels --------------------------------------------------------------
+
+/* Shared memory layout (dynamic):
+     [0, 512)            class table: u8 (pre-scaled offsets < 256) or u16
+     [512, 512 + bytes)  transition table (smem mode only)                 */
+constexpr uint32_t kClsBytes = 512;
+
+template <class ClsT>
+__device__ __forceinline__ void stage_classes(const ProgramDev &pd,
+                                              unsigned char *smem) {
+  ClsT *cls = reinterpret_cast<ClsT *>(smem);
+  for (int ii = threadIdx.x; ii < 256; ii += blockDim.x)
+    cls[ii] = static_cast<ClsT>(pd.clsOffset[ii]);
+}
+
+__device__ __forceinline__ void stage_table(const ProgramDev &pd,
+                                            unsigned char *dst) {
+  // tableBytes is padded to a multiple of 16 by the uploader
+  const uint4 *src = reinterpret_cast<const uint4 *>(pd.table);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  const uint32_t n = pd.tableBytes >> 4;
+  for (uint32_t ii = threadIdx.x; ii < n; ii += blockDim.x)
+    d[ii] = __ldg(src + ii);
+}
+
+template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool FAST>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_anchored_kernel(const ProgramDev pd, const BatchArgs args) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+
+  // persistent CTAs: tile t covers lines [t*blockDim, (t+1)*blockDim)
+  const uint64_t tiles = (args.nLines + blockDim.x - 1) / blockDim.x;
+  for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint64_t line = t * blockDim.x + threadIdx.x;
+    if (line >= args.nLines)
+      continue;
+    const uint8_t *p = args.text + args.starts[line];
+    uint32_t len = args.lens[line];
+    uint32_t v0 = pd.initV;
+    int32_t result = 0;
+    uint32_t start = 0, end = 0;
+    bool viable = true;
+    if (args.checkLeader) {
+      /* check() with the leader optimisation (Matcher.h:369-376): the
+         required prefix is compared first and the walk starts after it, from
+         the state it leads to.  Kept because it is observable: an accepting
+         state reached exactly at the end of the leader is not noticed until
+         the next byte has been consumed. */
+      for (uint32_t ii = 0; ii < pd.leaderLen; ++ii)
+        if ((ii >= len) || (pd.leader[ii] != cls[__ldg(p + ii)])) {
+          viable = false;
+          break;
+        }
+      p += pd.leaderLen;
+      len -= pd.leaderLen;
+      v0 = pd.leaderV;
+    }
+    if (!viable) {
+      // nothing: result 0
+    }
+    else if (SMEM) {
+      SmemTable<K> tab{smem + kClsBytes};
+      walk_line<STYLE, WANT_START, FAST>(pd, tab, cls, p, len, v0, result, start, end);
+    }
+    else {
+      GlobalTable tab{static_cast<const unsigned char *>(pd.table)};
+      walk_line<STYLE, WANT_START, FAST>(pd, tab, cls, p, len, v0, result, start, end);
+    }
+    args.results[line] = result;
+    if (WANT_START)
+      args.matchStarts[line] = start;
+    if (args.matchEnds)
+      args.matchEnds[line] = end;
+  }
+}
+
+template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT>
+cudaError_t launch_one(const ProgramDev &pd, const BatchArgs &args,
+                       const LaunchGeometry &geo, const BatchTuning &tune,
+                       cudaStream_t stream) {
+  auto kern = tune.simpleWalk
+      ? batch_anchored_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>
+      : batch_anchored_kernel<STYLE, WANT_START, SMEM, K, ClsT, true>;
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  cudaError_t err = cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess)
+    return err;
+  int threads = tune.threads ? tune.threads : kMaxThreads;
+  int perSm = tune.ctasPerSm ? tune.ctasPerSm : 1;
+  uint64_t tiles = (args.nLines + threads - 1) / threads;
+  uint64_t grid = static_cast<uint64_t>(geo.smCount) * perSm;
+  if (grid > tiles)
+    grid = tiles;
+  if (grid == 0)
+    return cudaSuccess;
+  kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(pd, args);
+  return cudaGetLastError();
+}
+
+template <int STYLE, bool WANT_START>
+cudaError_t dispatch_table(const ProgramDev &pd, bool smemTable,
+                           const BatchArgs &args, const LaunchGeometry &geo,
+                           const BatchTuning &tune, cudaStream_t stream) {
+  const bool cls8 = pd.clsMaxOffset < 256;
+  if (smemTable) {
+    if (pd.unitShift == 0)
+      return cls8 ? launch_one<STYLE, WANT_START, true, 1, uint8_t>(pd, args, geo, tune, stream)
+                  : launch_one<STYLE, WANT_START, true, 1, uint16_t>(pd, args, geo, tune, stream);
+    if (pd.unitShift == 1)
+      return cls8 ? launch_one<STYLE, WANT_START, true, 2, uint8_t>(pd, args, geo, tune, stream)
+                  : launch_one<STYLE, WANT_START, true, 2, uint16_t>(pd, args, geo, tune, stream);
+    return cudaErrorInvalidValue;
+  }
+  return cls8 ? launch_one<STYLE, WANT_START, false, 0, uint8_t>(pd, args, geo, tune, stream)
+              : launch_one<STYLE, WANT_START, false, 0, uint16_t>(pd, args, geo, tune, stream);
+}
+
+template <bool WANT_START>
+cudaError_t dispatch_style(const ProgramDev &pd, bool smemTable,
+                           const BatchArgs &args, int style,
+                           const LaunchGeometry &geo, const BatchTuning &tune,
+                           cudaStream_t stream) {
+  switch (style) {
+  case STY_INSTANT: return dispatch_table<STY_INSTANT, WANT_START>(pd, smemTable, args, geo, tune, stream);
+  case STY_FIRST:   return dispatch_table<STY_FIRST, WANT_START>(pd, smemTable, args, geo, tune, stream);
+  case STY_TANGENT: return dispatch_table<STY_TANGENT, WANT_START>(pd, smemTable, args, geo, tune, stream);
+  case STY_LAST:    return dispatch_table<STY_LAST, WANT_START>(pd, smemTable, args, geo, tune, stream);
+  case STY_FULL:    return dispatch_table<STY_FULL, WANT_START>(pd, smemTable, args, geo, tune, stream);
+  default:          return cudaErrorInvalidValue;
+  }
+}
+
+
+// ---- sliding verbs: scan / search -----------------------------------------
+
+/* scanCore / searchCore (Matcher.h:498-641): try the anchored walk at
+   successive start positions until one matches.  One lane per line, bytes
+   read one at a time through the read-only path: this is the reference's
+   O(len^2) algorithm as is, kept simple because multi-pattern users are told
+   to use a loose-start DFA with match() instead (doc/Usage.md).
+
+   SCAN reproduces a quirk of the reference when the program has a leader:
+   compareThrough() advances the caller's cursor (Matcher.h:349), so after a
+   leader comparison - failed or not - the bytes it consumed are never tried
+   as start positions. */
+template <int STYLE, bool SEARCH, class Tab, class ClsT>
+__device__ __forceinline__ void
+slide_line(const ProgramDev &pd, const Tab &tab, const ClsT *cls,
+           const uint8_t *p, uint32_t len, int32_t &result, uint32_t &start,
+           uint32_t &end) {
+  Walk<STYLE, SEARCH> wk;
+  wk.begin(pd);
+  wk.finish(pd, 0, result, start, end);  // empty text: the initial state's result
+  start = 0;
+  end = 0;
+  if (len == 0)
+    return;
+  result = 0;
+  for (uint32_t pos = 0; pos < len; ++pos) {
+    wk.begin(pd);
+    if (!SEARCH && (pd.leaderLen > 0)) {
+      bool ok = true;
+      uint32_t ii = 0;
+      for (; ii < pd.leaderLen; ++ii) {
+        if ((pos + ii >= len) || (pd.leader[ii] != cls[__ldg(p + pos + ii)])) {
+          ok = false;
+          break;
+        }
+      }
+      pos += ii;
+      if (!ok)
+        continue;
+      wk.v = pd.leaderV;
+    }
+    wk.mstart = pos;
+    wk.mend = pos;
+    for (uint32_t idx = pos; idx < len; ++idx)
+      if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
+        break;
+    int32_t r;
+    uint32_t s, e;
+    wk.finish(pd, len, r, s, e);
+    if (r > 0) {
+      result = r;
+      start = s;
+      end = e;
+      return;
+    }
+  }
+}
+
+template <int STYLE, bool SEARCH, bool SMEM, int K, class ClsT>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_sliding_kernel(const ProgramDev pd, const BatchArgs args) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  const uint64_t tiles = (args.nLines + blockDim.x - 1) / blockDim.x;
+  for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint64_t line = t * blockDim.x + threadIdx.x;
+    if (line >= args.nLines)
+      continue;
+    const uint8_t *p = args.text + args.starts[line];
+    const uint32_t len = args.lens[line];
+    int32_t result;
+    uint32_t start, end;
+    if (SMEM) {
+      SmemTable<K> tab{smem + kClsBytes};
+      slide_line<STYLE, SEARCH>(pd, tab, cls, p, len, result, start, end);
+    }
+    else {
+      GlobalTable tab{static_cast<const unsigned char *>(pd.table)};
+      slide_line<STYLE, SEARCH>(pd, tab, cls, p, len, result, start, end);
+    }
+    args.results[line] = result;
+    if (args.matchStarts)
+      args.matchStarts[line] = start;
+    if (args.matchEnds)
+      args.matchEnds[line] = end;
+  }
+}
+
+template <int STYLE, bool SEARCH, bool SMEM, int K, class ClsT>
+cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
+                         const LaunchGeometry &geo, cudaStream_t stream) {
+  auto kern = batch_sliding_kernel<STYLE, SEARCH, SMEM, K, ClsT>;
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  cudaError_t err = cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess)
+    return err;
+  const int threads = 256;  // lines differ wildly in cost: smaller tiles
+  uint64_t tiles = (args.nLines + threads - 1) / threads;
+  uint64_t perSm = SMEM ? std::max<uint64_t>(1, std::min<uint64_t>(4, (200u << 10) / smem)) : 4;
+  uint64_t grid = std::min<uint64_t>(tiles, static_cast<uint64_t>(geo.smCount) * perSm);
+  if (grid == 0)
+    return cudaSuccess;
+  kern<<<static_cast<unsigned>(grid), threads, smem, stream>>>(pd, args);
+  return cudaGetLastError();
+}
+
+template <int STYLE, bool SEARCH>
+cudaError_t slide_table(const ProgramDev &pd, bool smemTable,
+                        const BatchArgs &args, const LaunchGeometry &geo,
+                        cudaStream_t stream) {
+  const bool cls8 = pd.clsMaxOffset < 256;
+  if (smemTable) {
+    if (pd.unitShift == 0)
+      return cls8 ? launch_slide<STYLE, SEARCH, true, 1, uint8_t>(pd, args, geo, stream)
+                  : launch_slide<STYLE, SEARCH, true, 1, uint16_t>(pd, args, geo, stream);
+    if (pd.unitShift == 1)
+      return cls8 ? launch_slide<STYLE, SEARCH, true, 2, uint8_t>(pd, args, geo, stream)
+                  : launch_slide<STYLE, SEARCH, true, 2, uint16_t>(pd, args, geo, stream);
+    return cudaErrorInvalidValue;
+  }
+  return cls8 ? launch_slide<STYLE, SEARCH, false, 0, uint8_t>(pd, args, geo, stream)
+              : launch_slide<STYLE, SEARCH, false, 0, uint16_t>(pd, args, geo, stream);
+}
+
+template <bool SEARCH>
+cudaError_t slide_style(const ProgramDev &pd, bool smemTable,
+                        const BatchArgs &args, int style,
+                        const LaunchGeometry &geo, cudaStream_t stream) {
+  switch (style) {
+  case STY_INSTANT: return slide_table<STY_INSTANT, SEARCH>(pd, smemTable, args, geo, stream);
+  case STY_FIRST:   return slide_table<STY_FIRST, SEARCH>(pd, smemTable, args, geo, stream);
+  case STY_TANGENT: return slide_table<STY_TANGENT, SEARCH>(pd, smemTable, args, geo, stream);
+  case STY_LAST:    return slide_table<STY_LAST, SEARCH>(pd, smemTable, args, geo, stream);
+  case STY_FULL:    return slide_table<STY_FULL, SEARCH>(pd, smemTable, args, geo, stream);
+  default:          return cudaErrorInvalidValue;
+  }
+}
+
+} // anonymous
+
+cudaError_t launch_batch_anchored(const ProgramDev &pd, bool smemTable,
+                                  const BatchArgs &args, int style,
+                                  const LaunchGeometry &geo,
+                                  const BatchTuning &tune, cudaStream_t stream,
+                                  int *launches) {
+  cudaError_t err = args.matchStarts
+      ? dispatch_style<true>(pd, smemTable, args, style, geo, tune, stream)
+      : dispatch_style<false>(pd, smemTable, args, style, geo, tune, stream);
+  if ((err == cudaSuccess) && launches && args.nLines)
+    *launches += 1;
+  return err;
+}
+
+cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
+                                 const BatchArgs &args, int style,
+                                 bool wantPositions,
+                                 const LaunchGeometry &geo,
+                                 cudaStream_t stream, int *launches) {
+  cudaError_t err = wantPositions
+      ? slide_style<true>(pd, smemTable, args, style, geo, stream)
+      : slide_style<false>(pd, smemTable, args, style, geo, stream);
+  if ((err == cudaSuccess) && launches && args.nLines)
+    *launches += 1;
+  return err;
+}
+
+} // namespace red_b200

@@ -1,0 +1,249 @@
+/* program.cpp - parse/validate a serialized RED program, build the GPU image.
+   See program.h for both layouts.  Host code only (no CUDA). */
+
+#include "program.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace red_b200 {
+
+namespace {
+
+template <class T> T loadLE(const uint8_t *p) {
+  T v;
+  memcpy(&v, p, sizeof(T));
+  return v;
+}
+
+uint64_t readValue(const uint8_t *p, uint32_t width) {
+  switch (width) {
+  case 1: return *p;
+  case 2: return loadLE<uint16_t>(p);
+  default: return loadLE<uint32_t>(p);
+  }
+}
+
+} // anonymous
+
+// FNV-1a (32 bit) of everything from the format byte on
+// (reference: calcChecksum, lib/Serializer.cpp:301; include/Fnv.h:45-63)
+uint32_t calc_checksum(const void *ptr, size_t len) {
+  const uint8_t *p = static_cast<const uint8_t *>(ptr);
+  uint32_t h = 0x811c9dc5u;
+  for (size_t ii = 12; ii < len; ++ii)
+    h = (h ^ p[ii]) * 0x01000193u;
+  return h;
+}
+
+// reference: checkHeader, lib/Serializer.cpp:270-298 (same order, same text)
+const char *check_header(const void *ptr, size_t len) {
+  if (!ptr || (len < kHeaderSize))
+    return "Serialized DFA: header too short";
+  const uint8_t *p = static_cast<const uint8_t *>(ptr);
+  if (memcmp(p, "REDA", 4) != 0)
+    return "Serialized DFA: bad magic number";
+  if ((loadLE<uint16_t>(p + 4) != 1) || (loadLE<uint16_t>(p + 6) != 0))
+    return "Serialized DFA: unrecognized version";
+  uint32_t stored = loadLE<uint32_t>(p + 8);
+  uint32_t actual = calc_checksum(ptr, len);
+  if (stored != actual) {
+    if (stored == __builtin_bswap32(actual))
+      return "serialized DFA: foreign endian-ness";
+    return "serialized DFA: checksum mismatch";
+  }
+  uint8_t fmt = p[12];
+  if ((fmt != 1) && (fmt != 2) && (fmt != 4))
+    return "Serialized DFA: unsupported format";
+  return nullptr;
+}
+
+bool parse_program(const void *ptr, size_t len, ParsedProgram &out,
+                   std::string &why) {
+  if (const char *msg = check_header(ptr, len)) {
+    why = msg;
+    return false;
+  }
+  const uint8_t *p = static_cast<const uint8_t *>(ptr);
+  out.format = p[12];
+  out.maxChar = p[13];
+  out.classCount = out.maxChar + 1;
+  out.leaderLen = p[14];
+  out.stateCount = loadLE<uint32_t>(p + 16);
+  uint32_t initialOff = loadLE<uint32_t>(p + 20);
+  uint32_t leaderOff = loadLE<uint32_t>(p + 24);
+  memcpy(out.equiv, p + 32, 256);
+
+  // The reference trusts the checksum; the GPU must never index out of
+  // bounds, so the structure is verified as well.
+  const size_t width = out.format;
+  const size_t rowVals = static_cast<size_t>(out.maxChar) + 2;
+  const size_t pad = (out.leaderLen + 7u) & ~7u;
+  const size_t need = kHeaderSize + pad +
+                      static_cast<size_t>(out.stateCount) * rowVals * width;
+  if (out.stateCount < 2) {
+    why = "serialized DFA: fewer than two states";
+    return false;
+  }
+  if (len < need) {
+    why = "serialized DFA: truncated state table";
+    return false;
+  }
+  for (int ii = 0; ii < 256; ++ii)
+    if (out.equiv[ii] > out.maxChar) {
+      why = "serialized DFA: class map exceeds maxChar";
+      return false;
+    }
+  out.leader.assign(p + kHeaderSize, p + kHeaderSize + out.leaderLen);
+  for (uint8_t c : out.leader)
+    if (c > out.maxChar) {
+      why = "serialized DFA: leader exceeds maxChar";
+      return false;
+    }
+
+  auto offToRow = [&](uint64_t off, uint32_t &row) {
+    if ((off % rowVals) != 0)
+      return false;
+    uint64_t r = off / rowVals;
+    if (r >= out.stateCount)
+      return false;
+    row = static_cast<uint32_t>(r);
+    return true;
+  };
+  if (!offToRow(initialOff, out.initialState) ||
+      !offToRow(leaderOff, out.leaderState)) {
+    why = "serialized DFA: initial/leader offset out of range";
+    return false;
+  }
+
+  const uint8_t *base = p + kHeaderSize + pad;
+  const uint32_t topBit = 8 * out.format - 1;
+  const uint64_t deadMask = 1ull << topBit;
+  const uint32_t C = out.classCount;
+  out.result.resize(out.stateCount);
+  out.deadEnd.resize(out.stateCount);
+  out.pureDead.resize(out.stateCount);
+  out.next.resize(static_cast<size_t>(out.stateCount) * C);
+  for (uint32_t st = 0; st < out.stateCount; ++st) {
+    const uint8_t *row = base + static_cast<size_t>(st) * rowVals * width;
+    uint64_t head = readValue(row, out.format);
+    out.result[st] = static_cast<int32_t>(head & (deadMask - 1));
+    out.deadEnd[st] = (head >> topBit) & 1;
+    out.pureDead[st] = (head == deadMask);
+    for (uint32_t c = 0; c < C; ++c) {
+      uint64_t off = readValue(row + (1 + c) * width, out.format);
+      uint32_t nx;
+      if (!offToRow(off, nx)) {
+        why = "serialized DFA: transition out of range";
+        return false;
+      }
+      out.next[static_cast<size_t>(st) * C + c] = nx;
+    }
+  }
+  return true;
+}
+
+void build_image(const ParsedProgram &pp, size_t smemBudget,
+                 DeviceImage &img) {
+  const uint32_t n = pp.stateCount;
+  const uint32_t C = pp.classCount;
+
+  // renumber: rejecting states, then accepting, then pure dead ends, so that
+  // the per-byte test for "nothing special happened" is one compare:
+  //   v < acceptV            ordinary rejecting state (the common case)
+  //   acceptV <= v < pureV   accepting
+  //   v >= pureV             pure dead end (reference: DfaProxy::pureDeadEnd)
+  std::vector<uint32_t> order;
+  order.reserve(n);
+  for (uint32_t st = 0; st < n; ++st)
+    if (!pp.pureDead[st] && (pp.result[st] <= 0))
+      order.push_back(st);
+  uint32_t firstAccept = static_cast<uint32_t>(order.size());
+  for (uint32_t st = 0; st < n; ++st)
+    if (!pp.pureDead[st] && (pp.result[st] > 0))
+      order.push_back(st);
+  uint32_t firstPure = static_cast<uint32_t>(order.size());
+  for (uint32_t st = 0; st < n; ++st)
+    if (pp.pureDead[st])
+      order.push_back(st);
+  img.acceptCount = firstPure - firstAccept;
+  img.pureCount = n - firstPure;
+  std::vector<uint32_t> oldToNew(n);
+  for (uint32_t ii = 0; ii < n; ++ii)
+    oldToNew[order[ii]] = ii;
+  img.newToOld = order;
+
+  img.stateCount = n;
+  img.classCount = C;
+  img.results.resize(n);
+  img.maxResult = 0;
+  for (uint32_t ii = 0; ii < n; ++ii) {
+    img.results[ii] = pp.result[order[ii]];
+    img.maxResult = std::max(img.maxResult, img.results[ii]);
+  }
+  img.initResult = pp.result[pp.initialState];
+  img.leader = pp.leader;
+
+  // The reference stops walking the moment it enters a pure dead end
+  // (Matcher.h:405, 478) and never looks at that row's exits.  Making those
+  // rows absorbing in the image is the same semantics, and lets a kernel step
+  // through them without a per-byte check.
+  auto absorbing = [&](uint32_t newIdx) { return newIdx >= firstPure; };
+
+  // smallest unit shift for which every v fits 16 bits
+  bool smem = false;
+  uint32_t shift = 0, vps = 0, stride = 0;
+  for (shift = 0; shift <= 8; ++shift) {
+    vps = (C + (1u << shift) - 1) >> shift;
+    stride = vps << shift;
+    uint64_t maxV = static_cast<uint64_t>(n) * vps;  // acceptV may equal n*vps
+    uint64_t bytes = static_cast<uint64_t>(n) * stride * 2;
+    if ((maxV <= 0xffff) && (bytes <= smemBudget)) {
+      smem = true;
+      break;
+    }
+    if (bytes > smemBudget)
+      break;
+  }
+
+  img.clsOffset.resize(256);
+  if (smem) {
+    img.mode = kTableSmemU16;
+    img.unitShift = shift;
+    img.vPerState = vps;
+    img.rowStride = stride;
+    img.table16.assign(static_cast<size_t>(n) * stride, 0);
+    for (uint32_t ii = 0; ii < n; ++ii) {
+      const uint32_t *src = &pp.next[static_cast<size_t>(order[ii]) * C];
+      uint16_t *dst = &img.table16[static_cast<size_t>(ii) * stride];
+      for (uint32_t c = 0; c < C; ++c)
+        dst[c] = static_cast<uint16_t>((absorbing(ii) ? ii : oldToNew[src[c]]) * vps);
+      // padding entries are never addressed (class < C); point them at self
+      for (uint32_t c = C; c < stride; ++c)
+        dst[c] = static_cast<uint16_t>(ii * vps);
+    }
+    for (int b = 0; b < 256; ++b)
+      img.clsOffset[b] = static_cast<uint16_t>(pp.equiv[b] * 2);
+  }
+  else {
+    img.mode = kTableGlobalU32;
+    img.unitShift = 0;
+    img.vPerState = C;
+    img.rowStride = C;
+    img.table32.resize(static_cast<size_t>(n) * C);
+    for (uint32_t ii = 0; ii < n; ++ii) {
+      const uint32_t *src = &pp.next[static_cast<size_t>(order[ii]) * C];
+      uint32_t *dst = &img.table32[static_cast<size_t>(ii) * C];
+      for (uint32_t c = 0; c < C; ++c)
+        dst[c] = (absorbing(ii) ? ii : oldToNew[src[c]]) * C;
+    }
+    for (int b = 0; b < 256; ++b)
+      img.clsOffset[b] = static_cast<uint16_t>(pp.equiv[b] * 4);
+  }
+  img.initV = oldToNew[pp.initialState] * img.vPerState;
+  img.leaderV = oldToNew[pp.leaderState] * img.vPerState;
+  img.pureV = firstPure * img.vPerState;
+  img.acceptV = firstAccept * img.vPerState;
+}
+
+} // namespace red_b200

@@ -1,0 +1,100 @@
+/* program.h - host-side view of a serialized RED program and the device image
+   built from it.
+
+   The serialized layout is the reference's REDA format
+   (reference: include/Serializer.h:42-77, lib/Executable.cpp:159-170):
+
+     bytes 0..3    "REDA"
+     4..5, 6..7    major (1), minor (0)
+     8..11         FNV-1a/32 of bytes 12..end
+     12            format: width in bytes of a table value (1, 2 or 4)
+     13            maxChar: largest byte-class number
+     14            leaderLen
+     16..19        stateCnt
+     20..23        initialOff   (in value units from the first row)
+     24..27        leaderOff
+     32..287       equivMap[256]: byte -> class
+     288..         leader, zero-padded to a multiple of 8
+     then          stateCnt rows of (maxChar + 2) values:
+                     [ result | deadEnd << topbit , next[0..maxChar] ]
+                   next[] are row offsets in value units.
+
+   The GPU does not walk that layout.  build_image() re-lays it out:
+
+     * states are renumbered  [ rejecting | accepting | pure dead ends ]
+       so that "did anything special happen" is one compare of the state
+       value against a threshold - no load of the row head per byte;
+     * the row head is dropped from the table; results live in a side array
+       that is read only when an accepting state is entered;
+     * a table entry holds the next state already multiplied into an entry
+       offset ("v"), so one step is   v = T[v * unit + class]  ;
+     * the class map is stored pre-scaled to byte offsets.
+ */
+
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace red_b200 {
+
+constexpr size_t kHeaderSize = 288;
+
+struct ParsedProgram {
+  uint32_t format = 0;      // 1, 2, 4
+  uint32_t maxChar = 0;
+  uint32_t classCount = 0;  // maxChar + 1
+  uint32_t leaderLen = 0;
+  uint32_t stateCount = 0;
+  uint32_t initialState = 0;  // row index
+  uint32_t leaderState = 0;   // row index
+  uint8_t equiv[256];
+  std::vector<uint8_t> leader;
+  std::vector<int32_t> result;     // per row
+  std::vector<uint8_t> deadEnd;    // per row (flag as serialized)
+  std::vector<uint8_t> pureDead;   // per row: head == 1 << topbit
+  std::vector<uint32_t> next;      // stateCount * classCount, row indices
+};
+
+// returns nullptr if fine, else the reference's complaint
+const char *check_header(const void *ptr, size_t len);
+uint32_t calc_checksum(const void *ptr, size_t len);
+
+// header check + structural validation; false with `why` set on failure
+bool parse_program(const void *ptr, size_t len, ParsedProgram &out,
+                   std::string &why);
+
+enum TableMode { kTableSmemU16 = 1, kTableGlobalU32 = 2 };
+
+struct DeviceImage {
+  TableMode mode = kTableSmemU16;
+  uint32_t stateCount = 0;
+  uint32_t classCount = 0;
+  uint32_t rowStride = 0;   // entries per row (>= classCount)
+  uint32_t unitShift = 0;   // entry index of a row = v << unitShift
+  uint32_t initV = 0;       // v of the initial state
+  uint32_t leaderV = 0;
+  uint32_t acceptV = 0;     // acceptV <= v < pureV -> accepting
+  uint32_t pureV = 0;       // v >= pureV -> pure dead end
+  uint32_t vPerState = 0;   // v = newIndex * vPerState
+  int32_t initResult = 0;
+  uint32_t acceptCount = 0;
+  uint32_t pureCount = 0;
+  int32_t maxResult = 0;
+  std::vector<uint16_t> clsOffset;   // 256: class * entryBytes
+  std::vector<uint16_t> table16;     // mode smem
+  std::vector<uint32_t> table32;     // mode global
+  std::vector<int32_t> results;      // by new index
+  std::vector<uint32_t> newToOld;    // new index -> serialized row
+  std::vector<uint8_t> leader;       // class space
+  size_t tableBytes() const {
+    return mode == kTableSmemU16 ? table16.size() * 2 : table32.size() * 4;
+  }
+};
+
+// smemBudget: bytes of shared memory the table may take
+void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img);
+
+} // namespace red_b200

@@ -1,0 +1,287 @@
+/* stream.cu - line index (split at a delimiter), order-preserving compaction
+   of matching lines, and the long-stream matcher.
+
+   Index and compaction are the same three-step shape, sized for HBM:
+     1. every warp counts the hits in its own contiguous segment,
+     2. one block turns the per-segment counts into exclusive offsets,
+     3. every warp walks its segment again and writes each hit at
+        offset + (ballot rank inside the warp).
+   Text is read twice, 16 bytes per lane, fully coalesced. */
+
+#include "stream.h"
+
+#include <vector>
+
+namespace red_b200 {
+
+namespace {
+
+constexpr int kScanThreads = 1024;
+constexpr uint32_t kSegBytes = 16384;  // text bytes per warp segment
+constexpr uint32_t kSegLines = 4096;   // results per warp segment
+
+__device__ __forceinline__ uint32_t match_mask16(const uint4 &q, uint32_t d4) {
+  // bit j set <=> byte j of the 16-byte block equals the delimiter
+  uint32_t m = 0;
+  uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t eq = __vcmpeq4(w[i], d4);  // 0xff per equal byte
+    // gather the top bit of each byte into 4 adjacent bits
+    uint32_t bits = ((eq & 0x80808080u) * 0x00204081u) >> 28;
+    m |= bits << (4 * i);
+  }
+  return m;
+}
+
+__global__ void count_delims_kernel(const uint8_t *text, uint64_t len,
+                                    uint32_t d4, uint32_t *segCounts,
+                                    uint64_t nSegs) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t seg = warp; seg < nSegs; seg += nWarps) {
+    const uint64_t base = seg * kSegBytes;
+    const uint64_t end = min(len, base + kSegBytes);
+    uint32_t cnt = 0;
+    for (uint64_t off = base + lane * 16; off < end; off += 512) {
+      uint4 q = __ldg(reinterpret_cast<const uint4 *>(text + off));
+      uint32_t m = match_mask16(q, d4);
+      if (off + 16 > end)
+        m &= (1u << (end - off)) - 1;
+      cnt += __popc(m);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0)
+      segCounts[seg] = cnt;
+  }
+}
+
+__global__ void count_matches_kernel(const int32_t *results, uint64_t n,
+                                     uint32_t *segCounts, uint64_t nSegs) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t seg = warp; seg < nSegs; seg += nWarps) {
+    const uint64_t base = seg * kSegLines;
+    const uint64_t end = min(n, base + kSegLines);
+    uint32_t cnt = 0;
+    for (uint64_t i = base + lane; i < end; i += 32)
+      cnt += (__ldg(results + i) > 0);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0)
+      segCounts[seg] = cnt;
+  }
+}
+
+/* exclusive scan of segCounts (u32) into segOffsets (u64); total to *total.
+   One block; each thread owns a contiguous run so the pass is two sweeps. */
+__global__ void __launch_bounds__(kScanThreads)
+scan_counts_kernel(const uint32_t *segCounts, uint64_t *segOffsets,
+                   uint64_t nSegs, uint64_t *total) {
+  __shared__ uint64_t partial[kScanThreads];
+  const uint64_t per = (nSegs + kScanThreads - 1) / kScanThreads;
+  const uint64_t lo = min(nSegs, per * threadIdx.x);
+  const uint64_t hi = min(nSegs, lo + per);
+  uint64_t sum = 0;
+  for (uint64_t i = lo; i < hi; ++i)
+    sum += segCounts[i];
+  partial[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis-Steele over 1024 partials
+  for (int d = 1; d < kScanThreads; d <<= 1) {
+    uint64_t add = (threadIdx.x >= d) ? partial[threadIdx.x - d] : 0;
+    __syncthreads();
+    partial[threadIdx.x] += add;
+    __syncthreads();
+  }
+  uint64_t run = partial[threadIdx.x] - sum;  // exclusive
+  for (uint64_t i = lo; i < hi; ++i) {
+    segOffsets[i] = run;
+    run += segCounts[i];
+  }
+  if (threadIdx.x == kScanThreads - 1)
+    *total = partial[kScanThreads - 1];
+}
+
+/* Delimiter number r (0-based) at position d ends line r and starts line r+1:
+     lens[r]     = low 32 bits of d      (fixed up to a length afterwards)
+     starts[r+1] = d + 1                 (if that line exists)            */
+__global__ void write_lines_kernel(const uint8_t *text, uint64_t len,
+                                   uint32_t d4, const uint64_t *segOffsets,
+                                   uint64_t nSegs, uint64_t nLines,
+                                   uint64_t *starts, uint32_t *lens) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t seg = warp; seg < nSegs; seg += nWarps) {
+    const uint64_t base = seg * kSegBytes;
+    const uint64_t end = min(len, base + kSegBytes);
+    uint64_t rank = segOffsets[seg];
+    for (uint64_t off0 = base; off0 < end; off0 += 512) {
+      const uint64_t off = off0 + lane * 16;
+      uint32_t m = 0;
+      if (off < end) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(text + off));
+        m = match_mask16(q, d4);
+        if (off + 16 > end)
+          m &= (1u << (end - off)) - 1;
+      }
+      uint32_t c = __popc(m);
+      // exclusive prefix of c across the warp
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+          incl += up;
+      }
+      uint64_t r = rank + (incl - c);
+      while (m) {
+        uint32_t j = __ffs(m) - 1;
+        m &= m - 1;
+        uint64_t d = off + j;
+        lens[r] = static_cast<uint32_t>(d);
+        if (r + 1 < nLines)
+          starts[r + 1] = d + 1;
+        ++r;
+      }
+      rank += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
+__global__ void finish_lines_kernel(uint64_t len, uint64_t nDelims,
+                                    uint64_t nLines, uint64_t *starts,
+                                    uint32_t *lens) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       i < nLines; i += stride) {
+    uint64_t s = (i == 0) ? 0 : starts[i];
+    if (i == 0)
+      starts[0] = 0;
+    uint32_t e = (i < nDelims) ? lens[i] : static_cast<uint32_t>(len);
+    lens[i] = e - static_cast<uint32_t>(s);
+  }
+}
+
+__global__ void write_matches_kernel(const int32_t *results, uint64_t n,
+                                     const uint64_t *segOffsets, uint64_t nSegs,
+                                     uint64_t *indices) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t seg = warp; seg < nSegs; seg += nWarps) {
+    const uint64_t base = seg * kSegLines;
+    const uint64_t end = min(n, base + kSegLines);
+    uint64_t rank = segOffsets[seg];
+    for (uint64_t i0 = base; i0 < end; i0 += 32) {
+      const uint64_t i = i0 + lane;
+      bool hit = (i < end) && (__ldg(results + i) > 0);
+      uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+      if (hit)
+        indices[rank + __popc(ballot & ((1u << lane) - 1))] = i;
+      rank += __popc(ballot);
+    }
+  }
+}
+
+struct Scratch {
+  uint32_t *counts = nullptr;
+  uint64_t *offsets = nullptr;
+  uint64_t *total = nullptr;
+  ~Scratch() {
+    cudaFree(counts);
+    cudaFree(offsets);
+    cudaFree(total);
+  }
+  cudaError_t alloc(uint64_t nSegs) {
+    cudaError_t e;
+    if ((e = cudaMalloc(&counts, nSegs * 4 + 4)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&offsets, nSegs * 8 + 8)) != cudaSuccess) return e;
+    return cudaMalloc(&total, 8);
+  }
+};
+
+int grid_for(uint64_t nSegs, int threads) {
+  uint64_t warpsPerBlock = threads / 32;
+  uint64_t blocks = (nSegs + warpsPerBlock - 1) / warpsPerBlock;
+  return static_cast<int>(std::min<uint64_t>(blocks, 148 * 8));
+}
+
+int cuda_why(cudaError_t e, const char *what, std::string &why) {
+  why = std::string(what) + ": " + cudaGetErrorString(e);
+  return RED_B200_ECUDA;
+}
+
+#define TRY(expr)                                  \
+  do {                                             \
+    cudaError_t e_ = (expr);                       \
+    if (e_ != cudaSuccess)                         \
+      return cuda_why(e_, #expr, why);             \
+  } while (0)
+
+} // anonymous
+
+int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
+                uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
+                uint64_t *nLinesOut, cudaStream_t stream, std::string &why) {
+  *nLinesOut = 0;
+  if (len == 0)
+    return RED_B200_OK;
+  if (reinterpret_cast<uintptr_t>(dText) & 15) {
+    why = "text must be 16-byte aligned";
+    return RED_B200_EAPI;
+  }
+  const uint64_t nSegs = (len + kSegBytes - 1) / kSegBytes;
+  const uint32_t d4 = delim * 0x01010101u;
+  Scratch sc;
+  TRY(sc.alloc(nSegs));
+  const int threads = 256;
+  const int grid = grid_for(nSegs, threads);
+  count_delims_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.counts, nSegs);
+  scan_counts_kernel<<<1, kScanThreads, 0, stream>>>(sc.counts, sc.offsets, nSegs, sc.total);
+  TRY(cudaGetLastError());
+  uint64_t nDelims = 0;
+  uint8_t last = 0;
+  TRY(cudaMemcpyAsync(&nDelims, sc.total, 8, cudaMemcpyDeviceToHost, stream));
+  TRY(cudaMemcpyAsync(&last, dText + len - 1, 1, cudaMemcpyDeviceToHost, stream));
+  TRY(cudaStreamSynchronize(stream));
+  const uint64_t nLines = nDelims + ((last != delim) ? 1 : 0);
+  if (nLines > capacity) {
+    why = "line index capacity too small";
+    *nLinesOut = nLines;
+    return RED_B200_ELIMIT;
+  }
+  write_lines_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.offsets, nSegs,
+                                                   nLines, dStarts, dLens);
+  finish_lines_kernel<<<148 * 4, 256, 0, stream>>>(len, nDelims, nLines, dStarts, dLens);
+  TRY(cudaGetLastError());
+  TRY(cudaStreamSynchronize(stream));
+  *nLinesOut = nLines;
+  return RED_B200_OK;
+}
+
+int compact_matches(const int32_t *dResults, uint64_t n, uint64_t *dIndices,
+                    uint64_t *dCount, cudaStream_t stream, std::string &why) {
+  if (n == 0) {
+    TRY(cudaMemsetAsync(dCount, 0, 8, stream));
+    return RED_B200_OK;
+  }
+  const uint64_t nSegs = (n + kSegLines - 1) / kSegLines;
+  uint32_t *counts = nullptr;
+  uint64_t *offsets = nullptr;
+  TRY(cudaMallocAsync(&counts, nSegs * 4 + 4, stream));
+  TRY(cudaMallocAsync(&offsets, nSegs * 8 + 8, stream));
+  const int threads = 256;
+  const int grid = grid_for(nSegs, threads);
+  count_matches_kernel<<<grid, threads, 0, stream>>>(dResults, n, counts, nSegs);
+  scan_counts_kernel<<<1, kScanThreads, 0, stream>>>(counts, offsets, nSegs, dCount);
+  write_matches_kernel<<<grid, threads, 0, stream>>>(dResults, n, offsets, nSegs, dIndices);
+  TRY(cudaGetLastError());
+  TRY(cudaFreeAsync(counts, stream));
+  TRY(cudaFreeAsync(offsets, stream));
+  return RED_B200_OK;
+}
+
+} // namespace red_b200
