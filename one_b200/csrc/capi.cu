@@ -253,6 +253,12 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.clsMaxOffset = *std::max_element(img.clsOffset.begin(), img.clsOffset.end());
   pd.initResult = img.initResult;
 
+  // cudaMemcpy from pageable memory may return before the DMA has landed, and
+  // the kernels run on non-blocking streams that do not order against the
+  // legacy default stream: make the upload visible before anyone can launch.
+  if ((err = cudaDeviceSynchronize()) != cudaSuccess)
+    return cleanup(err, "cudaDeviceSynchronize(upload)");
+
   // the host copies of the big tables are no longer needed
   std::vector<uint16_t>().swap(img.table16);
   std::vector<uint32_t>().swap(img.table32);

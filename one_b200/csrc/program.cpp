@@ -110,8 +110,12 @@ bool parse_program(const void *ptr, size_t len, ParsedProgram &out,
     row = static_cast<uint32_t>(r);
     return true;
   };
-  if (!offToRow(initialOff, out.initialState) ||
-      !offToRow(leaderOff, out.leaderState)) {
+  // initialOff_/leaderOff_ are BYTE offsets from the first row (they are fed
+  // to DfaProxy::init, Proxy.h:127), unlike the row entries, which are in
+  // value units (DfaProxy::trans multiplies by sizeof(Value), Proxy.h:143).
+  if ((initialOff % width) || (leaderOff % width) ||
+      !offToRow(initialOff / width, out.initialState) ||
+      !offToRow(leaderOff / width, out.leaderState)) {
     why = "serialized DFA: initial/leader offset out of range";
     return false;
   }

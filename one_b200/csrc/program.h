@@ -11,8 +11,8 @@
      13            maxChar: largest byte-class number
      14            leaderLen
      16..19        stateCnt
-     20..23        initialOff   (in value units from the first row)
-     24..27        leaderOff
+     20..23        initialOff   (BYTE offset of the initial row from the first row)
+     24..27        leaderOff    (BYTE offset of the row reached after the leader)
      32..287       equivMap[256]: byte -> class
      288..         leader, zero-padded to a multiple of 8
      then          stateCnt rows of (maxChar + 2) values:

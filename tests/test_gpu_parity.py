@@ -1,0 +1,212 @@
+"""Parity of the CUDA path against the oracle, through the C ABI.  GPU only.
+
+Bit-exact: per line result id, match start and match end, for every verb and
+style, on the reference's golden vectors and on seeded synthetic corpora."""
+
+import numpy as np
+import pytest
+
+from conftest import unb64, unz
+
+pytestmark = pytest.mark.gpu
+
+VERBS = ["check", "match", "scan", "search"]
+STYLES = ["instant", "first", "tangent", "last", "full"]
+
+
+def pack(texts, sep=b"\n", lead=b""):
+    blob = lead + sep.join(texts) + sep
+    lens = np.array([len(t) for t in texts], dtype=np.uint32)
+    starts = np.zeros(len(texts), dtype=np.uint64)
+    pos = len(lead)
+    for i, t in enumerate(texts):
+        starts[i] = pos
+        pos += len(t) + len(sep)
+    return np.frombuffer(blob, dtype=np.uint8), starts, lens
+
+
+def triple(res, ms, me):
+    return [[int(a), int(b), int(c)] for a, b, c in zip(res, ms, me)]
+
+
+def test_known_answers_from_reference_tests(gpu_red, kat):
+    n = 0
+    for case in kat["matcher_cpp"]:
+        prog = gpu_red.Program(unz(case["program"]))
+        for verb, style, text, exp in case["rows"]:
+            got = prog.run(unb64(text), verb, style)
+            for k in range(3):
+                if exp[k] is not None:
+                    assert got[k] == exp[k], (case["rules"], verb, style, unb64(text), exp, got)
+            n += 1
+        prog.close()
+    assert n > 500
+
+
+def test_omnibus_known_answers(gpu_red, kat):
+    for rec in kat["omnibus_cpp"]:
+        if rec["program"] is None:
+            continue
+        prog = gpu_red.Program(unz(rec["program"]))
+        text = unb64(rec["text"])
+        res = prog.check(text, "full")
+        assert res == prog.match(text, "full").result
+        assert (res == 1) == rec["match"], (unb64(rec["regex"]), text)
+        prog.close()
+
+
+def test_reference_vectors_all_verbs_styles(gpu_red, vectors):
+    for case in vectors["cases"]:
+        prog = gpu_red.Program(unz(case["program"]))
+        texts = [unb64(t) for t in case["texts"]]
+        # odd lead-in so that line starts hit every alignment
+        text, starts, lens = pack(texts, lead=b"#" * 3)
+        for verb in VERBS:
+            for sty in STYLES:
+                res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+                assert triple(res, ms, me) == case["expected"][verb][sty], (case["name"], verb, sty)
+        prog.close()
+
+
+@pytest.mark.parametrize("name", ["single_auto", "union64", "keywords300"])
+def test_synthetic_corpus_vs_oracle(gpu_red, vectors, oracle_cls, name):
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == name)
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(60000, seed=42)
+    for verb in ("check", "match"):
+        for sty in STYLES:
+            res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+            eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+            assert np.array_equal(res, eres), (verb, sty)
+            assert np.array_equal(ms, ems) and np.array_equal(me, eme), (verb, sty)
+    if name != "keywords300":  # random keywords do not occur in syslog text
+        assert (eres > 0).any()
+    # sliding verbs on a slice (quadratic in the reference, too)
+    sl = slice(0, 4000)
+    for verb in ("scan", "search"):
+        for sty in ("instant", "last"):
+            res, ms, me = prog.match_batch_host(text, starts[sl], lens[sl], verb, sty)
+            eres, ems, eme = orc.batch(text, starts[sl], lens[sl], verb, sty)
+            assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme)
+    prog.close()
+
+
+def test_simple_walk_variant_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
+    """The per-byte-decision kernel (A/B baseline) gives the same answers."""
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    monkeypatch.setenv("RED_B200_SIMPLE_WALK", "1")
+    prog = gpu_red.Program(blob)
+    monkeypatch.delenv("RED_B200_SIMPLE_WALK")
+    orc = oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(20000, seed=3)
+    for sty in STYLES:
+        res, ms, me = prog.match_batch_host(text, starts, lens, "match", sty)
+        eres, ems, eme = orc.batch(text, starts, lens, "match", sty)
+        assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme)
+    prog.close()
+
+
+def test_global_table_path_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Force the L2/global-table kernels on a DFA that would fit shared memory."""
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    monkeypatch.setenv("RED_B200_SMEM_TABLE_LIMIT", "1024")
+    prog = gpu_red.Program(blob)
+    monkeypatch.delenv("RED_B200_SMEM_TABLE_LIMIT")
+    assert prog.info["table_mode"] == 2
+    orc = oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(20000, seed=4)
+    for verb in VERBS:
+        for sty in ("first", "last"):
+            n = 20000 if verb in ("check", "match") else 2000
+            res, ms, me = prog.match_batch_host(text, starts[:n], lens[:n], verb, sty)
+            eres, ems, eme = orc.batch(text, starts[:n], lens[:n], verb, sty)
+            assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme)
+    prog.close()
+
+
+def test_edge_cases_ragged_and_empty(gpu_red, vectors, oracle_cls):
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    rng = np.random.RandomState(11)
+    phrase = b"Failed password for"
+    texts = [b"", b"", b"x", phrase, phrase[:-1], b" " * 15 + phrase, b" " * 16 + phrase, b" " * 17 + phrase]
+    for ln in list(range(0, 70)) + [255, 256, 257, 1000, 4097, 70000]:
+        body = bytes(rng.choice(list(b"abcdefghij klmnop=:"), size=ln).astype(np.uint8))
+        texts.append(body)
+        if ln > 25:
+            k = rng.randint(0, ln - 20)
+            texts.append(body[:k] + phrase + body[k + len(phrase):])
+    # no separator at all: lines abut, starts unaligned
+    text, starts, lens = pack(texts, sep=b"")
+    for verb in ("check", "match"):
+        for sty in STYLES:
+            res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+            eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+            assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), (verb, sty)
+    # zero lines
+    res, ms, me = prog.match_batch_host(text, starts[:0], lens[:0], "match", "last")
+    assert len(res) == 0
+    # lines out of text order and overlapping views
+    perm = rng.permutation(len(texts))
+    res, ms, me = prog.match_batch_host(text, starts[perm], lens[perm], "match", "last")
+    eres, ems, eme = orc.batch(text, starts[perm], lens[perm], "match", "last")
+    assert np.array_equal(res, eres) and np.array_equal(me, eme)
+    prog.close()
+
+
+def test_device_resident_batch_and_compaction(gpu_red, vectors, oracle_cls):
+    import torch
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(50000, seed=8)
+    dt = torch.from_numpy(text.copy()).cuda()
+    ds = torch.from_numpy(starts.astype(np.int64)).cuda()
+    dl = torch.from_numpy(lens.astype(np.int32)).cuda()
+    res, ms, me = prog.match_batch_device(dt, ds, dl, "match", "instant", want_starts=True, want_ends=True)
+    torch.cuda.synchronize()
+    eres, ems, eme = orc.batch(text, starts, lens, "match", "instant")
+    assert np.array_equal(res.cpu().numpy(), eres)
+    assert np.array_equal(ms.cpu().numpy().astype(np.uint32), ems)
+    assert np.array_equal(me.cpu().numpy().astype(np.uint32), eme)
+    idx = gpu_red.compact_matches_device(res)
+    assert np.array_equal(idx.cpu().numpy(), np.nonzero(eres > 0)[0])
+    # the line index built on the GPU equals the one the generator made
+    gs, gl = gpu_red.split_lines_device(dt)
+    assert np.array_equal(gs.cpu().numpy().astype(np.uint64), starts)
+    assert np.array_equal(gl.cpu().numpy().astype(np.uint32), lens)
+    prog.close()
+
+
+def test_split_lines_edge_cases(gpu_red):
+    import torch
+    for raw in [b"", b"\n", b"a", b"a\n", b"\n\n", b"ab\ncd", b"ab\n\ncd\n", b"x" * 40000 + b"\n" + b"y" * 33]:
+        t = torch.frombuffer(bytearray(raw + b"\0" * 16), dtype=torch.uint8)[:len(raw)].cuda() if raw else \
+            torch.empty(0, dtype=torch.uint8, device="cuda")
+        gs, gl = gpu_red.split_lines_device(t)
+        parts = raw.split(b"\n")
+        if raw.endswith(b"\n") or raw == b"":
+            parts = parts[:-1]
+        exp_lens = [len(p) for p in parts]
+        exp_starts = list(np.cumsum([0] + [n + 1 for n in exp_lens[:-1]])) if parts else []
+        assert gl.cpu().tolist() == exp_lens, raw[:20]
+        assert gs.cpu().tolist() == exp_starts, raw[:20]
+
+
+def test_style_and_verb_errors(gpu_red, vectors):
+    prog = gpu_red.Program(unz(vectors["cases"][0]["program"]))
+    with pytest.raises(gpu_red.RedExceptExec):
+        prog.run(b"abc", 1, 0)   # styInvalid
+    with pytest.raises(gpu_red.RedExceptExec):
+        prog.run(b"abc", 1, 6)
+    with pytest.raises(gpu_red.RedExceptExec):
+        prog.run(b"abc", 9, 4)
+    prog.close()
