@@ -25,7 +25,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wextra",
 def sources():
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp"))
                   + glob.glob(os.path.join(CSRC, "compile", "*.cpp")))
-    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "compile", "*.h"))
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "compile", "*.h"))
                   + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     return srcs, hdrs
 

@@ -26,6 +26,8 @@ using namespace red_b200;
 
 namespace {
 
+constexpr unsigned kCounters = 256;
+
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) {
@@ -85,6 +87,8 @@ struct red_b200_program {
   void *dCls = nullptr;
   void *dResults = nullptr;
   void *dLeader = nullptr;
+  unsigned long long *dCounters = nullptr;  // kCounters block counters, used round-robin
+  unsigned nextCounter = 0;
   BatchTuning tune;
   std::mutex mu;        // guards the lazily created host pipeline
   struct HostPipe *pipe = nullptr;
@@ -189,7 +193,8 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   size_t budget = prop.sharedMemPerBlockOptin - 1024;
   if (const char *env = getenv("RED_B200_SMEM_TABLE_LIMIT"))
     budget = std::min<size_t>(budget, strtoull(env, nullptr, 0));
-  build_image(prog->parsed, budget, prog->img);
+  build_image(prog->parsed, budget, prog->img,
+              getenv("RED_B200_NO_BYTE_ROWS") == nullptr);
   DeviceImage &img = prog->img;
   prog->smemTable = (img.mode == kTableSmemU16);
   prog->format = prog->parsed.format;
@@ -204,7 +209,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
 
   auto cleanup = [&](cudaError_t e, const char *what) {
     cudaFree(prog->dTable); cudaFree(prog->dCls); cudaFree(prog->dResults);
-    cudaFree(prog->dLeader);
+    cudaFree(prog->dLeader); cudaFree(prog->dCounters);
     delete prog;
     return cuda_fail(e, what);
   };
@@ -225,20 +230,24 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     return cleanup(err, "cudaMemcpy(results)");
 
   {
-    // the leader in the same pre-scaled class space as clsOffset
-    std::vector<uint16_t> lead(std::max<size_t>(1, img.leader.size()), 0);
-    uint32_t entryBytes = prog->smemTable ? 2 : 4;
+    // raw class map (256 bytes) followed by the leader (classes)
+    std::vector<uint8_t> aux(256 + std::max<size_t>(1, img.leader.size()), 0);
+    memcpy(aux.data(), prog->parsed.equiv, 256);
     for (size_t ii = 0; ii < img.leader.size(); ++ii)
-      lead[ii] = static_cast<uint16_t>(img.leader[ii] * entryBytes);
-    if ((err = cudaMalloc(&prog->dLeader, lead.size() * 2)) != cudaSuccess)
+      aux[256 + ii] = img.leader[ii];
+    if ((err = cudaMalloc(&prog->dLeader, aux.size())) != cudaSuccess)
       return cleanup(err, "cudaMalloc(leader)");
-    if ((err = cudaMemcpy(prog->dLeader, lead.data(), lead.size() * 2,
+    if ((err = cudaMemcpy(prog->dLeader, aux.data(), aux.size(),
                           cudaMemcpyHostToDevice)) != cudaSuccess)
       return cleanup(err, "cudaMemcpy(leader)");
   }
 
+  if ((err = cudaMalloc(&prog->dCounters, kCounters * sizeof(unsigned long long))) != cudaSuccess)
+    return cleanup(err, "cudaMalloc(counters)");
+
   ProgramDev &pd = prog->dev;
-  pd.leader = static_cast<const uint16_t *>(prog->dLeader);
+  pd.equiv = static_cast<const uint8_t *>(prog->dLeader);
+  pd.leader = pd.equiv + 256;
   pd.leaderLen = static_cast<uint32_t>(img.leader.size());
   pd.leaderV = img.leaderV;
   pd.clsOffset = static_cast<const uint16_t *>(prog->dCls);
@@ -248,10 +257,22 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.unitShift = img.unitShift;
   pd.initV = img.initV;
   pd.acceptV = img.acceptV;
+  pd.absV = img.absV;
   pd.pureV = img.pureV;
   pd.vPerState = img.vPerState;
+  {
+    // reciprocal for v / vPerState, kept only if exact over the whole v range
+    const uint64_t d = img.vPerState;
+    const uint64_t maxV = static_cast<uint64_t>(img.stateCount) * d;
+    uint64_t magic = (1ull << 32) / d + 1;
+    bool exact = (magic <= 0xffffffffull) && (maxV <= (1ull << 20));
+    for (uint64_t v = 0; exact && (v < maxV); ++v)
+      exact = ((v * magic) >> 32) == v / d;
+    pd.divMagic = exact ? static_cast<uint32_t>(magic) : 0;
+  }
   pd.clsMaxOffset = *std::max_element(img.clsOffset.begin(), img.clsOffset.end());
   pd.initResult = img.initResult;
+  pd.byteRows = img.byteRows ? 1 : 0;
 
   // cudaMemcpy from pageable memory may return before the DMA has landed, and
   // the kernels run on non-blocking streams that do not order against the
@@ -268,6 +289,10 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     prog->tune.threads = atoi(env);
   if (const char *env = getenv("RED_B200_CTAS_PER_SM"))
     prog->tune.ctasPerSm = atoi(env);
+  if (const char *env = getenv("RED_B200_VARIANT"))
+    prog->tune.variant = atoi(env);
+  if (const char *env = getenv("RED_B200_LINES_PER_LANE"))
+    prog->tune.linesPerLane = atoi(env);
   if (const char *env = getenv("RED_B200_SIMPLE_WALK"))
     prog->tune.simpleWalk = atoi(env) != 0;
 
@@ -287,6 +312,7 @@ void red_b200_program_free(red_b200_program *prog) {
   cudaFree(prog->dCls);
   cudaFree(prog->dResults);
   cudaFree(prog->dLeader);
+  cudaFree(prog->dCounters);
   delete prog;
 }
 
@@ -324,8 +350,16 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
   if ((verb == RED_B200_VERB_CHECK) || (verb == RED_B200_VERB_MATCH)) {
     BatchArgs a = args;
     a.checkLeader = (verb == RED_B200_VERB_CHECK) && (prog->dev.leaderLen > 0);
-    err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
-                                prog->geo, prog->tune, stream, &launches);
+    if (prog->tune.variant == 1)
+      err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
+                                  prog->geo, prog->tune, stream, &launches);
+    else {
+      // every launch gets its own block counter: launches of one program may
+      // overlap on different streams (the host pipeline does that)
+      unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
+      err = launch_batch_lanes(prog->dev, prog->smemTable, a, style, prog->geo,
+                               prog->tune, ctr, stream, &launches);
+    }
   }
   else
     err = launch_batch_sliding(prog->dev, prog->smemTable, args, style,

@@ -13,17 +13,21 @@ struct ProgramDev {
   const uint16_t *clsOffset;  // [256] byte -> class * entryBytes
   const void *table;          // u16 (smem mode) or u32 (global mode) entries
   const int32_t *results;     // [stateCount], by renumbered state index
-  const uint16_t *leader;     // [leaderLen] required prefix, as class offsets
+  const uint8_t *equiv;       // [256] byte -> class (as serialized)
+  const uint8_t *leader;      // [leaderLen] required prefix, as classes
   uint32_t leaderLen;
   uint32_t leaderV;           // state reached after the leader
   uint32_t tableBytes;
   uint32_t unitShift;   // smem mode: row entry index = v << unitShift
   uint32_t initV;
   uint32_t acceptV;     // acceptV <= v < pureV : accepting
+  uint32_t absV;        // absV <= v < pureV   : accepting, can never be left
   uint32_t pureV;       // v >= pureV          : pure dead end
   uint32_t vPerState;
+  uint32_t divMagic;    // 0, or M with (v * M) >> 32 == v / vPerState for all v
   uint32_t clsMaxOffset;  // largest value in clsOffset
   int32_t initResult;
+  uint32_t byteRows;    // 1: 256-column rows indexed by the raw byte (unitShift 8)
 };
 
 struct BatchArgs {
@@ -47,6 +51,8 @@ struct BatchTuning {
   int threads = 0;      // 0 = pick
   int ctasPerSm = 0;    // 0 = pick
   bool simpleWalk = false;  // per-byte decisions only (A/B baseline)
+  int variant = 0;      // 0 = persistent lanes (production), 1 = tile per CTA (v1)
+  int linesPerLane = 0; // persistent lanes: lines per lane per claimed block (0 = pick)
 };
 
 // verbs check/match (anchored walk).  smemTable selects the table mode.
@@ -55,6 +61,15 @@ cudaError_t launch_batch_anchored(const ProgramDev &pd, bool smemTable,
                                   const LaunchGeometry &geo,
                                   const BatchTuning &tune, cudaStream_t stream,
                                   int *launches);
+
+// verbs check/match, persistent lanes (kernels_lanes.cu): the production path.
+// `counter` is a zeroable device word used to hand out blocks of lines.
+cudaError_t launch_batch_lanes(const ProgramDev &pd, bool smemTable,
+                               const BatchArgs &args, int style,
+                               const LaunchGeometry &geo,
+                               const BatchTuning &tune,
+                               unsigned long long *counter,
+                               cudaStream_t stream, int *launches);
 
 // verbs scan/search (sliding start position)
 cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,

@@ -20,6 +20,7 @@
  */
 
 #include "device_program.h"
+#include "walk.cuh"
 
 #include <algorithm>
 
@@ -27,110 +28,7 @@ namespace red_b200 {
 
 namespace {
 
-constexpr uint32_t kNone = 0xffffffffu;
-constexpr int kMaxThreads = 1024;
-
-enum { STY_INSTANT = 1, STY_FIRST = 2, STY_TANGENT = 3, STY_LAST = 4,
-       STY_FULL = 5 };
-
-// ---- table accessors ------------------------------------------------------
-
-// u16 entries in shared memory; K = unitShift + 1 (byte offset of row = v<<K)
-template <int K> struct SmemTable {
-  const unsigned char *base;
-  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
-    return *reinterpret_cast<const uint16_t *>(base + ((v << K) + co));
-  }
-};
-
-// u32 entries in global memory (L1/L2 resident); byte offset of row = v * 4
-struct GlobalTable {
-  const unsigned char *base;
-  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
-    return __ldg(reinterpret_cast<const uint32_t *>(
-        base + ((static_cast<size_t>(v) << 2) + co)));
-  }
-};
-
-// ---- the walk -------------------------------------------------------------
-
-template <int STYLE, bool WANT_START> struct Walk {
-  uint32_t v;       // current state
-  uint32_t limit;   // states >= limit need a decision
-  uint32_t accV;    // last accepting state seen (kNone: none)
-  uint32_t mstart;  // where the initial state was last left
-  uint32_t mend;    // one past the last accepting position
-
-  __device__ __forceinline__ void begin(const ProgramDev &pd) {
-    v = pd.initV;
-    // a Full walk only ever has to notice pure dead ends (to stop early)
-    limit = (STYLE == STY_FULL) ? pd.pureV : pd.acceptV;
-    accV = kNone;
-    mstart = 0;
-    mend = 0;
-  }
-
-  // out-of-line part of a step; true = the walk is over
-  __device__ __forceinline__ bool special(const ProgramDev &pd, uint32_t pos) {
-    if (v >= pd.pureV)
-      return true;  // pure dead end: Matcher.h:405/478
-    if (STYLE == STY_FULL)
-      return false;
-    if (v >= pd.acceptV) {
-      if (STYLE == STY_FIRST) {
-        // stop when the result changes (Matcher.h:455-460)
-        if ((accV != kNone) && (v != accV) &&
-            (pd.results[v / pd.vPerState] != pd.results[accV / pd.vPerState]))
-          return true;
-      }
-      accV = v;
-      mend = pos + 1;
-      if (STYLE == STY_INSTANT)
-        return true;
-      if ((STYLE == STY_FIRST) || (STYLE == STY_TANGENT))
-        limit = 0;  // from now on the first rejecting state ends the walk
-      return false;
-    }
-    // ordinary rejecting state after an accept (First/Tangent only)
-    return true;
-  }
-
-  template <class Tab>
-  __device__ __forceinline__ bool step(const ProgramDev &pd, const Tab &tab,
-                                       uint32_t co, uint32_t pos) {
-    uint32_t nv = tab.next(v, co);
-    if (WANT_START) {
-      if ((v == pd.initV) && (nv != pd.initV))
-        mstart = pos;
-    }
-    v = nv;
-    if (v >= limit)
-      return special(pd, pos);
-    return false;
-  }
-
-  __device__ __forceinline__ void finish(const ProgramDev &pd, uint32_t len,
-                                         int32_t &result, uint32_t &start,
-                                         uint32_t &end) const {
-    int32_t cur = ((v >= pd.acceptV) && (v < pd.pureV))
-                      ? pd.results[v / pd.vPerState] : 0;
-    int32_t prev = 0;
-    if ((STYLE != STY_FULL) && (STYLE != STY_INSTANT) && (accV != kNone))
-      prev = pd.results[accV / pd.vPerState];
-    result = (prev > 0) ? prev : cur;
-    uint32_t e = (STYLE == STY_FULL) ? len : mend;
-    start = (result > 0) ? mstart : 0;
-    end = (result > 0) ? e : 0;
-  }
-};
-
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int j) {
-  return __byte_perm(w, 0, 0x4440 | j);
-}
-
-__device__ __forceinline__ uint32_t word_of(const uint4 &q, int i) {
-  return (i == 0) ? q.x : (i == 1) ? q.y : (i == 2) ? q.z : q.w;
-}
+using namespace dev;
 
 /* One line, anchored.  p need not be aligned: the walk reads the aligned
    16-byte blocks that cover [p, p+len) and skips the bytes outside.  The
@@ -209,31 +107,6 @@ done:
   wk.finish(pd, len, result, start, end);
 }
 
-// ---- kernels --------------------------------------------------------------
-
-/* Shared memory layout (dynamic):
-     [0, 512)            class table: u8 (pre-scaled offsets < 256) or u16
-     [512, 512 + bytes)  transition table (smem mode only)                 */
-constexpr uint32_t kClsBytes = 512;
-
-template <class ClsT>
-__device__ __forceinline__ void stage_classes(const ProgramDev &pd,
-                                              unsigned char *smem) {
-  ClsT *cls = reinterpret_cast<ClsT *>(smem);
-  for (int ii = threadIdx.x; ii < 256; ii += blockDim.x)
-    cls[ii] = static_cast<ClsT>(pd.clsOffset[ii]);
-}
-
-__device__ __forceinline__ void stage_table(const ProgramDev &pd,
-                                            unsigned char *dst) {
-  // tableBytes is padded to a multiple of 16 by the uploader
-  const uint4 *src = reinterpret_cast<const uint4 *>(pd.table);
-  uint4 *d = reinterpret_cast<uint4 *>(dst);
-  const uint32_t n = pd.tableBytes >> 4;
-  for (uint32_t ii = threadIdx.x; ii < n; ii += blockDim.x)
-    d[ii] = __ldg(src + ii);
-}
-
 template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool FAST>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 batch_anchored_kernel(const ProgramDev pd, const BatchArgs args) {
@@ -263,7 +136,7 @@ batch_anchored_kernel(const ProgramDev pd, const BatchArgs args) {
          state reached exactly at the end of the leader is not noticed until
          the next byte has been consumed. */
       for (uint32_t ii = 0; ii < pd.leaderLen; ++ii)
-        if ((ii >= len) || (pd.leader[ii] != cls[__ldg(p + ii)])) {
+        if ((ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + ii)])) {
           viable = false;
           break;
         }
@@ -326,6 +199,8 @@ cudaError_t dispatch_table(const ProgramDev &pd, bool smemTable,
     if (pd.unitShift == 1)
       return cls8 ? launch_one<STYLE, WANT_START, true, 2, uint8_t>(pd, args, geo, tune, stream)
                   : launch_one<STYLE, WANT_START, true, 2, uint16_t>(pd, args, geo, tune, stream);
+    if (pd.unitShift == 8)  // byte-indexed rows
+      return launch_one<STYLE, WANT_START, true, 9, uint16_t>(pd, args, geo, tune, stream);
     return cudaErrorInvalidValue;
   }
   return cls8 ? launch_one<STYLE, WANT_START, false, 0, uint8_t>(pd, args, geo, tune, stream)
@@ -379,7 +254,7 @@ slide_line(const ProgramDev &pd, const Tab &tab, const ClsT *cls,
       bool ok = true;
       uint32_t ii = 0;
       for (; ii < pd.leaderLen; ++ii) {
-        if ((pos + ii >= len) || (pd.leader[ii] != cls[__ldg(p + pos + ii)])) {
+        if ((pos + ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + pos + ii)])) {
           ok = false;
           break;
         }
@@ -471,6 +346,8 @@ cudaError_t slide_table(const ProgramDev &pd, bool smemTable,
     if (pd.unitShift == 1)
       return cls8 ? launch_slide<STYLE, SEARCH, true, 2, uint8_t>(pd, args, geo, stream)
                   : launch_slide<STYLE, SEARCH, true, 2, uint16_t>(pd, args, geo, stream);
+    if (pd.unitShift == 8)
+      return launch_slide<STYLE, SEARCH, true, 9, uint16_t>(pd, args, geo, stream);
     return cudaErrorInvalidValue;
   }
   return cls8 ? launch_slide<STYLE, SEARCH, false, 0, uint8_t>(pd, args, geo, stream)

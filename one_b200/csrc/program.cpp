@@ -148,23 +148,36 @@ bool parse_program(const void *ptr, size_t len, ParsedProgram &out,
 }
 
 void build_image(const ParsedProgram &pp, size_t smemBudget,
-                 DeviceImage &img) {
+                 DeviceImage &img, bool allowByteRows) {
   const uint32_t n = pp.stateCount;
   const uint32_t C = pp.classCount;
 
   // renumber: rejecting states, then accepting, then pure dead ends, so that
   // the per-byte test for "nothing special happened" is one compare:
   //   v < acceptV            ordinary rejecting state (the common case)
-  //   acceptV <= v < pureV   accepting
+  //   acceptV <= v < pureV   accepting (absV <= v: and can never be left)
   //   v >= pureV             pure dead end (reference: DfaProxy::pureDeadEnd)
   std::vector<uint32_t> order;
   order.reserve(n);
   for (uint32_t st = 0; st < n; ++st)
     if (!pp.pureDead[st] && (pp.result[st] <= 0))
       order.push_back(st);
+  // An accepting state all of whose transitions lead back to itself (the tail
+  // of a pattern with a loose end, ".*foo.*") can never be left: once there,
+  // the outcome of every style is known without reading the rest of the line.
+  auto selfLoop = [&](uint32_t st) {
+    for (uint32_t c = 0; c < C; ++c)
+      if (pp.next[static_cast<size_t>(st) * C + c] != st)
+        return false;
+    return true;
+  };
   uint32_t firstAccept = static_cast<uint32_t>(order.size());
   for (uint32_t st = 0; st < n; ++st)
-    if (!pp.pureDead[st] && (pp.result[st] > 0))
+    if (!pp.pureDead[st] && (pp.result[st] > 0) && !selfLoop(st))
+      order.push_back(st);
+  uint32_t firstAbsorb = static_cast<uint32_t>(order.size());
+  for (uint32_t st = 0; st < n; ++st)
+    if (!pp.pureDead[st] && (pp.result[st] > 0) && selfLoop(st))
       order.push_back(st);
   uint32_t firstPure = static_cast<uint32_t>(order.size());
   for (uint32_t st = 0; st < n; ++st)
@@ -194,10 +207,16 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   // through them without a per-byte check.
   auto absorbing = [&](uint32_t newIdx) { return newIdx >= firstPure; };
 
-  // smallest unit shift for which every v fits 16 bits
+  // Small DFAs: rows of 256 entries indexed by the raw byte, so that a step
+  // is ONE shared-memory load (no class lookup).  v is the state index.
+  const bool byteRows = allowByteRows &&
+                        (static_cast<uint64_t>(n) * 256 * 2 <= smemBudget) &&
+                        (n <= 0xffff);
+
+  // otherwise: smallest unit shift for which every v fits 16 bits
   bool smem = false;
   uint32_t shift = 0, vps = 0, stride = 0;
-  for (shift = 0; shift <= 8; ++shift) {
+  for (shift = 0; !byteRows && (shift <= 1); ++shift) {
     vps = (C + (1u << shift) - 1) >> shift;
     stride = vps << shift;
     uint64_t maxV = static_cast<uint64_t>(n) * vps;  // acceptV may equal n*vps
@@ -211,7 +230,23 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   }
 
   img.clsOffset.resize(256);
-  if (smem) {
+  img.byteRows = byteRows;
+  if (byteRows) {
+    img.mode = kTableSmemU16;
+    img.unitShift = 8;
+    img.vPerState = 1;
+    img.rowStride = 256;
+    img.table16.assign(static_cast<size_t>(n) * 256, 0);
+    for (uint32_t ii = 0; ii < n; ++ii) {
+      const uint32_t *src = &pp.next[static_cast<size_t>(order[ii]) * C];
+      uint16_t *dst = &img.table16[static_cast<size_t>(ii) * 256];
+      for (uint32_t b = 0; b < 256; ++b)
+        dst[b] = static_cast<uint16_t>(absorbing(ii) ? ii : oldToNew[src[pp.equiv[b]]]);
+    }
+    for (int b = 0; b < 256; ++b)
+      img.clsOffset[b] = static_cast<uint16_t>(b * 2);  // identity "classes"
+  }
+  else if (smem) {
     img.mode = kTableSmemU16;
     img.unitShift = shift;
     img.vPerState = vps;
@@ -248,6 +283,7 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   img.leaderV = oldToNew[pp.leaderState] * img.vPerState;
   img.pureV = firstPure * img.vPerState;
   img.acceptV = firstAccept * img.vPerState;
+  img.absV = firstAbsorb * img.vPerState;
 }
 
 } // namespace red_b200

@@ -77,12 +77,14 @@ struct DeviceImage {
   uint32_t initV = 0;       // v of the initial state
   uint32_t leaderV = 0;
   uint32_t acceptV = 0;     // acceptV <= v < pureV -> accepting
+  uint32_t absV = 0;        // absV <= v < pureV -> accepting and absorbing
   uint32_t pureV = 0;       // v >= pureV -> pure dead end
   uint32_t vPerState = 0;   // v = newIndex * vPerState
   int32_t initResult = 0;
   uint32_t acceptCount = 0;
   uint32_t pureCount = 0;
   int32_t maxResult = 0;
+  bool byteRows = false;    // rows indexed by the raw byte (256 columns), identity class map
   std::vector<uint16_t> clsOffset;   // 256: class * entryBytes
   std::vector<uint16_t> table16;     // mode smem
   std::vector<uint32_t> table32;     // mode global
@@ -95,6 +97,7 @@ struct DeviceImage {
 };
 
 // smemBudget: bytes of shared memory the table may take
-void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img);
+void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img,
+                 bool allowByteRows = true);
 
 } // namespace red_b200

@@ -110,6 +110,35 @@ def test_simple_walk_variant_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
     prog.close()
 
 
+def test_table_layouts_agree(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Small DFAs use byte-indexed rows (one load per byte); the class-compressed
+    layout and the v1 tile kernel must give the same answers."""
+    from one_b200 import synth
+    text, starts, lens = synth.make_corpus(20000, seed=5)
+    for name in ("single_auto", "n3_fmt1", "newyork", "leader_class"):
+        case = next(c for c in vectors["cases"] if c["name"] == name)
+        blob = unz(case["program"])
+        orc = oracle_cls(blob)
+        progs = [gpu_red.Program(blob)]
+        assert progs[0].info["row_stride"] == 256
+        monkeypatch.setenv("RED_B200_NO_BYTE_ROWS", "1")
+        progs.append(gpu_red.Program(blob))
+        assert progs[1].info["row_stride"] < 256
+        monkeypatch.setenv("RED_B200_VARIANT", "1")
+        progs.append(gpu_red.Program(blob))
+        monkeypatch.delenv("RED_B200_NO_BYTE_ROWS")
+        progs.append(gpu_red.Program(blob))
+        monkeypatch.delenv("RED_B200_VARIANT")
+        for verb in ("check", "match"):
+            for sty in STYLES:
+                eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+                for pr in progs:
+                    res, ms, me = pr.match_batch_host(text, starts, lens, verb, sty)
+                    assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), (name, verb, sty)
+        for pr in progs:
+            pr.close()
+
+
 def test_global_table_path_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
     """Force the L2/global-table kernels on a DFA that would fit shared memory."""
     from one_b200 import synth

@@ -27,14 +27,29 @@ def main():
     sts = torch.empty(n, dtype=torch.int32, device=dev)
     print("lines", n, "bytes %.2f GB" % (nbytes / 1e9), flush=True)
     envs = []
-    for threads, ctas, simple in itertools.product([256, 512, 1024], [1, 2, 4], [0, 1]):
-        if threads * ctas > 2048:
-            continue
-        envs.append({"RED_B200_THREADS": str(threads), "RED_B200_CTAS_PER_SM": str(ctas),
-                     "RED_B200_SIMPLE_WALK": str(simple)})
+    cfgs = os.environ.get("SWEEP", "v0,v1").split(",")
+    for c in cfgs:
+        env = {"RED_B200_THREADS": "1024", "RED_B200_CTAS_PER_SM": "1", "RED_B200_SIMPLE_WALK": "0",
+               "RED_B200_VARIANT": "0", "RED_B200_LINES_PER_LANE": "0"}
+        for kv in c.split("+"):
+            if kv == "v0":
+                env["RED_B200_VARIANT"] = "0"
+            elif kv == "v1":
+                env["RED_B200_VARIANT"] = "1"
+            elif kv.startswith("T"):
+                env["RED_B200_LINES_PER_LANE"] = kv[1:]
+            elif kv.startswith("thr"):
+                env["RED_B200_THREADS"] = kv[3:]
+            elif kv == "nobyte":
+                env["RED_B200_NO_BYTE_ROWS"] = "1"
+            elif kv == "simple":
+                env["RED_B200_SIMPLE_WALK"] = "1"
+        env["name"] = c
+        envs.append(env)
     extra = os.environ.get("SWEEP_EXTRA")
     for env in envs:
-        os.environ.update(env)
+        os.environ.pop("RED_B200_NO_BYTE_ROWS", None)
+        os.environ.update({k: v for k, v in env.items() if k != 'name'})
         try:
             prog = red.Program(blob)
         except Exception as ex:  # noqa: BLE001
@@ -53,9 +68,8 @@ def main():
                 b.record()
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / 3
-                print("thr=%s ctas=%s simple=%s style=%s start=%d : %.3f ms  %.1f GB/s" % (
-                    env["RED_B200_THREADS"], env["RED_B200_CTAS_PER_SM"], env["RED_B200_SIMPLE_WALK"],
-                    style, want_start, ms, nbytes / ms / 1e6), flush=True)
+                print("%-16s style=%s start=%d : %.3f ms  %.1f GB/s" % (
+                    env["name"], style, want_start, ms, nbytes / ms / 1e6), flush=True)
             except Exception as ex:  # noqa: BLE001
                 print(env, style, "failed", ex, flush=True)
                 torch.cuda.synchronize()
