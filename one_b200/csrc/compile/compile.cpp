@@ -1,14 +1,45 @@
-/* compile.cpp - placeholder until the host compile pipeline lands. */
+/* compile.cpp - patterns -> serialized REDA program: the host-side compile
+   pipeline behind red_b200_compile() (reference: compileToSerialized,
+   lib/Compile.cpp:26). */
+
 #include "compile.h"
+
+#include <cstdlib>
+#include <new>
+
 #include "../../../include/red_b200.h"
+#include "dfa.h"
+#include "parser.h"
 
 namespace red_b200 {
 
-int compile_patterns(int, const char *const *, const uint64_t *,
-                     const int32_t *, const uint32_t *, const int32_t *, int,
-                     uint64_t, std::string &, std::string &why) {
-  why = "compile pipeline not built yet";
-  return RED_B200_EINTERNAL;
+int compile_patterns(int n, const char *const *patterns,
+                     const uint64_t *patternLens, const int32_t *results,
+                     const uint32_t *flags, const int32_t *langs, int format,
+                     uint64_t maxStates, std::string &out, std::string &why) {
+  try {
+    const uint64_t budget = maxStates ? maxStates : ~0ull;
+    rx::PatternParser parser(maxStates, 0);
+    for (int i = 0; i < n; ++i)
+      parser.add(langs[i], reinterpret_cast<const uint8_t *>(patterns[i]),
+                 patternLens[i], results[i], flags[i]);
+    rx::Nfa &nfa = parser.finish();
+    rx::RawDfa raw = rx::determinize(nfa, budget);
+    const char *env = getenv("RED_B200_MINIMIZE");
+    rx::MinimizeMode mode = (env && (std::string(env) == "exact"))
+        ? rx::kMinimizeExact : rx::kMinimizeLikeReference;
+    rx::MinDfa min = rx::minimize(raw, mode);
+    out = rx::serialize(min, format);
+    return RED_B200_OK;
+  }
+  catch (const rx::CompileError &ex) {
+    why = ex.msg;
+    return ex.code;
+  }
+  catch (const std::bad_alloc &) {
+    why = "out of memory";
+    return RED_B200_ELIMIT;
+  }
 }
 
 } // namespace red_b200
