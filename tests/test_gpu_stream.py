@@ -1,0 +1,110 @@
+"""One long byte stream on the GPU (chunked, speculated start states, stitched)
+against the oracle's match() over the same text.  GPU only."""
+
+import numpy as np
+import pytest
+
+from conftest import unz
+
+pytestmark = pytest.mark.gpu
+
+STYLES = ["instant", "first", "tangent", "last", "full"]
+
+
+def to_dev(raw):
+    import torch
+    buf = bytearray(raw) + bytearray(64)
+    return torch.frombuffer(buf, dtype=torch.uint8).cuda()[:len(raw)]
+
+
+def check_stream(gpu_red, oracle_cls, blob, raw, what):
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    dt = to_dev(raw)
+    for sty in STYLES:
+        exp = orc.run(raw, "match", sty, False)
+        got = tuple(prog.match_stream_device(dt, "match", sty))
+        assert got == exp, (what, sty, got, exp)
+        assert prog.match_stream_device(dt, "check", sty).result == exp[0]
+    prog.close()
+
+
+def test_stream_union64_on_log_text(gpu_red, vectors, oracle_cls):
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    text, _, _ = synth.make_corpus(40000, seed=21)
+    raw = text.tobytes()
+    check_stream(gpu_red, oracle_cls, blob, raw, "union64")
+    # no match anywhere: only noise lines
+    noise = b"\n".join(l for l in synth.make_lines(30000, seed=5) if b"CRON" in l or b"ntpd" in l)
+    check_stream(gpu_red, oracle_cls, blob, noise, "union64-noise")
+    # a single match at the very end / very start
+    check_stream(gpu_red, oracle_cls, blob, noise + b" Quarantined", "tail")
+    check_stream(gpu_red, oracle_cls, blob, b"Quarantined " + noise, "head")
+
+
+def test_stream_edge_sizes(gpu_red, vectors, oracle_cls):
+    case = next(c for c in vectors["cases"] if c["name"] == "newyork")
+    blob = unz(case["program"])
+    rng = np.random.RandomState(3)
+    for n in (1, 15, 16, 17, 255, 1024, 1025, 16384, 16385, 70001):
+        body = bytes(rng.choice(list(b"abc NewYork."), size=n).astype(np.uint8))
+        check_stream(gpu_red, oracle_cls, blob, body, n)
+    import torch
+    prog = gpu_red.Program(blob)
+    assert tuple(prog.match_stream_device(torch.empty(0, dtype=torch.uint8, device="cuda"), "match", "last")) == (0, 0, 0)
+    prog.close()
+
+
+@pytest.mark.parametrize("name", ["single_auto", "loose_both", "n3_fmt2", "nullable", "initloop", "exact", "bytes"])
+def test_stream_other_programs(gpu_red, vectors, oracle_cls, name):
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == name)
+    blob = unz(case["program"])
+    rng = np.random.RandomState(9)
+    text, _, _ = synth.make_corpus(5000, seed=2)
+    check_stream(gpu_red, oracle_cls, blob, text.tobytes(), name)
+    for alphabet in (b"ab", b"abc0123456789", b"abc\x00\xff\x80", b"(ab|c)xyz"):
+        body = bytes(rng.choice(list(alphabet), size=200000).astype(np.uint8))
+        check_stream(gpu_red, oracle_cls, blob, body, (name, alphabet))
+
+
+def test_stream_dfa_that_never_forgets(gpu_red, redlib, oracle_cls):
+    """A parity counter: the guess from the lookback window is wrong half of
+    the time and a wrong start gives a wrong end, so stitching has to iterate.
+    Still exact."""
+    p = redlib.Parser()
+    p.add(b"((a|b)(a|b))*", 1, 0)
+    blob = redlib.compileToSerialized(p)
+    for n in (40000, 40001):
+        check_stream(gpu_red, oracle_cls, blob, b"ab" * (n // 2) + b"a" * (n % 2), ("parity", n))
+
+
+def test_large_dfa_uses_global_table(gpu_red, redlib, oracle_cls):
+    """BASELINE configs[2]: a union too large for shared memory (L2-resident
+    global table, 4-byte entries), first/last styles."""
+    from one_b200 import synth
+    p = redlib.Parser()
+    rules = synth.rules_keywords(2000)
+    for pat, res, flags, lang in rules:
+        p.addAs(lang, pat, res, flags)
+    blob = redlib.compileToSerialized(p)
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    info = prog.info
+    assert info["table_mode"] == 2 and info["state_count"] > 10000, info
+    rng = np.random.RandomState(4)
+    lines = synth.make_lines(30000, seed=12)
+    # plant keywords into a third of the lines
+    for i in range(0, len(lines), 3):
+        kw = rules[rng.randint(len(rules))][0]
+        k = rng.randint(0, len(lines[i]))
+        lines[i] = lines[i][:k] + kw + lines[i][k:]
+    text, starts, lens = synth.pack_lines(lines)
+    for verb in ("check", "match"):
+        for sty in ("first", "last", "instant"):
+            res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+            eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+            assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), (verb, sty)
+    assert (eres > 0).sum() > 5000
+    check_stream(gpu_red, oracle_cls, blob, text.tobytes()[:400000], "keywords2000")
+    prog.close()
