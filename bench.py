@@ -351,13 +351,13 @@ def main():
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "batch_anchored_kernel<instant>", "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel": "batch_lanes_kernel<instant>", "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": kern_ms}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
             tj = json.load(f)
-        roofline["traffic"] = tj.get("dram_bytes_per_launch")
+        roofline["traffic"] = tj["dram_bytes_per_line"] * n
         roofline["traffic_note"] = tj.get("note")
 
     cpu = None

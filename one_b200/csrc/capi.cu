@@ -109,7 +109,6 @@ struct HostPipe {
   int32_t *dRes[kSlots]{};
   uint32_t *dMs[kSlots]{};
   uint32_t *dMe[kSlots]{};
-  uint64_t *hStarts[kSlots]{};  // pinned: chunk-relative starts
 
   void release() {
     for (int s = 0; s < kSlots; ++s) {
@@ -117,7 +116,6 @@ struct HostPipe {
       if (done[s]) cudaEventDestroy(done[s]);
       cudaFree(dText[s]); cudaFree(dStarts[s]); cudaFree(dLens[s]);
       cudaFree(dRes[s]); cudaFree(dMs[s]); cudaFree(dMe[s]);
-      if (hStarts[s]) cudaFreeHost(hStarts[s]);
     }
   }
 };
@@ -425,7 +423,6 @@ static int ensure_pipe(red_b200_program *prog, size_t textCap, size_t lineCap) {
     CUDA_TRY(cudaMalloc(&pp->dRes[s], lineCap * 4));
     CUDA_TRY(cudaMalloc(&pp->dMs[s], lineCap * 4));
     CUDA_TRY(cudaMalloc(&pp->dMe[s], lineCap * 4));
-    CUDA_TRY(cudaMallocHost(&pp->hStarts[s], lineCap * 8));
   }
   return RED_B200_OK;
 }
@@ -499,18 +496,18 @@ int red_b200_match_batch_host(const red_b200_program *cprog,
     cudaStream_t st = pp->stream[s];
     // slot free? (its previous copy-out finished)
     CUDA_TRY(cudaEventSynchronize(pp->done[s]));
-    // the device copy keeps the span's alignment modulo 16
+    // The device copy keeps the span's alignment modulo 16, and the kernels are
+    // handed a text base shifted by the span's (aligned) start, so the caller's
+    // absolute start offsets are used as they are - no per-line rewriting.
     uint64_t lo16 = c.lo & ~uint64_t(15);
-    for (uint64_t k = 0; k < c.count; ++k)
-      pp->hStarts[s][k] = starts[c.first + k] - lo16;
     CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (c.lo - lo16), text + c.lo,
                              c.hi - c.lo, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], pp->hStarts[s], c.count * 8,
+    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], starts + c.first, c.count * 8,
                              cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + c.first, c.count * 4,
                              cudaMemcpyHostToDevice, st));
     BatchArgs args;
-    args.text = pp->dText[s];
+    args.text = pp->dText[s] - lo16;
     args.starts = pp->dStarts[s];
     args.lens = pp->dLens[s];
     args.nLines = c.count;
