@@ -99,7 +99,7 @@ struct red_b200_program {
    that the copy-in of chunk i+1 overlaps the kernel of chunk i and the
    copy-out of chunk i-1. */
 struct HostPipe {
-  static constexpr int kSlots = 2;
+  static constexpr int kSlots = 3;
   size_t textCap = 0, lineCap = 0;
   cudaStream_t stream[kSlots]{};
   cudaEvent_t done[kSlots]{};
@@ -455,78 +455,90 @@ int red_b200_match_batch_host(const red_b200_program *cprog,
 
   /* Cut the batch into chunks of consecutive lines whose bytes form one
      span of the text (lines are normally in text order; a batch that is not
-     is still correct, its spans just get longer).  Chunk targets: ~64 MiB of
+     is still correct, its spans just get longer).  Chunk targets: ~32 MiB of
      text or 1 Mi lines, whichever comes first. */
-  size_t textTarget = 64u << 20;
+  size_t textTarget = 32u << 20;
   size_t lineTarget = 1u << 20;
   if (const char *env = getenv("RED_B200_HOST_CHUNK_BYTES"))
     textTarget = std::max<size_t>(1 << 16, strtoull(env, nullptr, 0));
 
-  struct Chunk { uint64_t first, count, lo, hi; };
-  std::vector<Chunk> chunks;
-  {
-    uint64_t ii = 0;
-    while (ii < n_lines) {
-      Chunk c{ii, 0, starts[ii], starts[ii] + lens[ii]};
-      while (ii < n_lines) {
-        uint64_t lo = std::min(c.lo, starts[ii]);
-        uint64_t hi = std::max(c.hi, starts[ii] + lens[ii]);
-        if (hi > text_len)
-          return fail(RED_B200_EAPI, "line extends past end of text");
-        if (c.count && (((hi - lo) > textTarget) || (c.count >= lineTarget)))
-          break;
-        c.lo = lo; c.hi = hi; ++c.count; ++ii;
+  /* Chunks are planned one at a time, while the GPU works on the previous
+     ones: the plan is a min/max over the lines' extents, taken in blocks of
+     4096 lines so that the loop stays branch-free. */
+  const uint64_t kBlock = 4096;
+  uint64_t first = 0;
+  int rc = RED_B200_OK;
+  for (size_t ci = 0; first < n_lines; ++ci) {
+    uint64_t lo = ~0ull, hi = 0, count = 0;
+    while (first + count < n_lines) {
+      const uint64_t m = std::min<uint64_t>(kBlock, n_lines - first - count);
+      const uint64_t *sp = starts + first + count;
+      const uint32_t *lp = lens + first + count;
+      uint64_t blo = ~0ull, bhi = 0;
+      for (uint64_t k = 0; k < m; ++k) {
+        const uint64_t a0 = sp[k], a1 = sp[k] + lp[k];
+        blo = a0 < blo ? a0 : blo;
+        bhi = a1 > bhi ? a1 : bhi;
       }
-      chunks.push_back(c);
+      const uint64_t nlo = std::min(lo, blo), nhi = std::max(hi, bhi);
+      if (count && (((nhi - nlo) > textTarget) || (count + m > lineTarget)))
+        break;
+      lo = nlo;
+      hi = nhi;
+      count += m;
     }
-  }
-  size_t maxText = 0, maxLines = 0;
-  for (const Chunk &c : chunks) {
-    maxText = std::max<size_t>(maxText, c.hi - c.lo);
-    maxLines = std::max<size_t>(maxLines, c.count);
-  }
-  int rc = ensure_pipe(prog, maxText, maxLines);
-  if (rc != RED_B200_OK)
-    return rc;
-  HostPipe *pp = prog->pipe;
-
-  for (size_t ci = 0; ci < chunks.size(); ++ci) {
-    const Chunk &c = chunks[ci];
-    int s = static_cast<int>(ci % HostPipe::kSlots);
+    if (hi > text_len)
+      return fail(RED_B200_EAPI, "line extends past end of text");
+    // (re)size the staging buffers; growing waits for the work in flight
+    if (!prog->pipe || (prog->pipe->textCap < hi - lo) || (prog->pipe->lineCap < count)) {
+      if (prog->pipe)
+        for (int s = 0; s < HostPipe::kSlots; ++s)
+          CUDA_TRY(cudaStreamSynchronize(prog->pipe->stream[s]));
+      rc = ensure_pipe(prog, std::max<size_t>(hi - lo, textTarget + (8u << 20)),
+                       std::max<size_t>(count, lineTarget));
+      if (rc != RED_B200_OK)
+        return rc;
+    }
+    HostPipe *pp = prog->pipe;
+    const int s = static_cast<int>(ci % HostPipe::kSlots);
     cudaStream_t st = pp->stream[s];
     // slot free? (its previous copy-out finished)
     CUDA_TRY(cudaEventSynchronize(pp->done[s]));
     // The device copy keeps the span's alignment modulo 16, and the kernels are
     // handed a text base shifted by the span's (aligned) start, so the caller's
     // absolute start offsets are used as they are - no per-line rewriting.
-    uint64_t lo16 = c.lo & ~uint64_t(15);
-    CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (c.lo - lo16), text + c.lo,
-                             c.hi - c.lo, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], starts + c.first, c.count * 8,
+    const uint64_t lo16 = lo & ~uint64_t(15);
+    CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (lo - lo16), text + lo, hi - lo,
                              cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + c.first, c.count * 4,
+    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], starts + first, count * 8,
+                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + first, count * 4,
                              cudaMemcpyHostToDevice, st));
     BatchArgs args;
     args.text = pp->dText[s] - lo16;
     args.starts = pp->dStarts[s];
     args.lens = pp->dLens[s];
-    args.nLines = c.count;
+    args.nLines = count;
     args.results = pp->dRes[s];
     args.matchStarts = match_starts ? pp->dMs[s] : nullptr;
     args.matchEnds = match_ends ? pp->dMe[s] : nullptr;
     rc = launch_batch(prog, args, verb, style, st);
     if (rc != RED_B200_OK)
       return rc;
-    CUDA_TRY(cudaMemcpyAsync(results + c.first, pp->dRes[s], c.count * 4,
+    CUDA_TRY(cudaMemcpyAsync(results + first, pp->dRes[s], count * 4,
                              cudaMemcpyDeviceToHost, st));
     if (match_starts)
-      CUDA_TRY(cudaMemcpyAsync(match_starts + c.first, pp->dMs[s], c.count * 4,
+      CUDA_TRY(cudaMemcpyAsync(match_starts + first, pp->dMs[s], count * 4,
                                cudaMemcpyDeviceToHost, st));
     if (match_ends)
-      CUDA_TRY(cudaMemcpyAsync(match_ends + c.first, pp->dMe[s], c.count * 4,
+      CUDA_TRY(cudaMemcpyAsync(match_ends + first, pp->dMe[s], count * 4,
                                cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(pp->done[s], st));
+    first += count;
   }
+  HostPipe *pp = prog->pipe;
+  if (!pp)
+    return RED_B200_OK;
   for (int s = 0; s < HostPipe::kSlots; ++s)
     CUDA_TRY(cudaStreamSynchronize(pp->stream[s]));
   return RED_B200_OK;

@@ -270,6 +270,8 @@ batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
           if (q == 3) { mq3 = m; }
         }
         const uint32_t eLimit = fast.encLimit(wk.limit);
+        const uint32_t ePure = fast.enc(pd.pureV);
+        const uint32_t eAbs = fast.enc(pd.absV);
         const uint32_t mAll = max(max(mq0, mq1), max(mq2, mq3));
         if ((mAll < eLimit) || !cValid) {
           wk.v = fast.dec(e);
@@ -283,6 +285,9 @@ batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
           int q = (mq0 >= eLimit) ? 0 : (mq1 >= eLimit) ? 1 : (mq2 >= eLimit) ? 2 : 3;
           if (WANT_START)
             q = 0;
+          constexpr bool kLean = !WANT_START &&
+              ((STYLE == STY_INSTANT) || (STYLE == STY_LAST) || (STYLE == STY_FULL));
+          uint32_t ee = e;
 #pragma unroll 1
           for (; (q < 4) && !stopped; ++q) {
             const uint32_t m = (q == 0) ? mq0 : (q == 1) ? mq1 : (q == 2) ? mq2 : mq3;
@@ -290,15 +295,46 @@ batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
               const uint32_t eq = (q == 0) ? eIn : (q == 1) ? cp0 : (q == 2) ? cp1 : cp2;
               const uint32_t word = (q == 0) ? cur.x : (q == 1) ? cur.y : (q == 2) ? cur.z : cur.w;
               const uint32_t nib = mask >> (4 * q);
-              wk.v = fast.dec(eq);
+              if (kLean) {
+                // Instant / Last / Full without start tracking: the decisions
+                // are compares on the encoded state (Matcher.h:441-478)
+                ee = eq;
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (!stopped && (nib & (1u << jj)))
-                  stopped = wk.step(pd, tab, cls[byte_of(word, jj)], pos0 + 4 * q + jj);
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (!stopped && (nib & (1u << jj))) {
+                    ee = fast.step(ee, word, jj);
+                    if (ee >= eLimit) {
+                      if (ee >= ePure)
+                        stopped = true;           // pure dead end
+                      else if (STYLE == STY_FULL)
+                        stopped = true;           // absorbing accept: outcome known
+                      else {
+                        wk.accV = fast.dec(ee);
+                        wk.mend = pos0 + 4 * q + jj + 1;
+                        if (STYLE == STY_INSTANT)
+                          stopped = true;
+                        else if (ee >= eAbs) {
+                          wk.absorbed = true;
+                          stopped = true;
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+              else {
+                wk.v = fast.dec(eq);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (!stopped && (nib & (1u << jj)))
+                    stopped = wk.step(pd, tab, cls[byte_of(word, jj)], pos0 + 4 * q + jj);
+                }
               }
             }
           }
-          if (!stopped)
+          if (kLean)
+            wk.v = fast.dec(stopped ? ee : e);
+          else if (!stopped)
             wk.v = fast.dec(e);
         }
       }
