@@ -133,7 +133,11 @@ const char *red_b200_check_header(const void *serialized, size_t len);
    and (verbs match/search) where the match started/ended, exactly as
    Outcome would hold them; results of 0 come with start = end = 0.
    match_starts / match_ends may be NULL when not wanted.
-   All pointers are device pointers; the call is asynchronous on `stream`. */
+   All pointers are device pointers; the call is asynchronous on `stream`.
+   The kernels read text in aligned 16-byte blocks: the text allocation must be
+   readable from the 16-byte boundary at or below the first line's start to the
+   16-byte boundary at or above the last line's end (any cudaMalloc'd or torch
+   buffer is, CUDA allocations being 256-byte granular). */
 int red_b200_match_batch_device(const red_b200_program *prog,
                                 const uint8_t *d_text,
                                 const uint64_t *d_starts,

@@ -261,7 +261,8 @@ batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
               if (act && (e == eInit) && (ne != eInit))
                 msFast = pos0 + j;
             }
-            e = act ? ne : e;
+            if (act)
+              e = ne;
             m = max(m, e);
           }
           if (q == 0) { mq0 = m; cp0 = e; }
