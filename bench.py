@@ -337,6 +337,30 @@ def main():
                "d2h_bytes_per_step": int(hn * 8), "lines_per_step": hn,
                "ms_per_step": float(tt[0]) * 1e3,
                "api": "red_b200_match_batch_host (pinned host text/index in, results+ends out)"}
+        # the blob entry point (text only over PCIe, matching lines back):
+        # same lines, same outcomes, reported beside e2e
+        recs = np.zeros(hn // 2, dtype=red.LINE_MATCH_DTYPE)
+        nm, nl = __import__("ctypes").c_uint64(), __import__("ctypes").c_uint64()
+
+        def grep_step():
+            red._check(red.lib().red_b200_grep_host(prog._h, tn.ctypes.data, tn.size, 10, red.STYLES[STYLE],
+                                                    recs.ctypes.data, recs.size,
+                                                    __import__("ctypes").byref(nm), __import__("ctypes").byref(nl)))
+
+        grep_step()
+        assert nl.value == hn and nm.value == int((hres > 0).sum()), (nl.value, hn, nm.value)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            grep_step()
+        gdt = (time.perf_counter() - t0) / k
+        tg = torch.tensor([gdt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        e2e["grep"] = {"value": float(tb[0]) / float(tg[0]) / 1e9, "unit": "GB/s",
+                       "h2d_bytes_per_step": int(htext.numel()),
+                       "d2h_bytes_per_step": int(nm.value * 24), "ms_per_step": float(tg[0]) * 1e3,
+                       "api": "red_b200_grep_host (log blob in, matching lines out; index, match, "
+                              "compaction on the GPU)"}
         del htext, hstarts, hlens, hres, hends
 
     if rank != 0:

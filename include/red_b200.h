@@ -182,6 +182,29 @@ int red_b200_compact_matches_device(const int32_t *d_results, uint64_t n_lines,
                                     uint64_t *d_indices, uint64_t *d_count,
                                     int device, void *stream);
 
+/* ---- a log blob, end to end (the flume / loggle workload) ---------------- */
+
+typedef struct {
+  uint64_t line_start;   /* byte offset of the line in the text              */
+  uint32_t line_len;     /* without the delimiter                            */
+  int32_t  result;       /* > 0                                              */
+  uint32_t match_start;  /* Outcome.start_ / end_, relative to the line      */
+  uint32_t match_end;
+} red_b200_line_match;
+
+/* text is a sequence of lines separated by `delim` (a last line without one
+   counts).  Every line is matched as match(exec, line, style) would
+   (include/Matcher.h:79); the lines with a result > 0 are returned in text
+   order.  Line index, matching and compaction run on the GPU: only the text
+   goes in and only these records come out.  *n_lines gets the number of lines
+   seen.  RED_B200_ELIMIT if there are more matching lines than `capacity`
+   (the first `capacity` are stored) or if a line is longer than the staging
+   piece.  Synchronous. */
+int red_b200_grep_host(const red_b200_program *prog, const uint8_t *text,
+                       uint64_t text_len, uint8_t delim, int style,
+                       red_b200_line_match *matches, uint64_t capacity,
+                       uint64_t *n_matches, uint64_t *n_lines);
+
 /* ---- one long byte stream ---------------------------------------------- */
 
 /* match()/check() of one long device-resident text: the text is cut into

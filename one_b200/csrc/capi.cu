@@ -20,13 +20,12 @@
 #include "compile/compile.h"
 #include "device_program.h"
 #include "program.h"
+#include "program_handle.h"
 #include "stream.h"
 
 using namespace red_b200;
 
 namespace {
-
-constexpr unsigned kCounters = 256;
 
 thread_local std::string g_err;
 
@@ -72,28 +71,6 @@ struct DeviceGuard {
 };
 
 } // anonymous
-
-struct red_b200_program {
-  int device = 0;
-  LaunchGeometry geo{};
-  DeviceImage img;      // host copy (tables cleared after upload)
-  ParsedProgram parsed; // kept small: tables cleared after upload
-  ProgramDev dev{};
-  bool smemTable = false;
-  uint32_t format = 0;
-  uint32_t leaderLen = 0;
-  uint64_t tableBytes = 0;
-  void *dTable = nullptr;
-  void *dCls = nullptr;
-  void *dResults = nullptr;
-  void *dLeader = nullptr;
-  unsigned long long *dCounters = nullptr;  // kCounters block counters, used round-robin
-  unsigned nextCounter = 0;
-  BatchTuning tune;
-  std::mutex mu;        // guards the lazily created host pipeline
-  struct HostPipe *pipe = nullptr;
-  long launches = 0;    // kernels launched through this program (for bench)
-};
 
 /* Pinned staging + device buffers for the *_host entry points: two slots so
    that the copy-in of chunk i+1 overlaps the kernel of chunk i and the
@@ -306,6 +283,7 @@ void red_b200_program_free(red_b200_program *prog) {
     prog->pipe->release();
     delete prog->pipe;
   }
+  release_grep_pipe(prog);
   cudaFree(prog->dTable);
   cudaFree(prog->dCls);
   cudaFree(prog->dResults);
@@ -368,6 +346,22 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
   prog->launches += launches;
   return RED_B200_OK;
 }
+
+} // extern "C"
+
+namespace red_b200 {
+void set_last_error(const std::string &msg) { g_err = msg; }
+
+int launch_batch_for(red_b200_program *prog, const BatchArgs &args, int verb,
+                     int style, cudaStream_t stream, std::string &why) {
+  int rc = launch_batch(prog, args, verb, style, stream);
+  if (rc != RED_B200_OK)
+    why = g_err;
+  return rc;
+}
+}
+
+extern "C" {
 
 int red_b200_match_batch_device(const red_b200_program *cprog,
                                 const uint8_t *d_text,
@@ -552,16 +546,32 @@ int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
     return fail(RED_B200_EEXEC, "unsupported style");
   if (!valid_verb(verb))
     return fail(RED_B200_EEXEC, "unsupported verb");
+  if (len && !text)
+    return fail(RED_B200_EAPI, "null text");
+  // Long texts: copy to the GPU once and take the chunked stream path.  (check()
+  // on a program with a leader keeps the per-line kernel: its leader quirk is
+  // not a property of the stream matcher.)
+  const bool streamable = (verb == RED_B200_VERB_MATCH) ||
+                          ((verb == RED_B200_VERB_CHECK) && (prog->leaderLen == 0));
+  if (streamable && (len >= (256u << 10))) {
+    DeviceGuard guard(prog->device);
+    uint8_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, len + 64));
+    cudaError_t e = cudaMemcpy(d, text, len, cudaMemcpyHostToDevice);
+    int rc = (e == cudaSuccess)
+        ? red_b200_match_stream_device(prog, d, len, verb, style, out, nullptr)
+        : cuda_fail(e, "cudaMemcpy(text)");
+    cudaFree(d);
+    return rc;
+  }
   if (len >= (1ull << 31))
-    return fail(RED_B200_ELIMIT, "text too long for red_b200_match; use the stream entry point");
+    return fail(RED_B200_ELIMIT, "text too long for this verb; use match on the stream entry point");
   uint64_t start0 = 0;
   uint32_t len32 = static_cast<uint32_t>(len);
   int32_t res = 0;
   uint32_t ms = 0, me = 0;
   static const uint8_t empty[1] = {0};
   const uint8_t *t = len ? static_cast<const uint8_t *>(text) : empty;
-  if (len && !text)
-    return fail(RED_B200_EAPI, "null text");
   int rc = red_b200_match_batch_host(prog, t, len, &start0, &len32, 1, verb,
                                      style, &res, &ms, &me);
   if (rc != RED_B200_OK)

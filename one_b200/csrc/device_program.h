@@ -39,6 +39,8 @@ struct BatchArgs {
   uint32_t *matchStarts;  // may be null
   uint32_t *matchEnds;    // may be null
   bool checkLeader = false;  // verb check on a program that has a leader
+  const uint64_t *nLinesDev = nullptr;  // if set: the line count lives on the device
+                                        // (nLines is then only an upper bound)
 };
 
 struct LaunchGeometry {

@@ -137,7 +137,7 @@ batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
 
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t perBlock = 32ull * T;
-  const uint64_t n = args.nLines;
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   const uint32_t leadLen = LEADER ? pd.leaderLen : 0;
 
   for (;;) {

@@ -1,0 +1,54 @@
+/* program_handle.h - the object behind `red_b200_program *` (private). */
+
+#pragma once
+
+#include <mutex>
+#include <string>
+
+#include "../../include/red_b200.h"
+#include "device_program.h"
+#include "program.h"
+
+struct HostPipe;
+struct GrepPipe;
+
+using red_b200::BatchArgs;
+using red_b200::BatchTuning;
+using red_b200::DeviceImage;
+using red_b200::LaunchGeometry;
+using red_b200::ParsedProgram;
+using red_b200::ProgramDev;
+
+constexpr unsigned kCounters = 256;
+
+struct red_b200_program {
+  int device = 0;
+  LaunchGeometry geo{};
+  DeviceImage img;      // host copy (tables cleared after upload)
+  ParsedProgram parsed; // kept small: tables cleared after upload
+  ProgramDev dev{};
+  bool smemTable = false;
+  uint32_t format = 0;
+  uint32_t leaderLen = 0;
+  uint64_t tableBytes = 0;
+  void *dTable = nullptr;
+  void *dCls = nullptr;
+  void *dResults = nullptr;
+  void *dLeader = nullptr;
+  unsigned long long *dCounters = nullptr;  // kCounters block counters, used round-robin
+  unsigned nextCounter = 0;
+  BatchTuning tune;
+  std::mutex mu;        // guards the lazily created host pipeline
+  HostPipe *pipe = nullptr;
+  GrepPipe *grep = nullptr;   // lazily created by red_b200_grep_host
+  long launches = 0;    // kernels launched through this program (for bench)
+};
+
+
+namespace red_b200 {
+// launch the per-line kernels for one batch (capi.cu)
+int launch_batch_for(red_b200_program *prog, const BatchArgs &args, int verb,
+                     int style, cudaStream_t stream, std::string &why);
+void release_grep_pipe(red_b200_program *prog);  // grep.cu
+void set_last_error(const std::string &msg);      // capi.cu: what red_b200_last_error() returns
+}

@@ -10,6 +10,7 @@
 
 #include "stream.h"
 
+#include <algorithm>
 #include <vector>
 
 namespace red_b200 {
@@ -17,6 +18,19 @@ namespace red_b200 {
 namespace {
 
 constexpr int kScanThreads = 1024;
+
+/* nDelims delimiters give nDelims lines plus one more if the text does not
+   end with a delimiter; clamped to the caller's capacity (overflow set) */
+__global__ void line_count_kernel(const uint8_t *text, uint64_t len, uint8_t delim,
+                                  uint64_t capacity, const uint64_t *total,
+                                  LineCount *info) {
+  uint64_t nd = *total;
+  uint64_t n = nd + ((len && (text[len - 1] != delim)) ? 1 : 0);
+  info->wanted = n;
+  info->overflow = n > capacity;
+  info->nLines = n > capacity ? capacity : n;
+  info->nDelims = nd;
+}
 constexpr uint32_t kSegBytes = 16384;  // text bytes per warp segment
 constexpr uint32_t kSegLines = 4096;   // results per warp segment
 
@@ -58,7 +72,10 @@ __global__ void count_delims_kernel(const uint8_t *text, uint64_t len,
 }
 
 __global__ void count_matches_kernel(const int32_t *results, uint64_t n,
-                                     uint32_t *segCounts, uint64_t nSegs) {
+                                     uint32_t *segCounts, uint64_t nSegs,
+                                     const uint64_t *nDev = nullptr) {
+  if (nDev)
+    n = min(n, *nDev);
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -109,8 +126,9 @@ scan_counts_kernel(const uint32_t *segCounts, uint64_t *segOffsets,
      starts[r+1] = d + 1                 (if that line exists)            */
 __global__ void write_lines_kernel(const uint8_t *text, uint64_t len,
                                    uint32_t d4, const uint64_t *segOffsets,
-                                   uint64_t nSegs, uint64_t nLines,
+                                   uint64_t nSegs, const LineCount *info,
                                    uint64_t *starts, uint32_t *lens) {
+  const uint64_t nLines = info->nLines;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -141,7 +159,8 @@ __global__ void write_lines_kernel(const uint8_t *text, uint64_t len,
         uint32_t j = __ffs(m) - 1;
         m &= m - 1;
         uint64_t d = off + j;
-        lens[r] = static_cast<uint32_t>(d);
+        if (r < nLines)
+          lens[r] = static_cast<uint32_t>(d);
         if (r + 1 < nLines)
           starts[r + 1] = d + 1;
         ++r;
@@ -151,9 +170,9 @@ __global__ void write_lines_kernel(const uint8_t *text, uint64_t len,
   }
 }
 
-__global__ void finish_lines_kernel(uint64_t len, uint64_t nDelims,
-                                    uint64_t nLines, uint64_t *starts,
-                                    uint32_t *lens) {
+__global__ void finish_lines_kernel(uint64_t len, const LineCount *info,
+                                    uint64_t *starts, uint32_t *lens) {
+  const uint64_t nLines = info->nLines, nDelims = info->nDelims;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
        i < nLines; i += stride) {
@@ -167,7 +186,9 @@ __global__ void finish_lines_kernel(uint64_t len, uint64_t nDelims,
 
 __global__ void write_matches_kernel(const int32_t *results, uint64_t n,
                                      const uint64_t *segOffsets, uint64_t nSegs,
-                                     uint64_t *indices) {
+                                     uint64_t *indices, const uint64_t *nDev = nullptr) {
+  if (nDev)
+    n = min(n, *nDev);
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -185,23 +206,6 @@ __global__ void write_matches_kernel(const int32_t *results, uint64_t n,
     }
   }
 }
-
-struct Scratch {
-  uint32_t *counts = nullptr;
-  uint64_t *offsets = nullptr;
-  uint64_t *total = nullptr;
-  ~Scratch() {
-    cudaFree(counts);
-    cudaFree(offsets);
-    cudaFree(total);
-  }
-  cudaError_t alloc(uint64_t nSegs) {
-    cudaError_t e;
-    if ((e = cudaMalloc(&counts, nSegs * 4 + 4)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&offsets, nSegs * 8 + 8)) != cudaSuccess) return e;
-    return cudaMalloc(&total, 8);
-  }
-};
 
 int grid_for(uint64_t nSegs, int threads) {
   uint64_t warpsPerBlock = threads / 32;
@@ -223,42 +227,85 @@ int cuda_why(cudaError_t e, const char *what, std::string &why) {
 
 } // anonymous
 
+int split_lines_async(const uint8_t *dText, uint64_t len, uint8_t delim,
+                      uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
+                      LineCount *dInfo, SplitScratch &sc, cudaStream_t stream,
+                      std::string &why) {
+  if (reinterpret_cast<uintptr_t>(dText) & 15) {
+    why = "text must be 16-byte aligned";
+    return RED_B200_EAPI;
+  }
+  const uint64_t nSegs = (len + kSegBytes - 1) / kSegBytes;
+  if (nSegs > sc.capSegs) {
+    why = "internal: split scratch too small";
+    return RED_B200_EINTERNAL;
+  }
+  const uint32_t d4 = delim * 0x01010101u;
+  const int threads = 256;
+  const int grid = std::max(1, grid_for(nSegs, threads));
+  if (len)
+    count_delims_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.counts, nSegs);
+  scan_counts_kernel<<<1, kScanThreads, 0, stream>>>(sc.counts, sc.offsets, nSegs, sc.total);
+  line_count_kernel<<<1, 1, 0, stream>>>(dText, len, delim, capacity, sc.total, dInfo);
+  if (len) {
+    write_lines_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.offsets, nSegs,
+                                                     dInfo, dStarts, dLens);
+    finish_lines_kernel<<<148 * 4, 256, 0, stream>>>(len, dInfo, dStarts, dLens);
+  }
+  TRY(cudaGetLastError());
+  return RED_B200_OK;
+}
+
+cudaError_t SplitScratch::alloc(uint64_t maxTextBytes) {
+  capSegs = (maxTextBytes + kSegBytes - 1) / kSegBytes + 1;
+  cudaError_t e;
+  if ((e = cudaMalloc(&counts, capSegs * 4 + 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&offsets, capSegs * 8 + 8)) != cudaSuccess) return e;
+  return cudaMalloc(&total, 8);
+}
+
+void SplitScratch::release() {
+  cudaFree(counts);
+  cudaFree(offsets);
+  cudaFree(total);
+  counts = nullptr;
+  offsets = nullptr;
+  total = nullptr;
+  capSegs = 0;
+}
+
 int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
                 uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
                 uint64_t *nLinesOut, cudaStream_t stream, std::string &why) {
   *nLinesOut = 0;
   if (len == 0)
     return RED_B200_OK;
-  if (reinterpret_cast<uintptr_t>(dText) & 15) {
-    why = "text must be 16-byte aligned";
-    return RED_B200_EAPI;
+  SplitScratch sc;
+  LineCount *dInfo = nullptr;
+  TRY(sc.alloc(len));
+  cudaError_t e = cudaMalloc(&dInfo, sizeof(LineCount));
+  if (e != cudaSuccess) {
+    sc.release();
+    return cuda_why(e, "cudaMalloc(LineCount)", why);
   }
-  const uint64_t nSegs = (len + kSegBytes - 1) / kSegBytes;
-  const uint32_t d4 = delim * 0x01010101u;
-  Scratch sc;
-  TRY(sc.alloc(nSegs));
-  const int threads = 256;
-  const int grid = grid_for(nSegs, threads);
-  count_delims_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.counts, nSegs);
-  scan_counts_kernel<<<1, kScanThreads, 0, stream>>>(sc.counts, sc.offsets, nSegs, sc.total);
-  TRY(cudaGetLastError());
-  uint64_t nDelims = 0;
-  uint8_t last = 0;
-  TRY(cudaMemcpyAsync(&nDelims, sc.total, 8, cudaMemcpyDeviceToHost, stream));
-  TRY(cudaMemcpyAsync(&last, dText + len - 1, 1, cudaMemcpyDeviceToHost, stream));
-  TRY(cudaStreamSynchronize(stream));
-  const uint64_t nLines = nDelims + ((last != delim) ? 1 : 0);
-  if (nLines > capacity) {
+  int rc = split_lines_async(dText, len, delim, capacity, dStarts, dLens, dInfo, sc, stream, why);
+  LineCount info{};
+  if (rc == RED_B200_OK) {
+    e = cudaMemcpyAsync(&info, dInfo, sizeof(info), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess)
+      rc = cuda_why(e, "split_lines", why);
+  }
+  cudaFree(dInfo);
+  sc.release();
+  if (rc != RED_B200_OK)
+    return rc;
+  *nLinesOut = info.overflow ? info.wanted : info.nLines;
+  if (info.overflow) {
     why = "line index capacity too small";
-    *nLinesOut = nLines;
     return RED_B200_ELIMIT;
   }
-  write_lines_kernel<<<grid, threads, 0, stream>>>(dText, len, d4, sc.offsets, nSegs,
-                                                   nLines, dStarts, dLens);
-  finish_lines_kernel<<<148 * 4, 256, 0, stream>>>(len, nDelims, nLines, dStarts, dLens);
-  TRY(cudaGetLastError());
-  TRY(cudaStreamSynchronize(stream));
-  *nLinesOut = nLines;
   return RED_B200_OK;
 }
 
@@ -281,6 +328,23 @@ int compact_matches(const int32_t *dResults, uint64_t n, uint64_t *dIndices,
   TRY(cudaGetLastError());
   TRY(cudaFreeAsync(counts, stream));
   TRY(cudaFreeAsync(offsets, stream));
+  return RED_B200_OK;
+}
+
+int compact_matches_n(const int32_t *dResults, uint64_t capLines, const uint64_t *dN,
+                      uint64_t *dIndices, uint64_t *dCount, SplitScratch &sc,
+                      cudaStream_t stream, std::string &why) {
+  const uint64_t nSegs = (capLines + kSegLines - 1) / kSegLines;
+  if (nSegs > sc.capSegs) {
+    why = "internal: compaction scratch too small";
+    return RED_B200_EINTERNAL;
+  }
+  const int threads = 256;
+  const int grid = std::max(1, grid_for(nSegs, threads));
+  count_matches_kernel<<<grid, threads, 0, stream>>>(dResults, capLines, sc.counts, nSegs, dN);
+  scan_counts_kernel<<<1, kScanThreads, 0, stream>>>(sc.counts, sc.offsets, nSegs, dCount);
+  write_matches_kernel<<<grid, threads, 0, stream>>>(dResults, capLines, sc.offsets, nSegs, dIndices, dN);
+  TRY(cudaGetLastError());
   return RED_B200_OK;
 }
 

@@ -13,12 +13,40 @@
 
 namespace red_b200 {
 
+struct LineCount {
+  uint64_t nLines;    // lines indexed (clamped to the capacity)
+  uint64_t nDelims;
+  uint64_t wanted;    // lines the text really has
+  uint64_t overflow;  // wanted > capacity
+};
+
+struct SplitScratch {
+  uint32_t *counts = nullptr;
+  uint64_t *offsets = nullptr;
+  uint64_t *total = nullptr;
+  uint64_t capSegs = 0;
+  cudaError_t alloc(uint64_t maxTextBytes);
+  void release();
+};
+
+// everything on `stream`, nothing read back: the count stays in *dInfo
+int split_lines_async(const uint8_t *dText, uint64_t len, uint8_t delim,
+                      uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
+                      LineCount *dInfo, SplitScratch &scratch,
+                      cudaStream_t stream, std::string &why);
+
 int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
                 uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
                 uint64_t *nLinesOut, cudaStream_t stream, std::string &why);
 
 int compact_matches(const int32_t *dResults, uint64_t n, uint64_t *dIndices,
                     uint64_t *dCount, cudaStream_t stream, std::string &why);
+
+// as compact_matches, but the number of lines is read from device memory
+// (capLines is its upper bound) and the scratch is the caller's
+int compact_matches_n(const int32_t *dResults, uint64_t capLines, const uint64_t *dN,
+                      uint64_t *dIndices, uint64_t *dCount, SplitScratch &scratch,
+                      cudaStream_t stream, std::string &why);
 
 int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &img,
                  const LaunchGeometry &geo, const uint8_t *dText, uint64_t len,

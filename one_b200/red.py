@@ -33,6 +33,9 @@ langRegexRaw, langRegexAuto, langGlob, langExact = 1, 2, 3, 4
 # Serializer.h:37-43
 fmtDirect1, fmtDirect2, fmtDirect4, fmtDirectAuto = 1, 2, 4, 255
 
+LINE_MATCH_DTYPE = np.dtype([("line_start", "<u8"), ("line_len", "<u4"), ("result", "<i4"),
+                             ("match_start", "<u4"), ("match_end", "<u4")])
+
 Outcome = namedtuple("Outcome", ["result", "start", "end"])
 
 
@@ -120,6 +123,7 @@ def lib():
                                                   C.POINTER(u64), i32, vp]
         L.red_b200_compact_matches_device.argtypes = [vp, u64, vp, vp, i32, vp]
         L.red_b200_match_stream_device.argtypes = [vp, vp, u64, i32, i32, C.POINTER(_Outcome), vp]
+        L.red_b200_grep_host.argtypes = [vp, vp, u64, C.c_uint8, i32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.red_b200_compile.argtypes = [i32, C.POINTER(C.c_char_p), vp, vp, vp, vp, i32, u64,
                                        C.POINTER(vp), C.POINTER(u64)]
         L.red_b200_free.argtypes = [vp]
@@ -306,6 +310,22 @@ class Program:
                               res.data_ptr(), ms.data_ptr() if ms is not None else 0,
                               me.data_ptr() if me is not None else 0, st)
         return res, ms, me
+
+    def grep_host(self, text, delim=b"\n", style=styInstant, capacity=None):
+        """Log blob in (uint8 ndarray / bytes), matching lines out.
+
+        -> (records, n_lines): records is a structured array with fields
+        line_start, line_len, result, match_start, match_end, in text order."""
+        text = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) \
+            else np.ascontiguousarray(text, dtype=np.uint8)
+        if capacity is None:
+            capacity = max(16, text.size // 8)
+        out = np.zeros(capacity, dtype=LINE_MATCH_DTYPE)
+        nm, nl = C.c_uint64(), C.c_uint64()
+        d = delim[0] if isinstance(delim, (bytes, bytearray)) else int(delim)
+        _check(lib().red_b200_grep_host(self._h, text.ctypes.data, text.size, d, _style(style),
+                                        out.ctypes.data, capacity, C.byref(nm), C.byref(nl)))
+        return out[:nm.value], nl.value
 
     def match_stream_device(self, text, verb=VERB_MATCH, style=styLast, stream=None) -> Outcome:
         """One long torch uint8 CUDA tensor."""

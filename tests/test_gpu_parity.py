@@ -239,3 +239,34 @@ def test_style_and_verb_errors(gpu_red, vectors):
     with pytest.raises(gpu_red.RedExceptExec):
         prog.run(b"abc", 9, 4)
     prog.close()
+
+
+def test_grep_host_blob(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Log blob in, matching lines out: index + match + compaction on the GPU."""
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(70000, seed=31)
+    for piece in (None, "65536"):  # default pieces, and many small ones
+        if piece:
+            monkeypatch.setenv("RED_B200_HOST_CHUNK_BYTES", piece)
+        for sty in ("instant", "last"):
+            recs, n_lines = prog.grep_host(text, b"\n", sty)
+            eres, ems, eme = orc.batch(text, starts, lens, "match", sty)
+            hit = np.nonzero(eres > 0)[0]
+            assert n_lines == len(starts)
+            assert np.array_equal(recs["line_start"], starts[hit])
+            assert np.array_equal(recs["line_len"], lens[hit])
+            assert np.array_equal(recs["result"], eres[hit])
+            assert np.array_equal(recs["match_start"], ems[hit])
+            assert np.array_equal(recs["match_end"], eme[hit])
+    monkeypatch.delenv("RED_B200_HOST_CHUNK_BYTES")
+    # no trailing delimiter, empty lines, nothing matching, capacity too small
+    recs, n = prog.grep_host(b"a\n\nFailed password for x\n\nQuarantined", b"\n", "instant")
+    assert n == 5 and recs["line_start"].tolist() == [3, 26] and recs["result"].tolist() == [5, 15]
+    recs, n = prog.grep_host(b"nothing here\nnor here\n", b"\n", "instant")
+    assert n == 2 and len(recs) == 0
+    with pytest.raises(gpu_red.RedExceptLimit):
+        prog.grep_host(text, b"\n", "instant", capacity=10)
+    prog.close()
