@@ -162,6 +162,34 @@ int red_b200_match_batch_host(const red_b200_program *prog,
 int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
                    int verb, int style, red_b200_outcome *out);
 
+/* ---- per line, all matches: matchAll() and Red::collect() ----------------- */
+
+typedef struct {
+  int32_t  result;
+  uint32_t start;   /* relative to the line, as Outcome's are to the text */
+  uint32_t end;
+} red_b200_span;
+
+enum { RED_B200_MULTI_MATCH_ALL = 0,  /* matchAll(), Matcher.h:127             */
+       RED_B200_MULTI_COLLECT   = 1   /* Red::collect(), Red.h:109             */ };
+
+/* For every line: counts[i] outcomes were found; the first
+   min(counts[i], max_per_line) are in spans[i * max_per_line ...].
+   Device pointers; asynchronous on `stream`. */
+int red_b200_multi_batch_device(const red_b200_program *prog,
+                                const uint8_t *d_text, const uint64_t *d_starts,
+                                const uint32_t *d_lens, uint64_t n_lines,
+                                int which, uint32_t max_per_line,
+                                uint32_t *d_counts, red_b200_span *d_spans,
+                                void *stream);
+
+/* Same with host buffers.  Synchronous. */
+int red_b200_multi_batch_host(const red_b200_program *prog,
+                              const uint8_t *text, uint64_t text_len,
+                              const uint64_t *starts, const uint32_t *lens,
+                              uint64_t n_lines, int which, uint32_t max_per_line,
+                              uint32_t *counts, red_b200_span *spans);
+
 /* ---- line index and match compaction ----------------------------------- */
 
 /* Split d_text[0..text_len) at `delim` bytes: writes the start offset and the

@@ -582,6 +582,84 @@ int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
   return RED_B200_OK;
 }
 
+int red_b200_multi_batch_device(const red_b200_program *cprog,
+                                const uint8_t *d_text, const uint64_t *d_starts,
+                                const uint32_t *d_lens, uint64_t n_lines,
+                                int which, uint32_t max_per_line,
+                                uint32_t *d_counts, red_b200_span *d_spans,
+                                void *stream) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if ((which != RED_B200_MULTI_MATCH_ALL) && (which != RED_B200_MULTI_COLLECT))
+    return fail(RED_B200_EEXEC, "unsupported multi-match kind");
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!d_text || !d_starts || !d_lens || !d_counts || (max_per_line && !d_spans))
+    return fail(RED_B200_EAPI, "null buffer");
+  DeviceGuard guard(prog->device);
+  int launches = 0;
+  static_assert(sizeof(red_b200_span) == sizeof(MultiSpan), "span layout");
+  cudaError_t err = launch_batch_multi(prog->dev, prog->smemTable, d_text, d_starts, d_lens,
+                                       n_lines, which, max_per_line, d_counts,
+                                       reinterpret_cast<MultiSpan *>(d_spans), prog->geo,
+                                       static_cast<cudaStream_t>(stream), &launches);
+  if (err != cudaSuccess)
+    return cuda_fail(err, "multi-match kernel launch");
+  prog->launches += launches;
+  return RED_B200_OK;
+}
+
+int red_b200_multi_batch_host(const red_b200_program *cprog,
+                              const uint8_t *text, uint64_t text_len,
+                              const uint64_t *starts, const uint32_t *lens,
+                              uint64_t n_lines, int which, uint32_t max_per_line,
+                              uint32_t *counts, red_b200_span *spans) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!text || !starts || !lens || !counts || (max_per_line && !spans))
+    return fail(RED_B200_EAPI, "null buffer");
+  for (uint64_t i = 0; i < n_lines; ++i)
+    if (starts[i] + lens[i] > text_len)
+      return fail(RED_B200_EAPI, "line extends past end of text");
+  DeviceGuard guard(prog->device);
+  // simple staging: this entry point is for moderate batches (articles, lines)
+  uint8_t *dText = nullptr;
+  uint64_t *dStarts = nullptr;
+  uint32_t *dLens = nullptr, *dCounts = nullptr;
+  red_b200_span *dSpans = nullptr;
+  auto freeAll = [&]() {
+    cudaFree(dText); cudaFree(dStarts); cudaFree(dLens); cudaFree(dCounts); cudaFree(dSpans);
+  };
+  const size_t spanBytes = std::max<size_t>(1, n_lines * max_per_line) * sizeof(red_b200_span);
+  cudaError_t e;
+  if ((e = cudaMalloc(&dText, text_len + 64)) != cudaSuccess ||
+      (e = cudaMalloc(&dStarts, n_lines * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&dLens, n_lines * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dCounts, n_lines * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dSpans, spanBytes)) != cudaSuccess ||
+      (e = cudaMemcpy(dText, text, text_len, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(dStarts, starts, n_lines * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(dLens, lens, n_lines * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    freeAll();
+    return cuda_fail(e, "multi-match staging");
+  }
+  int rc = red_b200_multi_batch_device(prog, dText, dStarts, dLens, n_lines, which,
+                                       max_per_line, dCounts, dSpans, nullptr);
+  if (rc == RED_B200_OK) {
+    if ((e = cudaMemcpy(counts, dCounts, n_lines * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (max_per_line &&
+         (e = cudaMemcpy(spans, dSpans, n_lines * max_per_line * sizeof(red_b200_span),
+                         cudaMemcpyDeviceToHost)) != cudaSuccess))
+      rc = cuda_fail(e, "multi-match copy-out");
+  }
+  freeAll();
+  return rc;
+}
+
 int red_b200_split_lines_device(const uint8_t *d_text, uint64_t text_len,
                                 uint8_t delim, uint64_t capacity,
                                 uint64_t *d_starts, uint32_t *d_lens,

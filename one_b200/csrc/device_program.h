@@ -73,6 +73,20 @@ cudaError_t launch_batch_lanes(const ProgramDev &pd, bool smemTable,
                                unsigned long long *counter,
                                cudaStream_t stream, int *launches);
 
+// one outcome of matchAll()/collect(), positions relative to the line
+struct MultiSpan {
+  int32_t result;
+  uint32_t start;
+  uint32_t end;
+};
+
+// per line: all matches (kernels_multi.cu); which = 0 matchAll, 1 collect
+cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8_t *text,
+                               const uint64_t *starts, const uint32_t *lens, uint64_t nLines,
+                               int which, uint32_t maxPerLine, uint32_t *counts,
+                               MultiSpan *spans, const LaunchGeometry &geo,
+                               cudaStream_t stream, int *launches);
+
 // verbs scan/search (sliding start position)
 cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
                                  const BatchArgs &args, int style,

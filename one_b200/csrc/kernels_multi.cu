@@ -1,0 +1,174 @@
+/* kernels_multi.cu - per line, ALL matches instead of one:
+
+     which = 0  matchAll()       one anchored walk that reports every run of
+                                 positions with the same positive result
+                                 (reference: matchAllCore, Matcher.h:711-767)
+     which = 1  Red::collect()   repeated search<styLast> from just after the
+                                 previous match: all non-overlapping matches in
+                                 order (reference: lib/Red.cpp:108-122)
+
+   One lane per line; spans[line * maxPerLine + k] holds the k-th outcome,
+   counts[line] the number found (it can exceed maxPerLine; only the first
+   maxPerLine are stored - the caller sees that from the count).  Positions
+   are relative to the line, as Outcome's are to the text. */
+
+#include "device_program.h"
+#include "walk.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace red_b200 {
+
+namespace {
+
+using namespace dev;
+
+template <class Tab, class ClsT>
+__device__ __forceinline__ uint32_t match_all_line(const ProgramDev &pd, const Tab &tab,
+                                                   const ClsT *cls, const uint8_t *p,
+                                                   uint32_t len, uint32_t cap,
+                                                   MultiSpan *out) {
+  // the leader only gates (Matcher.h:724-729)
+  for (uint32_t ii = 0; ii < pd.leaderLen; ++ii)
+    if ((ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + ii)]))
+      return 0;
+  uint32_t v = pd.initV, cnt = 0, mstart = 0;
+  int32_t prev = 0;
+  for (uint32_t idx = 0; idx < len; ++idx) {
+    const uint32_t nv = tab.next(v, cls[__ldg(p + idx)]);
+    if ((v == pd.initV) && (nv != pd.initV))
+      mstart = idx;
+    v = nv;
+    if (v >= pd.acceptV) {
+      if (v >= pd.pureV)
+        break;
+      const int32_t r = pd.results[state_index(pd, v)];
+      if (r == prev) {
+        if (cnt - 1 < cap)
+          out[cnt - 1].end = idx + 1;
+      }
+      else {
+        prev = r;
+        if (cnt < cap) {
+          out[cnt].result = r;
+          out[cnt].start = mstart;
+          out[cnt].end = idx + 1;
+        }
+        ++cnt;
+      }
+    }
+    else
+      prev = 0;
+  }
+  return cnt;
+}
+
+template <class Tab, class ClsT>
+__device__ __forceinline__ uint32_t collect_line(const ProgramDev &pd, const Tab &tab,
+                                                 const ClsT *cls, const uint8_t *p,
+                                                 uint32_t len, uint32_t cap,
+                                                 MultiSpan *out) {
+  uint32_t cnt = 0, off = 0;
+  while (off < len) {
+    // search<styLast, false> on p[off..len)
+    int32_t result = 0;
+    uint32_t start = 0, end = 0;
+    for (uint32_t pos = off; (pos < len) && (result == 0); ++pos) {
+      Walk<STY_LAST, true> wk;
+      wk.begin(pd);
+      wk.mstart = pos;
+      wk.mend = pos;
+      for (uint32_t idx = pos; idx < len; ++idx)
+        if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
+          break;
+      wk.finish(pd, len, result, start, end);
+    }
+    if (result <= 0)
+      break;
+    if (cnt < cap) {
+      out[cnt].result = result;
+      out[cnt].start = start;
+      out[cnt].end = end;
+    }
+    ++cnt;
+    off = end;
+  }
+  return cnt;
+}
+
+template <bool SMEM, int K, class ClsT>
+__global__ void __launch_bounds__(256)
+batch_multi_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *starts,
+                   const uint32_t *lens, uint64_t nLines, int which,
+                   uint32_t maxPerLine, uint32_t *counts, MultiSpan *spans) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes
+                     : static_cast<const unsigned char *>(pd.table)};
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t line = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       line < nLines; line += stride) {
+    const uint8_t *p = text + starts[line];
+    const uint32_t len = lens[line];
+    MultiSpan *out = spans + line * maxPerLine;
+    counts[line] = (which == 0)
+        ? match_all_line(pd, tab, cls, p, len, maxPerLine, out)
+        : collect_line(pd, tab, cls, p, len, maxPerLine, out);
+  }
+}
+
+template <bool SMEM, int K, class ClsT>
+cudaError_t launch_multi(const ProgramDev &pd, const uint8_t *text, const uint64_t *starts,
+                         const uint32_t *lens, uint64_t nLines, int which,
+                         uint32_t maxPerLine, uint32_t *counts, MultiSpan *spans,
+                         const LaunchGeometry &geo, cudaStream_t stream) {
+  auto kern = batch_multi_kernel<SMEM, K, ClsT>;
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  cudaError_t err = cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess)
+    return err;
+  uint64_t perSm = SMEM ? std::max<uint64_t>(1, std::min<uint64_t>(4, (200u << 10) / smem)) : 4;
+  uint64_t grid = std::min<uint64_t>((nLines + 255) / 256, static_cast<uint64_t>(geo.smCount) * perSm);
+  if (grid == 0)
+    return cudaSuccess;
+  kern<<<static_cast<unsigned>(grid), 256, smem, stream>>>(pd, text, starts, lens, nLines, which,
+                                                           maxPerLine, counts, spans);
+  return cudaGetLastError();
+}
+
+} // anonymous
+
+cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8_t *text,
+                               const uint64_t *starts, const uint32_t *lens, uint64_t nLines,
+                               int which, uint32_t maxPerLine, uint32_t *counts,
+                               MultiSpan *spans, const LaunchGeometry &geo,
+                               cudaStream_t stream, int *launches) {
+  const bool cls8 = pd.clsMaxOffset < 256;
+  cudaError_t err;
+#define GO(S, KK, CT) launch_multi<S, KK, CT>(pd, text, starts, lens, nLines, which, maxPerLine, counts, spans, geo, stream)
+  if (smemTable) {
+    if (pd.unitShift == 0)
+      err = cls8 ? GO(true, 1, uint8_t) : GO(true, 1, uint16_t);
+    else if (pd.unitShift == 1)
+      err = cls8 ? GO(true, 2, uint8_t) : GO(true, 2, uint16_t);
+    else if (pd.unitShift == 8)
+      err = GO(true, 9, uint16_t);
+    else
+      err = cudaErrorInvalidValue;
+  }
+  else
+    err = cls8 ? GO(false, 0, uint8_t) : GO(false, 0, uint16_t);
+#undef GO
+  if ((err == cudaSuccess) && launches && nLines)
+    *launches += 1;
+  return err;
+}
+
+} // namespace red_b200

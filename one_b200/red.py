@@ -36,6 +36,8 @@ fmtDirect1, fmtDirect2, fmtDirect4, fmtDirectAuto = 1, 2, 4, 255
 LINE_MATCH_DTYPE = np.dtype([("line_start", "<u8"), ("line_len", "<u4"), ("result", "<i4"),
                              ("match_start", "<u4"), ("match_end", "<u4")])
 
+SPAN_DTYPE = np.dtype([("result", "<i4"), ("start", "<u4"), ("end", "<u4")])
+
 Outcome = namedtuple("Outcome", ["result", "start", "end"])
 
 
@@ -123,6 +125,8 @@ def lib():
                                                   C.POINTER(u64), i32, vp]
         L.red_b200_compact_matches_device.argtypes = [vp, u64, vp, vp, i32, vp]
         L.red_b200_match_stream_device.argtypes = [vp, vp, u64, i32, i32, C.POINTER(_Outcome), vp]
+        L.red_b200_multi_batch_device.argtypes = [vp, vp, vp, vp, u64, i32, C.c_uint32, vp, vp, vp]
+        L.red_b200_multi_batch_host.argtypes = [vp, vp, u64, vp, vp, u64, i32, C.c_uint32, vp, vp]
         L.red_b200_grep_host.argtypes = [vp, vp, u64, C.c_uint8, i32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.red_b200_compile.argtypes = [i32, C.POINTER(C.c_char_p), vp, vp, vp, vp, i32, u64,
                                        C.POINTER(vp), C.POINTER(u64)]
@@ -310,6 +314,33 @@ class Program:
                               res.data_ptr(), ms.data_ptr() if ms is not None else 0,
                               me.data_ptr() if me is not None else 0, st)
         return res, ms, me
+
+    def multi_batch_host(self, text, starts, lens, which="collect", max_per_line=16):
+        """Per line all matches: which = 'match_all' (matchAll, Matcher.h:127) or
+        'collect' (Red::collect, Red.h:109).  -> (counts uint32[n], spans[n, max])."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = len(starts)
+        counts = np.zeros(n, dtype=np.uint32)
+        spans = np.zeros((n, max_per_line), dtype=SPAN_DTYPE)
+        kind = {"match_all": 0, "collect": 1}[which] if isinstance(which, str) else int(which)
+        _check(lib().red_b200_multi_batch_host(self._h, text.ctypes.data, text.size, starts.ctypes.data,
+                                               lens.ctypes.data, n, kind, max_per_line,
+                                               counts.ctypes.data, spans.ctypes.data))
+        return counts, spans
+
+    def collect(self, text, cap=256):
+        """Red::collect on one text -> list of Outcome."""
+        t = np.frombuffer(_bytes(text), dtype=np.uint8)
+        c, s = self.multi_batch_host(t, [0], [len(t)], "collect", cap)
+        return [Outcome(int(x["result"]), int(x["start"]), int(x["end"])) for x in s[0][:min(int(c[0]), cap)]]
+
+    def matchAll(self, text, cap=256):
+        """matchAll on one text -> list of Outcome."""
+        t = np.frombuffer(_bytes(text), dtype=np.uint8)
+        c, s = self.multi_batch_host(t, [0], [len(t)], "match_all", cap)
+        return [Outcome(int(x["result"]), int(x["start"]), int(x["end"])) for x in s[0][:min(int(c[0]), cap)]]
 
     def grep_host(self, text, delim=b"\n", style=styInstant, capacity=None):
         """Log blob in (uint8 ndarray / bytes), matching lines out.

@@ -78,6 +78,9 @@ class Oracle:
             lib.red_oracle_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_uint64, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.red_oracle_match_all.restype = C.c_uint64
+            lib.red_oracle_match_all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
             lib.red_oracle_collect.restype = C.c_uint64
             lib.red_oracle_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                                C.c_void_p, C.c_void_p, C.c_void_p]
@@ -132,6 +135,15 @@ class Oracle:
                                     n, VERBS.get(verb, verb), STYLES.get(style, style), int(do_leader),
                                     res.ctypes.data, so.ctypes.data, eo.ctypes.data)
         return res, so, eo
+
+    def match_all(self, text: bytes, cap=4096):
+        res = np.zeros(cap, dtype=np.int32)
+        st = np.zeros(cap, dtype=np.uint64)
+        en = np.zeros(cap, dtype=np.uint64)
+        n = self.lib().red_oracle_match_all(self._h, _u8ptr(text), len(text), cap,
+                                            res.ctypes.data, st.ctypes.data, en.ctypes.data)
+        n = min(n, cap)
+        return [(int(res[i]), int(st[i]), int(en[i])) for i in range(n)]
 
     def collect(self, text: bytes, cap=4096):
         res = np.zeros(cap, dtype=np.int32)

@@ -390,3 +390,62 @@ uint64_t red_oracle_collect(const red_oracle_prog *pg, const void *text,
   }
   return cnt;
 }
+
+/* matchAll(): one anchored walk that reports every run of positions with the
+   same positive result (Matcher.h:711-767; called with the leader on, which
+   only gates - a text that does not begin with the leader yields nothing).
+   Returns the number found; stores at most cap of them. */
+#define DEFINE_MATCH_ALL(SFX, T)                                              \
+  static uint64_t match_all_##SFX(const red_oracle_prog *pg, const uint8_t *t,\
+                                  uint64_t len, uint64_t cap, int32_t *results,\
+                                  uint64_t *starts, uint64_t *ends) {         \
+    const uint64_t init = pg->initialOff;                                     \
+    uint64_t s = init, cnt = 0, mstart = 0;                                   \
+    int32_t prev = 0;                                                         \
+    for (uint64_t idx = 0; idx < len; ++idx) {                                \
+      uint64_t nx = step_##SFX(pg, s, pg->equiv[t[idx]]);                     \
+      if ((s == init) && (nx != s))                                           \
+        mstart = idx;                                                         \
+      s = nx;                                                                 \
+      T head = rowhead_##SFX(pg, s);                                          \
+      int32_t result = res_##SFX(head);                                       \
+      if (result > 0) {                                                       \
+        if (result == prev) {                                                 \
+          if (cnt - 1 < cap)                                                  \
+            ends[cnt - 1] = idx + 1;                                          \
+        }                                                                     \
+        else {                                                                \
+          prev = result;                                                      \
+          if (cnt < cap) {                                                    \
+            results[cnt] = result;                                            \
+            starts[cnt] = mstart;                                             \
+            ends[cnt] = idx + 1;                                              \
+          }                                                                   \
+          ++cnt;                                                              \
+        }                                                                     \
+      }                                                                       \
+      else {                                                                  \
+        if (pure_dead_##SFX(head))                                            \
+          break;                                                              \
+        prev = 0;                                                             \
+      }                                                                       \
+    }                                                                         \
+    return cnt;                                                               \
+  }
+
+DEFINE_MATCH_ALL(1, uint8_t)
+DEFINE_MATCH_ALL(2, uint16_t)
+DEFINE_MATCH_ALL(4, uint32_t)
+
+uint64_t red_oracle_match_all(const red_oracle_prog *pg, const void *text,
+                              uint64_t len, uint64_t cap, int32_t *results,
+                              uint64_t *starts, uint64_t *ends) {
+  const uint8_t *t = (const uint8_t *)text;
+  if (!leader_at(pg, t, 0, len, NULL))
+    return 0;
+  switch (pg->fmt) {
+  case 1: return match_all_1(pg, t, len, cap, results, starts, ends);
+  case 2: return match_all_2(pg, t, len, cap, results, starts, ends);
+  default: return match_all_4(pg, t, len, cap, results, starts, ends);
+  }
+}

@@ -270,3 +270,39 @@ def test_grep_host_blob(gpu_red, vectors, oracle_cls, monkeypatch):
     with pytest.raises(gpu_red.RedExceptLimit):
         prog.grep_host(text, b"\n", "instant", capacity=10)
     prog.close()
+
+
+def test_match_all_and_collect(gpu_red, oracle_cls):
+    """Per line all matches: matchAll() and Red::collect() against the reference's
+    outputs (fixture) and against the oracle on a seeded corpus."""
+    import json, os
+    from conftest import GOLDEN
+    from one_b200 import synth
+    with open(os.path.join(GOLDEN, "ref_multi.json")) as f:
+        doc = json.load(f)
+    for case in doc["cases"]:
+        blob = unz(case["program"])
+        prog = gpu_red.Program(blob)
+        texts = [unb64(t) for t in case["texts"]]
+        text, starts, lens = pack(texts, lead=b"##")
+        for which in ("match_all", "collect"):
+            counts, spans = prog.multi_batch_host(text, starts, lens, which, max_per_line=24)
+            for i, exp in enumerate(case[which]):
+                assert counts[i] == len(exp), (case["name"], which, texts[i])
+                got = [[int(s["result"]), int(s["start"]), int(s["end"])] for s in spans[i][:counts[i]]]
+                assert got == exp, (case["name"], which, texts[i])
+        # the single-text conveniences
+        assert [list(o) for o in prog.collect(texts[0])] == case["collect"][0]
+        assert [list(o) for o in prog.matchAll(texts[0])] == case["match_all"][0]
+        prog.close()
+    # capped output: counts say how many there were
+    case = next(c for c in doc["cases"] if c["name"] == "cities")
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    lines = [b" ".join([b"tokyo", b"new york", b"x"] * 5)] * 100
+    text, starts, lens = pack(lines)
+    counts, spans = prog.multi_batch_host(text, starts, lens, "collect", max_per_line=3)
+    exp = orc.collect(lines[0])
+    assert (counts == len(exp)).all() and len(exp) == 10
+    assert [[int(s["result"]), int(s["start"]), int(s["end"])] for s in spans[7]] == [list(x) for x in exp[:3]]
+    prog.close()

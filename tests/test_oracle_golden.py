@@ -108,3 +108,19 @@ def test_oracle_matches_live_reference(vectors, oracle_cls, ref_cls):
             for verb in VERBS:
                 for sty in STYLES:
                     assert o.run(t, verb, sty) == r.run(t, verb, sty)
+
+
+def test_match_all_and_collect_vectors(oracle_cls):
+    import json, os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_multi.json")) as f:
+        doc = json.load(f)
+    n = 0
+    for case in doc["cases"]:
+        o = oracle_cls(unz(case["program"]))
+        for t, ma, co in zip(case["texts"], case["match_all"], case["collect"]):
+            t = unb64(t)
+            assert [list(x) for x in o.match_all(t)] == ma, (case["name"], t)
+            assert [list(x) for x in o.collect(t)] == co, (case["name"], t)
+            n += 1
+    assert n > 100

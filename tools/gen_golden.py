@@ -289,7 +289,42 @@ def gen_vectors():
     print("ref_vectors.json: %d cases, %d bytes" % (len(cases), os.path.getsize(path)))
 
 
+def gen_multi():
+    """matchAll() (Matcher.h:127) and Red::collect() (Red.h:109) outputs."""
+    rng = np.random.RandomState(424242)
+    cases = []
+
+    def add(name, rules, texts):
+        prog = RefLib.compile(rules)
+        ref = RefLib(prog)
+        cases.append({"name": name, "rules": [rule_json(r) for r in rules], "program": zb64(prog),
+                      "texts": [b64(t) for t in texts],
+                      "match_all": [ref.multi(t, "match_all") for t in texts],
+                      "collect": [ref.multi(t, "collect") for t in texts]})
+
+    # the two matchAll tests of test/matcher.cpp
+    add("matcher_cpp_matchAll", [("0", 1, 0), ("0123", 2, 0), ("[0-2]+", 3, 0), ("[3-9]+", 4, 0), ("012345", 5, 0)],
+        [b"0123456789", b"", b"0", b"9", b"01", b"33012"])
+    add("matcher_cpp_matchAllLoose", [("a+", 1, F_LOOSE_START), ("b+", 2, F_LOOSE_START)],
+        [b".aa..b.bb..abba.", b"", b"ab", b"....", b"bbbb"])
+    cities = [("tokyo", 1, F_IGNORE_CASE), ("new", 2, F_IGNORE_CASE), ("new york", 3, F_IGNORE_CASE),
+              ("york", 4, F_IGNORE_CASE), ("sao paulo", 5, F_IGNORE_CASE), ("ab+", 6, 0)]
+    texts = [bytes(rng.choice(list(b"new york tokyoabb NEW sao paulo"), size=rng.randint(0, 60)).astype(np.uint8))
+             for _ in range(60)]
+    texts += [b"I love New York and Tokyo, not Sao Paulo.", b"newnewnew yorkyork", b"abbbabab"]
+    add("cities", cities, texts)
+    add("union64_lines", synth.rules_union64(), synth.make_lines(80, seed=5))
+    add("leader", [("foo[0-9]+", 1, 0)], [b"foo1", b"xfoo12foo3", b"foofoo9", b"", b"fo"])
+    doc = {"generator": "tools/gen_golden.py", "cases": cases}
+    path = os.path.join(OUT_DIR, "ref_multi.json")
+    with open(path, "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("ref_multi.json: %d cases, %d bytes" % (len(cases), os.path.getsize(path)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT_DIR, exist_ok=True)
-    gen_kat()
-    gen_vectors()
+    if "--multi-only" not in sys.argv:
+        gen_kat()
+        gen_vectors()
+    gen_multi()
