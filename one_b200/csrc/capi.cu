@@ -326,7 +326,7 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
   if ((verb == RED_B200_VERB_CHECK) || (verb == RED_B200_VERB_MATCH)) {
     BatchArgs a = args;
     a.checkLeader = (verb == RED_B200_VERB_CHECK) && (prog->dev.leaderLen > 0);
-    if (prog->tune.variant == 1)
+    if (prog->tune.variant == 1)  // v1 tile kernel, kept as the A/B baseline
       err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
                                   prog->geo, prog->tune, stream, &launches);
     else {

@@ -53,7 +53,8 @@ struct BatchTuning {
   int threads = 0;      // 0 = pick
   int ctasPerSm = 0;    // 0 = pick
   bool simpleWalk = false;  // per-byte decisions only (A/B baseline)
-  int variant = 0;      // 0 = persistent lanes (production), 1 = tile per CTA (v1)
+  int variant = 0;      // 0 = tile schedule (production), 3 = persistent lanes,
+                        // 1 = first kernel (kernels.cu), kept as the A/B baseline
   int linesPerLane = 0; // persistent lanes: lines per lane per claimed block (0 = pick)
 };
 

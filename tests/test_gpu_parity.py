@@ -93,14 +93,36 @@ def test_synthetic_corpus_vs_oracle(gpu_red, vectors, oracle_cls, name):
     prog.close()
 
 
+def test_kernel_variants_agree(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Persistent-lane schedule (variant 3) and first kernel (variant 1): same answers."""
+    from one_b200 import synth
+    text, starts, lens = synth.make_corpus(30000, seed=13)
+    for name in ("union64", "single_auto", "leader_class"):
+        blob = unz(next(c for c in vectors["cases"] if c["name"] == name)["program"])
+        orc = oracle_cls(blob)
+        for variant in ("3", "1"):
+            monkeypatch.setenv("RED_B200_VARIANT", variant)
+            prog = gpu_red.Program(blob)
+            monkeypatch.delenv("RED_B200_VARIANT")
+            for verb in ("check", "match"):
+                for sty in STYLES:
+                    res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+                    eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+                    assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), \
+                        (name, variant, verb, sty)
+            prog.close()
+
+
 def test_simple_walk_variant_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
     """The per-byte-decision kernel (A/B baseline) gives the same answers."""
     from one_b200 import synth
     case = next(c for c in vectors["cases"] if c["name"] == "union64")
     blob = unz(case["program"])
     monkeypatch.setenv("RED_B200_SIMPLE_WALK", "1")
+    monkeypatch.setenv("RED_B200_VARIANT", "1")
     prog = gpu_red.Program(blob)
     monkeypatch.delenv("RED_B200_SIMPLE_WALK")
+    monkeypatch.delenv("RED_B200_VARIANT")
     orc = oracle_cls(blob)
     text, starts, lens = synth.make_corpus(20000, seed=3)
     for sty in STYLES:

@@ -27,7 +27,7 @@ def main():
     sts = torch.empty(n, dtype=torch.int32, device=dev)
     print("lines", n, "bytes %.2f GB" % (nbytes / 1e9), flush=True)
     envs = []
-    cfgs = os.environ.get("SWEEP", "v0,v1").split(",")
+    cfgs = os.environ.get("SWEEP", "v0,v3,v1").split(",")
     for c in cfgs:
         env = {"RED_B200_THREADS": "1024", "RED_B200_CTAS_PER_SM": "1", "RED_B200_SIMPLE_WALK": "0",
                "RED_B200_VARIANT": "0", "RED_B200_LINES_PER_LANE": "0"}
@@ -36,6 +36,8 @@ def main():
                 env["RED_B200_VARIANT"] = "0"
             elif kv == "v1":
                 env["RED_B200_VARIANT"] = "1"
+            elif kv == "v3":
+                env["RED_B200_VARIANT"] = "3"
             elif kv.startswith("T"):
                 env["RED_B200_LINES_PER_LANE"] = kv[1:]
             elif kv.startswith("thr"):
