@@ -4,6 +4,8 @@
 
 #include "compile.h"
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 
@@ -23,13 +25,28 @@ int compile_patterns(int n, const char *const *patterns,
     for (int i = 0; i < n; ++i)
       parser.add(langs[i], reinterpret_cast<const uint8_t *>(patterns[i]),
                  patternLens[i], results[i], flags[i]);
+    const bool timing = getenv("RED_B200_COMPILE_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+      if (!timing)
+        return;
+      auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "red_b200 compile: %s %.3f s\n", what,
+              std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+    };
+    lap("parse");
     rx::Nfa &nfa = parser.finish();
+    lap("finish");
     rx::RawDfa raw = rx::determinize(nfa, budget);
+    lap("determinize");
     const char *env = getenv("RED_B200_MINIMIZE");
     rx::MinimizeMode mode = (env && (std::string(env) == "exact"))
         ? rx::kMinimizeExact : rx::kMinimizeLikeReference;
     rx::MinDfa min = rx::minimize(raw, mode);
+    lap("minimize");
     out = rx::serialize(min, format);
+    lap("serialize");
     return RED_B200_OK;
   }
   catch (const rx::CompileError &ex) {

@@ -22,7 +22,10 @@
 #include "dfa.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <deque>
 #include <map>
 #include <set>
@@ -49,81 +52,262 @@ struct VecHash {
 
 } // anonymous
 
+/* Subset construction (reference: lib/Powerset.cpp:40-180 builds the same
+   automaton with per-byte multi-char sets; the numbering below - error 0,
+   initial 1, then in order of discovery by ascending byte - is the same).
+
+   Two things keep it fast on rule sets with thousands of loose-start rules,
+   where every subset contains the same few thousand looping nodes:
+
+   * bytes that no edge of the NFA tells apart are stepped once (NFA-level
+     byte classes, usually a few dozen);
+   * a subset is held as (core, rest): `core` is an interned set of
+     PERSISTENT nodes - nodes that loop to themselves on every byte and
+     therefore never leave a subset once in - and `rest` the other members.
+     What a core contributes to the step on each class is computed once per
+     core; per subset only `rest`, a handful of nodes, is walked.  */
 RawDfa determinize(const Nfa &nfa, uint64_t budget) {
   RawDfa dfa;
-  std::unordered_map<std::vector<NodeId>, uint32_t, VecHash> ids;
-  std::vector<std::vector<NodeId>> subsets;
-  auto intern = [&](std::vector<NodeId> &&s) -> uint32_t {
-    auto it = ids.find(s);
+  const size_t nNodes = nfa.size();
+
+  // --- NFA-level byte classes, numbered by first byte
+  unsigned clsOf[256];
+  std::vector<unsigned> rep;
+  {
+    std::map<std::vector<uint64_t>, int> distinct;
+    for (size_t id = 0; id < nNodes; ++id)
+      for (const Edge &e : nfa[static_cast<NodeId>(id)].out)
+        if (!e.on.empty())
+          distinct.emplace(std::vector<uint64_t>(e.on.w, e.on.w + 4), 0);
+    const size_t words = (distinct.size() + 63) / 64;
+    std::vector<std::vector<uint64_t>> sig(256, std::vector<uint64_t>(words, 0));
+    size_t k = 0;
+    for (auto &kv : distinct) {
+      for (unsigned c = 0; c < 256; ++c)
+        if ((kv.first[c >> 6] >> (c & 63)) & 1)
+          sig[c][k >> 6] |= 1ull << (k & 63);
+      ++k;
+    }
+    std::map<std::vector<uint64_t>, unsigned> seen;
+    for (unsigned c = 0; c < 256; ++c) {
+      auto it = seen.find(sig[c]);
+      if (it == seen.end()) {
+        it = seen.emplace(sig[c], static_cast<unsigned>(rep.size())).first;
+        rep.push_back(c);
+      }
+      clsOf[c] = it->second;
+    }
+  }
+  const unsigned C = static_cast<unsigned>(rep.size());
+
+  // --- per node: targets per class (CSR), smallest end mark, persistence
+  struct Fanout {
+    int32_t mark = 0;
+    bool persistent = false;
+    std::vector<uint32_t> begin;  // C + 1
+    std::vector<NodeId> to;
+  };
+  std::vector<Fanout> fan(nNodes);
+  std::vector<char> built(nNodes, 0);
+  auto fanout = [&](NodeId id) -> const Fanout & {
+    Fanout &f = fan[id];
+    if (!built[id]) {
+      built[id] = 1;
+      std::vector<std::pair<uint32_t, NodeId>> pairs;
+      for (const Edge &e : nfa[id].out) {
+        if (e.endMark > 0)
+          f.mark = f.mark ? std::min(f.mark, e.endMark) : e.endMark;
+        if (e.on.empty())
+          continue;
+        for (unsigned c = 0; c < C; ++c)
+          if (e.on.has(rep[c]))
+            pairs.emplace_back(c, e.to);
+      }
+      std::sort(pairs.begin(), pairs.end());
+      pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+      f.begin.assign(C + 1, 0);
+      for (auto &pr : pairs)
+        ++f.begin[pr.first + 1];
+      for (unsigned c = 0; c < C; ++c)
+        f.begin[c + 1] += f.begin[c];
+      f.to.reserve(pairs.size());
+      unsigned selfLoops = 0;
+      for (auto &pr : pairs) {
+        f.to.push_back(pr.second);
+        selfLoops += (pr.second == id);
+      }
+      f.persistent = (selfLoops == C);
+    }
+    return f;
+  };
+
+  // --- interned cores
+  struct CoreStep {
+    uint32_t core = 0;           // persistent targets, as a core id
+    std::vector<NodeId> loose;   // the other targets, sorted
+  };
+  struct Core {
+    std::vector<NodeId> nodes;   // sorted
+    bool stepped = false;
+    int32_t mark = 0, plain = 0;
+    std::vector<CoreStep> step;  // per class
+  };
+  std::vector<Core> cores;
+  std::unordered_map<std::vector<NodeId>, uint32_t, VecHash> coreIds;
+  auto internCore = [&](std::vector<NodeId> &&nodes) -> uint32_t {
+    auto it = coreIds.find(nodes);
+    if (it != coreIds.end())
+      return it->second;
+    uint32_t id = static_cast<uint32_t>(cores.size());
+    coreIds.emplace(nodes, id);
+    cores.emplace_back();
+    cores.back().nodes = std::move(nodes);
+    return id;
+  };
+  internCore({});  // core 0: no persistent members
+
+  // splits a sorted node list into persistent and other members
+  auto split = [&](const std::vector<NodeId> &all, std::vector<NodeId> &pers,
+                   std::vector<NodeId> &loose) {
+    pers.clear();
+    loose.clear();
+    for (NodeId id : all)
+      (fanout(id).persistent ? pers : loose).push_back(id);
+  };
+  std::vector<NodeId> tmpA, tmpB, tmpC;
+  auto stepCore = [&](uint32_t coreId) {
+    if (cores[coreId].stepped)
+      return;
+    std::vector<NodeId> members = cores[coreId].nodes;  // cores may grow below
+    int32_t mark = 0, plain = 0;
+    for (NodeId id : members) {
+      const Fanout &f = fanout(id);
+      if (f.mark)
+        mark = mark ? std::min(mark, f.mark) : f.mark;
+      if (nfa[id].result > 0)
+        plain = plain ? std::min(plain, nfa[id].result) : nfa[id].result;
+    }
+    std::vector<CoreStep> step(C);
+    for (unsigned c = 0; c < C; ++c) {
+      tmpA.clear();
+      for (NodeId id : members) {
+        const Fanout &f = fan[id];
+        tmpA.insert(tmpA.end(), f.to.begin() + f.begin[c], f.to.begin() + f.begin[c + 1]);
+      }
+      std::sort(tmpA.begin(), tmpA.end());
+      tmpA.erase(std::unique(tmpA.begin(), tmpA.end()), tmpA.end());
+      split(tmpA, tmpB, step[c].loose);
+      step[c].core = internCore(std::move(tmpB));
+      tmpB = std::vector<NodeId>();
+    }
+    Core &core = cores[coreId];
+    core.mark = mark;
+    core.plain = plain;
+    core.step = std::move(step);
+    core.stepped = true;
+  };
+
+  // --- subsets, keyed by (core id, rest)
+  struct Subset {
+    uint32_t core;
+    std::vector<NodeId> rest;
+  };
+  std::vector<Subset> subsets;
+  std::unordered_map<std::vector<NodeId>, uint32_t, VecHash> ids;  // key: rest + core id
+  std::vector<NodeId> key;
+  auto intern = [&](uint32_t core, const std::vector<NodeId> &rest) -> uint32_t {
+    key = rest;
+    key.push_back(static_cast<NodeId>(core));
+    auto it = ids.find(key);
     if (it != ids.end())
       return it->second;
     uint32_t id = static_cast<uint32_t>(subsets.size());
     if (nfa.statesUsed() + id + 1 > budget)
       fail_limit("state budget exceeded");
-    ids.emplace(s, id);
-    subsets.emplace_back(std::move(s));
+    ids.emplace(key, id);
+    subsets.push_back(Subset{core, rest});
     return id;
   };
-  intern({});                    // 0: the error state
-  intern({nfa.initial()});       // 1: the initial state
+  intern(0, {});  // 0: the error state
+  {
+    std::vector<NodeId> init{nfa.initial()}, pers, loose;
+    split(init, pers, loose);
+    intern(internCore(std::move(pers)), loose);  // 1: the initial state
+  }
 
-  std::vector<const Edge *> edges;
-  std::vector<uint32_t> sigOf(256);
+  std::vector<NodeId> R, Rp, Rl, newRest, merged, lastRest;
+  std::vector<uint32_t> rowC(C);
   for (uint32_t cur = 1; cur < subsets.size(); ++cur) {
-    edges.clear();
-    int32_t result = 0;
-    bool marked = false;
-    int32_t plain = 0;
-    {
-      const std::vector<NodeId> &S = subsets[cur];
-      for (NodeId id : S) {
-        const Node &n = nfa[id];
-        if (n.result > 0)
-          plain = plain ? std::min(plain, n.result) : n.result;
-        for (const Edge &e : n.out) {
-          if (e.endMark > 0) {
-            result = marked ? std::min(result, e.endMark) : e.endMark;
-            marked = true;
-          }
-          if (!e.on.empty())
-            edges.push_back(&e);
-        }
-      }
+    const uint32_t coreId = subsets[cur].core;
+    const std::vector<NodeId> rest = subsets[cur].rest;  // copy: intern() may reallocate
+    stepCore(coreId);
+    int32_t result = cores[coreId].mark, plain = cores[coreId].plain;
+    for (NodeId id : rest) {
+      const Fanout &f = fanout(id);
+      if (f.mark)
+        result = result ? std::min(result, f.mark) : f.mark;
+      if (nfa[id].result > 0)
+        plain = plain ? std::min(plain, nfa[id].result) : nfa[id].result;
     }
     dfa.result.resize(subsets.size(), 0);
-    dfa.result[cur] = marked ? result : plain;
+    dfa.result[cur] = result ? result : plain;
 
-    // bytes enabled on the same set of edges go to the same target
-    dfa.next.resize(subsets.size() * 256, 0);
-    std::map<std::vector<uint32_t>, uint32_t> targetOf;  // edge-index set -> dfa state
-    std::vector<uint32_t> sig;
-    for (unsigned c = 0; c < 256; ++c) {
-      sig.clear();
-      for (uint32_t i = 0; i < edges.size(); ++i)
-        if (edges[i]->on.has(c))
-          sig.push_back(i);
-      uint32_t tgt = 0;
-      if (!sig.empty()) {
-        auto it = targetOf.find(sig);
-        if (it != targetOf.end())
-          tgt = it->second;
-        else {
-          std::vector<NodeId> T;
-          for (uint32_t i : sig)
-            T.push_back(edges[i]->to);
-          std::sort(T.begin(), T.end());
-          T.erase(std::unique(T.begin(), T.end()), T.end());
-          tgt = intern(std::move(T));
-          targetOf.emplace(sig, tgt);
+    uint32_t lastCore = 0, lastId = 0;
+    bool haveLast = false;
+    for (unsigned c = 0; c < C; ++c) {
+      R.clear();
+      for (NodeId id : rest) {
+        const Fanout &f = fan[id];
+        R.insert(R.end(), f.to.begin() + f.begin[c], f.to.begin() + f.begin[c + 1]);
+      }
+      uint32_t newCore = cores[coreId].step[c].core;
+      const std::vector<NodeId> *looseOfCore = &cores[coreId].step[c].loose;
+      const std::vector<NodeId> *nr = looseOfCore;
+      if (!R.empty()) {
+        std::sort(R.begin(), R.end());
+        R.erase(std::unique(R.begin(), R.end()), R.end());
+        split(R, Rp, Rl);
+        if (!Rp.empty()) {
+          const std::vector<NodeId> &have = cores[newCore].nodes;
+          if (!std::includes(have.begin(), have.end(), Rp.begin(), Rp.end())) {
+            merged.clear();
+            std::set_union(have.begin(), have.end(), Rp.begin(), Rp.end(),
+                           std::back_inserter(merged));
+            newCore = internCore(std::move(merged));
+            merged = std::vector<NodeId>();
+            looseOfCore = &cores[coreId].step[c].loose;  // cores may have moved
+            nr = looseOfCore;
+          }
+        }
+        if (!Rl.empty()) {
+          newRest.clear();
+          std::set_union(looseOfCore->begin(), looseOfCore->end(), Rl.begin(), Rl.end(),
+                         std::back_inserter(newRest));
+          nr = &newRest;
         }
       }
-      sigOf[c] = tgt;
+      if (haveLast && (newCore == lastCore) && (*nr == lastRest)) {
+        rowC[c] = lastId;
+        continue;
+      }
+      lastRest = *nr;
+      lastCore = newCore;
+      lastId = intern(newCore, lastRest);
+      haveLast = true;
+      rowC[c] = lastId;
     }
     dfa.next.resize(subsets.size() * 256, 0);
-    for (unsigned c = 0; c < 256; ++c)
-      dfa.next[static_cast<size_t>(cur) * 256 + c] = sigOf[c];
+    for (unsigned b = 0; b < 256; ++b)
+      dfa.next[static_cast<size_t>(cur) * 256 + b] = rowC[clsOf[b]];
   }
   dfa.n = static_cast<uint32_t>(subsets.size());
+  if (getenv("RED_B200_COMPILE_TIMING")) {
+    size_t tot = 0;
+    for (auto &v : subsets)
+      tot += v.rest.size();
+    fprintf(stderr, "red_b200 determinize: nfa %zu classes %u subsets %zu cores %zu rest members %zu\n",
+            nNodes, C, subsets.size(), cores.size(), tot);
+  }
   dfa.result.resize(dfa.n, 0);
   dfa.next.resize(static_cast<size_t>(dfa.n) * 256, 0);
   return dfa;
