@@ -8,6 +8,7 @@
 #include "../../include/red_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,10 +48,19 @@ int cuda_fail(cudaError_t err, const char *what) {
   } while (0)
 
 bool usable_device(int dev) {
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+  // asked on every call: cached (cudaGetDeviceProperties takes milliseconds)
+  static std::atomic<int> known[64];  // 0 unknown, 1 usable, 2 not
+  if ((dev < 0) || (dev >= 64))
     return false;
-  return prop.major == 10;  // sm_100a code only
+  int k = known[dev].load(std::memory_order_relaxed);
+  if (k == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      return false;
+    k = (major == 10) ? 1 : 2;  // sm_100a code only
+    known[dev].store(k, std::memory_order_relaxed);
+  }
+  return k == 1;
 }
 
 bool valid_style(int style) { return (style >= 1) && (style <= 5); }

@@ -35,8 +35,7 @@
    Semantics per line are those of matchCore/checkCore (Matcher.h:363-495).
  */
 
-#include "device_program.h"
-#include "walk.cuh"
+#include "chunk_engine.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -46,189 +45,6 @@ namespace red_b200 {
 namespace {
 
 using namespace dev;
-
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-  uint32_t r;
-  asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
-  uint32_t r;
-  asm("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
-  return r;
-}
-
-/* Fast-pass policies.  The state is carried in an "encoded" form so that the
-   address of the next table entry is one add away.
-
-   SmemFast8 (table in shared memory, class offsets fit a byte): the encoded
-   state is the shared-memory address of its row; the class table sits on a
-   256-byte boundary so that PRMT builds its address from the text byte and
-   the table base in one instruction.  One step is
-       PRMT, LDS.U8, IADD, LDS.U16, LEA
-   GenericFast: plain accessors (global table, or > 128 classes). */
-template <int K> struct SmemFast8 {
-  uint32_t clsBase;  // shared address, low byte zero
-  uint32_t tBase;    // shared address of the transition table
-  __device__ __forceinline__ uint32_t enc(uint32_t v) const { return (v << K) + tBase; }
-  __device__ __forceinline__ uint32_t dec(uint32_t e) const { return (e - tBase) >> K; }
-  __device__ __forceinline__ uint32_t encLimit(uint32_t lim) const { return lim ? enc(lim) : 0; }
-  __device__ __forceinline__ uint32_t step(uint32_t e, uint32_t word, int jj) const {
-    const uint32_t a = __byte_perm(word, clsBase, 0x7650 | jj);
-    return enc(lds_u16(e + lds_u8(a)));
-  }
-};
-
-/* SmemFastByte (small DFAs): rows of 256 u16 entries indexed by the raw byte;
-   the encoded state is the row's shared address.  One step is
-       PRMT, LEA, LDS.U16, LEA  - a single table load per byte. */
-struct SmemFastByte {
-  uint32_t tBase;
-  __device__ __forceinline__ uint32_t enc(uint32_t v) const { return (v << 9) + tBase; }
-  __device__ __forceinline__ uint32_t dec(uint32_t e) const { return (e - tBase) >> 9; }
-  __device__ __forceinline__ uint32_t encLimit(uint32_t lim) const { return lim ? enc(lim) : 0; }
-  __device__ __forceinline__ uint32_t step(uint32_t e, uint32_t word, int jj) const {
-    return enc(lds_u16(e + (byte_of(word, jj) << 1)));
-  }
-};
-
-template <class Tab, class ClsT> struct GenericFast {
-  Tab tab;
-  const ClsT *cls;
-  __device__ __forceinline__ uint32_t enc(uint32_t v) const { return v; }
-  __device__ __forceinline__ uint32_t dec(uint32_t e) const { return e; }
-  __device__ __forceinline__ uint32_t encLimit(uint32_t lim) const { return lim; }
-  __device__ __forceinline__ uint32_t step(uint32_t e, uint32_t word, int jj) const {
-    return tab.next(e, cls[byte_of(word, jj)]);
-  }
-};
-
-/* One aligned 16-byte chunk of one line per lane.  `mask` marks the bytes that
-   belong to the line.  Returns true when the walk is over (style decision or a
-   state that can never be left); wk carries the walk across chunks. */
-template <int STYLE, bool WANT_START, class Fast, class Tab, class ClsT>
-__device__ __forceinline__ bool
-process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT *cls,
-              const uint4 &cur, const uint32_t mask, const uint32_t pos0,
-              Walk<STYLE, WANT_START> &wk, const bool cValid) {
-  bool stopped = false;
-  // A lane with nothing in this chunk (its line is over, or it has no line)
-  // stays out altogether: its lookups would be pure noise in the shared-memory
-  // banks (ncu: 2.6 wavefronts per table load with idle lanes in, see profiles/).
-  if (mask != 0) {
-        // ---- fast pass: no decisions, quarter maxima only -------------------
-        // Within an active lane the two table loads are issued for all 16
-        // bytes, also those outside the line (they read valid table memory and
-        // the value is dropped): a select is cheaper than 16 branches.
-        const uint32_t eIn = fast.enc(wk.v);
-        const uint32_t eInit = fast.enc(pd.initV);
-        uint32_t e = eIn;
-        uint32_t mq0 = 0, mq1 = 0, mq2 = 0, mq3 = 0;
-        uint32_t cp0 = 0, cp1 = 0, cp2 = 0;
-        uint32_t msFast = wk.mstart;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t word = word_of(cur, q);
-          uint32_t m = 0;
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * q + jj;
-            const bool act = (mask & (1u << j)) != 0;
-            const uint32_t ne = fast.step(e, word, jj);
-            if (WANT_START) {
-              if (act && (e == eInit) && (ne != eInit))
-                msFast = pos0 + j;
-            }
-            if (act)
-              e = ne;
-            m = max(m, e);
-          }
-          if (q == 0) { mq0 = m; cp0 = e; }
-          if (q == 1) { mq1 = m; cp1 = e; }
-          if (q == 2) { mq2 = m; cp2 = e; }
-          if (q == 3) { mq3 = m; }
-        }
-        const uint32_t eLimit = fast.encLimit(wk.limit);
-        const uint32_t ePure = fast.enc(pd.pureV);
-        const uint32_t eAbs = fast.enc(pd.absV);
-        const uint32_t mAll = max(max(mq0, mq1), max(mq2, mq3));
-        if ((mAll < eLimit) || !cValid) {
-          wk.v = fast.dec(e);
-          if (WANT_START)
-            wk.mstart = msFast;
-        }
-        else {
-          // ---- careful pass: from the first flagged quarter on, quarter by
-          // quarter, with the reference's per-byte decisions.  Quarters whose
-          // maximum stayed below the (current) limit are skipped.
-          int q = (mq0 >= eLimit) ? 0 : (mq1 >= eLimit) ? 1 : (mq2 >= eLimit) ? 2 : 3;
-          if (WANT_START)
-            q = 0;
-          constexpr bool kLean = !WANT_START &&
-              ((STYLE == STY_INSTANT) || (STYLE == STY_LAST) || (STYLE == STY_FULL));
-          uint32_t ee = e;
-#pragma unroll 1
-          for (; (q < 4) && !stopped; ++q) {
-            const uint32_t m = (q == 0) ? mq0 : (q == 1) ? mq1 : (q == 2) ? mq2 : mq3;
-            if (WANT_START || (m >= fast.encLimit(wk.limit))) {
-              const uint32_t eq = (q == 0) ? eIn : (q == 1) ? cp0 : (q == 2) ? cp1 : cp2;
-              const uint32_t word = (q == 0) ? cur.x : (q == 1) ? cur.y : (q == 2) ? cur.z : cur.w;
-              const uint32_t nib = mask >> (4 * q);
-              if (kLean) {
-                // Instant / Last / Full without start tracking: the decisions
-                // are compares on the encoded state (Matcher.h:441-478)
-                ee = eq;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  if (!stopped && (nib & (1u << jj))) {
-                    ee = fast.step(ee, word, jj);
-                    if (ee >= eLimit) {
-                      if (ee >= ePure)
-                        stopped = true;           // pure dead end
-                      else if (STYLE == STY_FULL)
-                        stopped = true;           // absorbing accept: outcome known
-                      else {
-                        wk.accV = fast.dec(ee);
-                        wk.mend = pos0 + 4 * q + jj + 1;
-                        if (STYLE == STY_INSTANT)
-                          stopped = true;
-                        else if (ee >= eAbs) {
-                          wk.absorbed = true;
-                          stopped = true;
-                        }
-                      }
-                    }
-                  }
-                }
-              }
-              else {
-                wk.v = fast.dec(eq);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  if (!stopped && (nib & (1u << jj)))
-                    stopped = wk.step(pd, tab, cls[byte_of(word, jj)], pos0 + 4 * q + jj);
-                }
-              }
-            }
-          }
-          if (kLean)
-            wk.v = fast.dec(stopped ? ee : e);
-          else if (!stopped)
-            wk.v = fast.dec(e);
-        }
-      }
-  return stopped;
-}
-
-/* Shared memory (dynamic): up to 255 bytes of padding so that the class table
-   starts on a 256-byte boundary, 512 bytes of class table, then the
-   transition table (smem mode). */
-constexpr uint32_t kLanesSmemExtra = 256 + kClsBytes;
 
 template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
 __global__ void __launch_bounds__(kMaxThreads, 1)
@@ -538,6 +354,224 @@ batch_tile_kernel(const ProgramDev pd, const BatchArgs args,
   }
 }
 
+/* batch_sorted_kernel (default when positions are tracked; RED_B200_VARIANT=4
+   forces it): the tile schedule with tiles of SIMILAR
+   lines.  In a tile every lane waits for the longest line; with consecutive
+   lines of a log one instruction serves 20 of 32 lanes on average (ncu:
+   profiles/), and the shared-memory pipe that bounds the kernel is busy with
+   mostly-empty wavefronts.  Here a warp claims a GROUP of 32*T consecutive
+   lines, buckets them by length in 16-byte chunks (a counting sort in its
+   slice of shared memory: two passes of shared-memory atomics, 2 per line),
+   and walks the group as T tiles of lines with (nearly) the same chunk count.
+   Outcomes go to the line's own slot, so the order of the results is
+   untouched.  The next group is claimed and its index entries pulled into L2
+   a whole group ahead; it is sorted just before the last tile of the current
+   group is walked, so the prefetch chain (index entry -> first chunk) never
+   drains. */
+constexpr uint32_t kNoIdx = 0xffffu;
+
+// bytes of shared memory the sort needs per CTA of `warps` warps
+inline size_t sorted_smem_bytes(int warps, uint32_t T) {
+  return static_cast<size_t>(warps) * (32u * T * 2u + 32u * 4u);
+}
+
+template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
+                    unsigned long long *groupCounter, const uint32_t T,
+                    const uint32_t sortOffset) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t nWarps = blockDim.x >> 5;
+  // sort scratch of this warp: bucket counters, then the sorted line offsets
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem + sortOffset) + warp * 32;
+  uint16_t *order = reinterpret_cast<uint16_t *>(smem + sortOffset + nWarps * 128) + warp * 32 * T;
+
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint32_t leadLen = LEADER ? pd.leaderLen : 0;
+  const uint64_t perGroup = 32ull * T;
+
+  auto claimGroup = [&]() -> uint64_t {
+    unsigned long long g = 0;
+    if (lane == 0)
+      g = atomicAdd(groupCounter, 1ull);
+    return __shfl_sync(kFull, g, 0) * perGroup;
+  };
+  // pull a group's index entries into L2 ahead of use
+  auto prefetchGroup = [&](uint64_t base) {
+    if (base >= n)
+      return;
+    const uint64_t cnt = min(n - base, perGroup);
+    const char *ls = reinterpret_cast<const char *>(args.lens + base);
+    const char *ss = reinterpret_cast<const char *>(args.starts + base);
+    for (uint64_t o = lane * 128ull; o < cnt * 4; o += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ls + o));
+    for (uint64_t o = lane * 128ull; o < cnt * 8; o += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ss + o));
+  };
+  auto bucketOf = [&](uint32_t len) -> uint32_t { return min(31u, (len + 15u) >> 4); };
+  // counting sort of the group's lines by chunk count -> order[]
+  auto prepare = [&](uint64_t base) {
+    const uint32_t cnt = static_cast<uint32_t>(min(n - base, perGroup));
+    hist[lane] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < cnt; i += 32)
+      atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+    __syncwarp();
+    // exclusive scan of the 32 counters
+    const uint32_t c = hist[lane];
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d)
+        incl += up;
+    }
+    __syncwarp();
+    hist[lane] = incl - c;
+    __syncwarp();
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t pos = atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+      order[pos] = static_cast<uint16_t>(i);
+    }
+    for (uint32_t i = cnt + lane; i < perGroup; i += 32)
+      order[i] = kNoIdx;
+    __syncwarp();
+  };
+
+  uint64_t gBase = claimGroup();
+  uint64_t gNext = claimGroup();
+  uint32_t t = 0;
+  bool more = gBase < n;
+  if (more)
+    prepare(gBase);
+  prefetchGroup(gNext);
+
+  // next tile: its line for this lane (~0: none), with the first chunk
+  uint64_t nLine = ~0ull;
+  const uint8_t *nPtr = nullptr;
+  uint32_t nLen = 0;
+  uint4 nFirst = make_uint4(0, 0, 0, 0);
+  auto pickTile = [&]() {
+    const uint32_t idx = order[t * 32 + lane];
+    nLine = (idx != kNoIdx) ? gBase + idx : ~0ull;
+  };
+  auto fetchMeta = [&]() {
+    if (nLine != ~0ull) {
+      nPtr = args.text + __ldg(args.starts + nLine);
+      nLen = __ldg(args.lens + nLine);
+    }
+  };
+  auto fetchFirst = [&]() {
+    if ((nLine != ~0ull) && (nLen > leadLen)) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(nPtr + leadLen);
+      nFirst = __ldg(reinterpret_cast<const uint4 *>(a & ~uintptr_t(15)));
+    }
+  };
+  if (more) {
+    pickTile();
+    fetchMeta();
+    fetchFirst();
+  }
+
+  while (more) {
+    // the prefetched tile becomes the current one
+    const uint64_t line = nLine;
+    bool active = line != ~0ull;
+    const uint8_t *p = nPtr;
+    uint32_t len = active ? nLen : 0;
+    uint4 cur = nFirst, nxt = nFirst;
+    Walk<STYLE, WANT_START> wk;
+    wk.begin(pd);
+    bool noResult = false;
+    if (LEADER && active) {
+      // check() with the leader (Matcher.h:369-376)
+      bool viable = true;
+      for (uint32_t ii = 0; ii < leadLen; ++ii)
+        if ((ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + ii)])) {
+          viable = false;
+          break;
+        }
+      p += leadLen;
+      len = viable ? len - leadLen : 0;
+      wk.v = pd.leaderV;
+      noResult = !viable;
+    }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t skip = active ? static_cast<uint32_t>(a & 15) : 0;
+    const uint4 *blk = reinterpret_cast<const uint4 *>(a - skip);
+    const uint32_t total = skip + len;
+    const uint32_t lineLen = len;
+
+    // move on to the tile after this one (sorting the next group when this
+    // was the last tile of its group) and ask for its index entries now; its
+    // first chunks are requested one iteration later, when the entries are in
+    if (++t == T) {
+      t = 0;
+      gBase = gNext;
+      more = gBase < n;
+      if (more) {
+        prepare(gBase);
+        gNext = claimGroup();
+        prefetchGroup(gNext);
+      }
+    }
+    nLine = ~0ull;
+    if (more) {
+      pickTile();
+      fetchMeta();
+    }
+    bool wantFirst = true;
+
+    uint32_t k = 0;
+    while (__any_sync(kFull, active)) {
+      uint32_t lo = 0, hi = 0;
+      bool lastChunk = true;
+      if (active) {
+        const uint32_t rem = total - k * 16;
+        lo = (k == 0) ? skip : 0;
+        hi = min(16u, rem);
+        lastChunk = rem <= 16;
+        if (!lastChunk)
+          nxt = __ldg(blk + k + 1);
+      }
+      if (wantFirst && (k == 1)) {
+        fetchFirst();
+        wantFirst = false;
+      }
+      const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
+      const uint32_t pos0 = k * 16 - skip;
+      const bool stopped =
+          process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur, mask, pos0, wk, active);
+      if (stopped || lastChunk)
+        active = false;
+      ++k;
+      cur = nxt;
+    }
+    if (wantFirst)
+      fetchFirst();
+
+    if (line != ~0ull) {
+      int32_t result = 0;
+      uint32_t start = 0, end = 0;
+      if (!(LEADER && noResult))
+        wk.finish(pd, lineLen, result, start, end);
+      args.results[line] = result;
+      if (WANT_START)
+        args.matchStarts[line] = start;
+      if (args.matchEnds)
+        args.matchEnds[line] = end;
+    }
+  }
+}
+
 template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT>
 cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
                          const LaunchGeometry &geo, const BatchTuning &tune,
@@ -568,6 +602,43 @@ cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
   err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
   if (err != cudaSuccess)
     return err;
+  // tiles per group of the sorted schedule: what fits beside the table, and
+  // not so many that a small batch leaves SMs without a group
+  uint32_t tiles = 0;
+  // Measured on B200 (profiles/r1_sorted_sweep.txt): sorting pays where a
+  // step is expensive (positions tracked: +14-17%); for the plain styles it
+  // gains 1-5% but the scattered tiles cost L1/L2 locality (DRAM traffic
+  // x1.7), so those stay on the plain tile schedule.
+  if (((tune.variant == 0) && WANT_START) || (tune.variant == 4)) {
+    const size_t room = (static_cast<size_t>(geo.maxSmemOptin) > smem)
+        ? static_cast<size_t>(geo.maxSmemOptin) - smem : 0;
+    uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 8;
+    want = std::max(1u, std::min(want, 32u));
+    const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * perSm * (threads / 32) * 2;
+    while ((want > 1) && ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
+      want >>= 1;
+    while ((want > 1) && (sorted_smem_bytes(threads / 32, want) > room))
+      want >>= 1;
+    if (sorted_smem_bytes(threads / 32, want) <= room)
+      tiles = want;
+  }
+  if (tiles) {
+    auto sk = (args.checkLeader && !WANT_START)
+        ? batch_sorted_kernel<STYLE, false, SMEM, K, ClsT, true>
+        : batch_sorted_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
+    // the sort scratch sits behind the tables (+256: worst-case alignment pad)
+    const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : 0) + 15) & ~15u);
+    const size_t total = smem + sorted_smem_bytes(threads / 32, tiles) + 16;
+    err = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(total));
+    if (err != cudaSuccess)
+      return err;
+    uint64_t groups = (args.nLines + 32ull * tiles - 1) / (32ull * tiles);
+    uint64_t sctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * perSm,
+                                        (groups + threads / 32 - 1) / (threads / 32));
+    sk<<<static_cast<unsigned>(sctas), threads, total, stream>>>(pd, args, counter, tiles, sortOffset);
+    return cudaGetLastError();
+  }
   if (tune.variant != 3) {
     auto tk = (args.checkLeader && !WANT_START)
         ? batch_tile_kernel<STYLE, false, SMEM, K, ClsT, true>

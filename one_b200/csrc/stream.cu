@@ -11,6 +11,7 @@
 #include "stream.h"
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 namespace red_b200 {
@@ -256,6 +257,57 @@ int split_lines_async(const uint8_t *dText, uint64_t len, uint8_t delim,
   return RED_B200_OK;
 }
 
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t stream) {
+  static std::mutex lock;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  if ((dev < 0) || (dev >= 64))
+    return cudaErrorInvalidDevice;
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> g(lock);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if ((e = cudaMemPoolCreate(&pools[dev], &props)) != cudaSuccess)
+        return e;
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool = pools[dev];
+  }
+  return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, stream);
+}
+
+void scratch_free(void *p, cudaStream_t stream) {
+  if (p)
+    cudaFreeAsync(p, stream);
+}
+
+cudaError_t SplitScratch::allocAsync(uint64_t maxTextBytes, cudaStream_t s) {
+  capSegs = (maxTextBytes + kSegBytes - 1) / kSegBytes + 1;
+  cudaError_t e;
+  if ((e = scratch_alloc(&counts, capSegs * 4 + 4, s)) != cudaSuccess) return e;
+  if ((e = scratch_alloc(&offsets, capSegs * 8 + 8, s)) != cudaSuccess) return e;
+  return scratch_alloc(&total, 8, s);
+}
+
+void SplitScratch::releaseAsync(cudaStream_t s) {
+  scratch_free(counts, s);
+  scratch_free(offsets, s);
+  scratch_free(total, s);
+  counts = nullptr;
+  offsets = nullptr;
+  total = nullptr;
+  capSegs = 0;
+}
+
 cudaError_t SplitScratch::alloc(uint64_t maxTextBytes) {
   capSegs = (maxTextBytes + kSegBytes - 1) / kSegBytes + 1;
   cudaError_t e;
@@ -282,11 +334,12 @@ int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
     return RED_B200_OK;
   SplitScratch sc;
   LineCount *dInfo = nullptr;
-  TRY(sc.alloc(len));
-  cudaError_t e = cudaMalloc(&dInfo, sizeof(LineCount));
+  cudaError_t e = sc.allocAsync(len, stream);
+  if (e == cudaSuccess)
+    e = scratch_alloc(&dInfo, sizeof(LineCount), stream);
   if (e != cudaSuccess) {
-    sc.release();
-    return cuda_why(e, "cudaMalloc(LineCount)", why);
+    sc.releaseAsync(stream);
+    return cuda_why(e, "split_lines scratch", why);
   }
   int rc = split_lines_async(dText, len, delim, capacity, dStarts, dLens, dInfo, sc, stream, why);
   LineCount info{};
@@ -297,8 +350,8 @@ int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
     if (e != cudaSuccess)
       rc = cuda_why(e, "split_lines", why);
   }
-  cudaFree(dInfo);
-  sc.release();
+  scratch_free(dInfo, stream);
+  sc.releaseAsync(stream);
   if (rc != RED_B200_OK)
     return rc;
   *nLinesOut = info.overflow ? info.wanted : info.nLines;
@@ -318,8 +371,8 @@ int compact_matches(const int32_t *dResults, uint64_t n, uint64_t *dIndices,
   const uint64_t nSegs = (n + kSegLines - 1) / kSegLines;
   uint32_t *counts = nullptr;
   uint64_t *offsets = nullptr;
-  TRY(cudaMallocAsync(&counts, nSegs * 4 + 4, stream));
-  TRY(cudaMallocAsync(&offsets, nSegs * 8 + 8, stream));
+  TRY(scratch_alloc(&counts, nSegs * 4 + 4, stream));
+  TRY(scratch_alloc(&offsets, nSegs * 8 + 8, stream));
   const int threads = 256;
   const int grid = grid_for(nSegs, threads);
   count_matches_kernel<<<grid, threads, 0, stream>>>(dResults, n, counts, nSegs);

@@ -20,13 +20,25 @@ struct LineCount {
   uint64_t overflow;  // wanted > capacity
 };
 
+/* Scratch for one call, from a per-device stream-ordered pool that keeps its
+   memory between calls (the default pool hands it back at every
+   synchronization, and cudaMalloc/cudaFree cost milliseconds). */
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t stream);
+void scratch_free(void *p, cudaStream_t stream);
+template <class T>
+cudaError_t scratch_alloc(T **p, size_t bytes, cudaStream_t stream) {
+  return scratch_alloc(reinterpret_cast<void **>(p), bytes, stream);
+}
+
 struct SplitScratch {
   uint32_t *counts = nullptr;
   uint64_t *offsets = nullptr;
   uint64_t *total = nullptr;
   uint64_t capSegs = 0;
-  cudaError_t alloc(uint64_t maxTextBytes);
+  cudaError_t alloc(uint64_t maxTextBytes);                       // cudaMalloc (long-lived)
   void release();
+  cudaError_t allocAsync(uint64_t maxTextBytes, cudaStream_t s);  // per call, from the pool
+  void releaseAsync(cudaStream_t s);
 };
 
 // everything on `stream`, nothing read back: the count stays in *dInfo

@@ -5,34 +5,42 @@
    parallelism unless the start state of a piece is known before the pieces
    in front of it are done.  What is done here:
 
-     1. cut the text into chunks (one lane per chunk, ~16 KB each);
-     2. SPECULATE the state at the start of chunk i: run the DFA from the
+     1. the text is taken in WINDOWS of growing size (32 MB, then x8): the
+        state at the start of a window is known exactly from the window in
+        front of it, and a walk that is decided early (Instant/First/Tangent
+        on the first match, any style in a state that can never be left) ends
+        after the window it was decided in, as the reference's does;
+     2. a window is cut into chunks, one lane per chunk (2-16 KB each);
+     3. SPECULATE the state at the start of chunk i: run the DFA from the
         initial state over a lookback window in front of the chunk.  DFAs of
         the ".*pattern" kind forget their past quickly, so the guess is almost
         always the true state;
-     3. walk every chunk from its guess, in parallel, recording the chunk's
-        end state and what the styles need: first and last accepting
-        position (with the state there) and the last position at which the
-        initial state was left;
-     4. STITCH: chunk i is confirmed when its start state equals the end state
-        of chunk i-1 (chunk 0 starts in the initial state by definition).  The
-        unconfirmed chunks get the correct start state and are walked again -
-        all of them in parallel - until a round changes nothing.  A chunk
-        whose guess was wrong usually still ENDS in the right state (the DFA
-        converges inside the chunk), so a wrong guess does not cascade and the
-        loop ends after one or two rounds; in the worst case (a DFA that never
-        forgets, e.g. a parity counter) it degrades to one chunk per round and
-        stays exact;
-     5. reduce the per-chunk records in text order, and finish the styles
-        that stop early with one short careful walk from the right chunk.
+     4. walk every chunk from its guess, in parallel, with the batch kernels'
+        chunk engine (chunk_engine.cuh) in style Last with start tracking: the
+        record of a chunk is its end state, its last accepting position with
+        the state there, and the last position at which the initial state was
+        left;
+     5. STITCH: chunk i is confirmed when its start state equals the end state
+        of chunk i-1.  The records in front of the first unconfirmed chunk are
+        reduced in text order; if they already decide the walk, it is over.
+        Otherwise the unconfirmed chunks get the correct start state and are
+        walked again - all of them in parallel - until a round changes
+        nothing.  A chunk whose guess was wrong usually still ENDS in the
+        right state (the DFA converges inside the chunk), so a wrong guess
+        does not cascade and the loop ends after one or two rounds; in the
+        worst case (a DFA that never forgets, e.g. a parity counter) it
+        degrades to one chunk per round and stays exact;
+     6. the styles that stop at the first match get one short careful walk
+        from the start of the chunk that holds it.
 
    Every answer is exact: nothing is derived from an unconfirmed chunk.
  */
 
 #include "stream.h"
-#include "walk.cuh"
+#include "chunk_engine.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace red_b200 {
@@ -43,201 +51,196 @@ using namespace dev;
 
 constexpr uint32_t kNoPos = 0xffffffffu;
 constexpr uint32_t kLookback = 256;
+constexpr uint64_t kFirstWindow = 32ull << 20;
+constexpr uint64_t kWindowGrowth = 8;
 
 struct ChunkRec {
   uint32_t startV;        // state the walk started from
-  uint32_t endV;          // state after the chunk's last byte
-  uint32_t firstAccOff;   // offset in chunk of the first accepting position, or kNoPos
-  uint32_t firstAccV;
-  uint32_t lastAccOff;    // ... of the last accepting position
-  uint32_t lastAccV;
-  uint32_t lastLeaveOff;  // last offset at which the initial state was left
+  uint32_t endV;          // state after the chunk's last byte (or the state
+                          // that can never be left, if the walk stopped there)
+  uint32_t accV;          // last accepting state in the chunk, or kNone
+  uint32_t accEnd;        // offset one past that position
+  uint32_t lastLeaveOff;  // last offset at which the initial state was left, or kNoPos
   uint32_t dirty;         // needs (re)walking from startV
 };
 
 struct StreamSummary {
+  unsigned long long bad;        // unconfirmed chunks (written by the verify kernel)
+  unsigned long long firstBad;   // first of them, or ~0
   uint64_t firstAccChunk, lastAccChunk, lastLeaveChunk;  // ~0 = none
-  uint32_t firstAccOff, firstAccV, lastAccOff, lastAccV, lastLeaveOff;
+  uint32_t firstAccStartV;
+  uint32_t lastAccEnd, lastAccV, lastLeaveOff;
   uint32_t finalV;
+  uint64_t reduced;              // chunks the summary covers (a confirmed prefix)
 };
 
-/* one chunk, from state v0; plain per-byte walk with event recording.
-   Stops early once the state can never change again. */
-template <class Tab, class ClsT>
-__device__ __forceinline__ void walk_chunk(const ProgramDev &pd, const Tab &tab,
-                                           const ClsT *cls, const uint8_t *p,
-                                           uint32_t n, uint32_t v0, bool record,
-                                           ChunkRec &rec) {
-  uint32_t v = v0;
-  uint32_t firstOff = kNoPos, firstV = 0, lastOff = kNoPos, lastV = 0, leaveOff = kNoPos;
-  // p is 16-byte aligned (chunk sizes are multiples of 16; the text base is
-  // required to be aligned); n may be short for the last chunk
+/* n bytes at p (16-byte aligned) from state wk.v, 16 bytes per step through
+   the chunk engine */
+template <int STYLE, bool WANT_START, class Eng, class ClsT>
+__device__ __forceinline__ void walk_bytes(const ProgramDev &pd, const typename Eng::Fast &fast,
+                                           const typename Eng::Tab &tab, const ClsT *cls,
+                                           const uint8_t *p, uint32_t n,
+                                           Walk<STYLE, WANT_START> &wk) {
   const uint4 *blk = reinterpret_cast<const uint4 *>(p);
   const uint32_t nblk = (n + 15) >> 4;
-  for (uint32_t k = 0; k < nblk; ++k) {
-    const uint4 q = __ldg(blk + k);
-    const uint32_t hi = min(16u, n - k * 16);
-    // fast pass
-    uint32_t e = v, m = 0;
-    bool left = false;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < hi) {
-        const uint32_t b = byte_of(word_of(q, j >> 2), j & 3);
-        const uint32_t ne = tab.next(e, cls[b]);
-        left |= (e == pd.initV) && (ne != pd.initV);
-        e = ne;
-        m = max(m, ne);
-      }
+  bool active = nblk > 0;
+  uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+  if (active)
+    cur = __ldg(blk);
+  uint32_t k = 0;
+  while (__any_sync(0xffffffffu, active)) {
+    uint32_t hi = 0;
+    bool last = true;
+    if (active) {
+      const uint32_t rem = n - k * 16;
+      hi = min(16u, rem);
+      last = rem <= 16;
+      if (!last)
+        nxt = __ldg(blk + k + 1);
     }
-    if (record && ((m >= pd.acceptV) || left)) {
-      // careful pass over this block: something to record happened in it
-      e = v;
-#pragma unroll 1
-      for (uint32_t j = 0; j < hi; ++j) {
-        const uint32_t w = word_of(q, j >> 2);
-        const uint32_t b = (w >> (8 * (j & 3))) & 0xffu;
-        const uint32_t ne = tab.next(e, cls[b]);
-        const uint32_t off = k * 16 + j;
-        if ((e == pd.initV) && (ne != pd.initV))
-          leaveOff = off;
-        e = ne;
-        if ((e >= pd.acceptV) && (e < pd.pureV)) {
-          if (firstOff == kNoPos) {
-            firstOff = off;
-            firstV = e;
-          }
-          lastOff = off;
-          lastV = e;
-        }
-      }
-    }
-    v = e;
-    if (v >= pd.absV) {
-      // absorbing accept (every later position accepts, same state) or pure
-      // dead end (nothing can happen any more)
-      if (record && (v < pd.pureV) && (n > 0)) {
-        lastOff = n - 1;
-        lastV = v;
-      }
-      break;
-    }
-  }
-  rec.endV = v;
-  if (record) {
-    rec.firstAccOff = firstOff;
-    rec.firstAccV = firstV;
-    rec.lastAccOff = lastOff;
-    rec.lastAccV = lastV;
-    rec.lastLeaveOff = leaveOff;
+    const uint32_t mask = 0xffffu >> (16 - hi);
+    const bool stopped = process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur, mask,
+                                                          k * 16, wk, active);
+    if (stopped || last)
+      active = false;
+    ++k;
+    cur = nxt;
   }
 }
 
+/* text/len: the window; v0: the (exact) state at its start */
 template <bool SMEM, int K, class ClsT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 stream_walk_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
                    uint32_t chunkBytes, uint64_t nChunks, ChunkRec *recs,
-                   int firstRound) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  stage_classes<ClsT>(pd, smem);
-  if (SMEM)
-    stage_table(pd, smem + kClsBytes);
-  __syncthreads();
+                   int firstRound, uint32_t v0) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
   const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
-  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
-  const Tab tab{SMEM ? smem + kClsBytes
-                     : static_cast<const unsigned char *>(pd.table)};
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
+
+  // whole warps stay in the loop together (walk_bytes votes)
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  for (uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-       c < nChunks; c += stride) {
-    ChunkRec rec = recs[c];
-    if (!firstRound && !rec.dirty)
-      continue;
-    const uint64_t begin = c * chunkBytes;
-    const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin));
+  const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t rounds = (nChunks + stride - 1) / stride;
+  for (uint64_t r = 0; r < rounds; ++r) {
+    const uint64_t c = first + r * stride;
+    ChunkRec rec{};
+    bool mine = c < nChunks;
+    if (mine && !firstRound) {
+      rec = recs[c];
+      mine = rec.dirty != 0;
+    }
+    const uint64_t begin = mine ? c * chunkBytes : 0;
+    const uint32_t n = mine ? static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin)) : 0;
     if (firstRound) {
       // speculate: the state after the lookback window, entered from the
-      // initial state (chunk 0 really starts in the initial state)
-      uint32_t v = pd.initV;
-      if (c > 0) {
-        ChunkRec tmp;
-        const uint32_t lb = static_cast<uint32_t>(min(static_cast<uint64_t>(kLookback), begin));
-        walk_chunk(pd, tab, cls, text + begin - lb, lb, v, false, tmp);
-        v = tmp.endV;
-      }
-      rec.startV = v;
+      // initial state (chunk 0 starts in the known state v0)
+      Walk<STY_FULL, false> sp;
+      sp.begin(pd);
+      const uint32_t lb = (mine && (c > 0)) ? kLookback : 0;  // chunkBytes >= kLookback
+      walk_bytes<STY_FULL, false, Eng>(pd, fast, tab, cls, text + begin - lb, lb, sp);
+      rec.startV = (c == 0) ? v0 : sp.v;
     }
-    walk_chunk(pd, tab, cls, text + begin, n, rec.startV, true, rec);
-    rec.dirty = 0;
-    recs[c] = rec;
+    Walk<STY_LAST, true> wk;
+    wk.begin(pd);
+    wk.v = rec.startV;
+    wk.mstart = kNoPos;
+    walk_bytes<STY_LAST, true, Eng>(pd, fast, tab, cls, text + begin, n, wk);
+    if (mine) {
+      rec.endV = wk.v;
+      rec.accV = wk.accV;
+      rec.accEnd = wk.absorbed ? n : wk.mend;
+      rec.lastLeaveOff = wk.mstart;
+      rec.dirty = 0;
+      recs[c] = rec;
+    }
   }
 }
 
 /* confirm chunk i against the end state of chunk i-1; hand the right start
-   state to the ones that fail and count them */
+   state to the ones that fail, count them and find the first */
 __global__ void stream_verify_kernel(ChunkRec *recs, uint64_t nChunks,
-                                     uint32_t initV,
-                                     unsigned long long *mismatches) {
+                                     uint32_t v0, StreamSummary *sum) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  unsigned long long bad = 0;
+  unsigned bad = 0;
+  unsigned long long firstBad = ~0ull;
   for (uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
        c < nChunks; c += stride) {
-    const uint32_t want = (c == 0) ? initV : recs[c - 1].endV;
+    const uint32_t want = (c == 0) ? v0 : recs[c - 1].endV;
     if (recs[c].startV != want) {
       recs[c].startV = want;
       recs[c].dirty = 1;
       ++bad;
+      firstBad = min(firstBad, static_cast<unsigned long long>(c));
     }
   }
-  bad = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(bad));
-  if (((threadIdx.x & 31) == 0) && bad)
-    atomicAdd(mismatches, bad);
+  __syncwarp();
+  if (__any_sync(0xffffffffu, bad != 0)) {
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    for (int d = 16; d > 0; d >>= 1)
+      firstBad = min(firstBad, __shfl_xor_sync(0xffffffffu, firstBad, d));
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sum->bad, static_cast<unsigned long long>(bad));
+      atomicMin(&sum->firstBad, firstBad);
+    }
+  }
 }
 
-/* in text order: first/last chunk with an accepting position, last chunk in
-   which the initial state was left, final state.  One block; every thread
-   takes a contiguous run of chunks, thread 0 combines. */
+/* over the confirmed prefix: first/last chunk with an accepting position, last
+   chunk in which the initial state was left, final state.  One block.
+   upTo = ~0: the prefix in front of sum->firstBad (after the verify kernel). */
 __global__ void __launch_bounds__(1024)
-stream_reduce_kernel(const ChunkRec *recs, uint64_t nChunks, StreamSummary *out) {
-  __shared__ unsigned long long sFirst[1024], sLast[1024], sLeave[1024];
-  const uint64_t per = (nChunks + blockDim.x - 1) / blockDim.x;
-  const uint64_t lo = min(nChunks, per * threadIdx.x);
-  const uint64_t hi = min(nChunks, lo + per);
-  unsigned long long f = ~0ull, l = ~0ull, lv = ~0ull;
-  for (uint64_t c = lo; c < hi; ++c) {
-    if (recs[c].firstAccOff != kNoPos) {
-      if (f == ~0ull)
-        f = c;
-      l = c;
+stream_reduce_kernel(const ChunkRec *recs, uint64_t nChunks, uint64_t upTo,
+                     StreamSummary *sum) {
+  __shared__ unsigned long long sFirst[32], sLast[32], sLeave[32];
+  const uint64_t n = (upTo != ~0ull) ? min(upTo, nChunks)
+                                     : min(static_cast<uint64_t>(sum->firstBad), nChunks);
+  // f: smallest chunk index with an accept; l, lv: largest index + 1 (0 = none)
+  unsigned long long f = ~0ull, l = 0, lv = 0;
+  for (uint64_t c = threadIdx.x; c < n; c += blockDim.x) {
+    if (recs[c].accV != kNone) {
+      f = min(f, static_cast<unsigned long long>(c));
+      l = c + 1;
     }
     if (recs[c].lastLeaveOff != kNoPos)
-      lv = c;
+      lv = c + 1;
   }
-  sFirst[threadIdx.x] = f;
-  sLast[threadIdx.x] = l;
-  sLeave[threadIdx.x] = lv;
+  __syncwarp();
+  for (int d = 16; d > 0; d >>= 1) {
+    f = min(f, __shfl_xor_sync(0xffffffffu, f, d));
+    l = max(l, __shfl_xor_sync(0xffffffffu, l, d));
+    lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sFirst[threadIdx.x >> 5] = f;
+    sLast[threadIdx.x >> 5] = l;
+    sLeave[threadIdx.x >> 5] = lv;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    f = l = lv = ~0ull;
-    for (unsigned t = 0; t < blockDim.x; ++t) {
-      if ((f == ~0ull) && (sFirst[t] != ~0ull))
-        f = sFirst[t];
-      if (sLast[t] != ~0ull)
-        l = sLast[t];
-      if (sLeave[t] != ~0ull)
-        lv = sLeave[t];
+  if (threadIdx.x < 32) {
+    const unsigned warps = (blockDim.x + 31) >> 5;
+    f = (threadIdx.x < warps) ? sFirst[threadIdx.x] : ~0ull;
+    l = (threadIdx.x < warps) ? sLast[threadIdx.x] : 0;
+    lv = (threadIdx.x < warps) ? sLeave[threadIdx.x] : 0;
+    for (int d = 16; d > 0; d >>= 1) {
+      f = min(f, __shfl_xor_sync(0xffffffffu, f, d));
+      l = max(l, __shfl_xor_sync(0xffffffffu, l, d));
+      lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
     }
-    StreamSummary s;
-    s.firstAccChunk = f;
-    s.lastAccChunk = l;
-    s.lastLeaveChunk = lv;
-    s.firstAccOff = (f != ~0ull) ? recs[f].firstAccOff : kNoPos;
-    s.firstAccV = (f != ~0ull) ? recs[f].firstAccV : 0;
-    s.lastAccOff = (l != ~0ull) ? recs[l].lastAccOff : kNoPos;
-    s.lastAccV = (l != ~0ull) ? recs[l].lastAccV : 0;
-    s.lastLeaveOff = (lv != ~0ull) ? recs[lv].lastLeaveOff : kNoPos;
-    s.finalV = nChunks ? recs[nChunks - 1].endV : 0;
-    *out = s;
+    if (threadIdx.x == 0) {
+      sum->firstAccChunk = f;
+      sum->lastAccChunk = l ? l - 1 : ~0ull;
+      sum->lastLeaveChunk = lv ? lv - 1 : ~0ull;
+      sum->firstAccStartV = (f != ~0ull) ? recs[f].startV : 0;
+      sum->lastAccEnd = l ? recs[l - 1].accEnd : 0;
+      sum->lastAccV = l ? recs[l - 1].accV : 0;
+      sum->lastLeaveOff = lv ? recs[lv - 1].lastLeaveOff : kNoPos;
+      sum->finalV = n ? recs[n - 1].endV : 0;
+      sum->reduced = n;
+    }
   }
 }
 
@@ -318,54 +321,48 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
       return fail(e_, #expr);                    \
   } while (0)
 
-  const size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : 0);
   auto walk = stream_walk_kernel<SMEM, K, ClsT>;
   auto tail = stream_tail_kernel<SMEM, K, ClsT>;
   TRY(cudaFuncSetAttribute(walk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 
-  // chunk size: ~4 chunks per lane of the whole chip, 1 KB .. 16 KB, 16-byte multiple
+  // chunk size of a window: one chunk per lane of the whole chip if that
+  // gives 1 KB .. 16 KB, a multiple of 16
   const uint64_t lanes = static_cast<uint64_t>(geo.smCount) * kMaxThreads;
-  uint64_t chunk = (len + lanes * 4 - 1) / (lanes * 4);
-  chunk = std::max<uint64_t>(1024, std::min<uint64_t>(16384, chunk));
-  chunk = (chunk + 15) & ~uint64_t(15);
-  const uint64_t nChunks = (len + chunk - 1) / chunk;
+  auto chunkFor = [&](uint64_t bytes) {
+    uint64_t chunk = (bytes + lanes - 1) / lanes;
+    chunk = std::max<uint64_t>(1024, std::min<uint64_t>(16384, chunk));
+    return (chunk + 15) & ~uint64_t(15);
+  };
+  // RED_B200_STREAM_WINDOW (bytes, for tests): size of the first window
+  uint64_t firstWindow = kFirstWindow;
+  if (const char *env = getenv("RED_B200_STREAM_WINDOW")) {
+    const uint64_t w = strtoull(env, nullptr, 10);
+    if (w >= 4096)
+      firstWindow = w & ~uint64_t(15);
+  }
+  uint64_t maxChunks = 0;
+  for (uint64_t pos = 0, w = firstWindow; pos < len; pos += w, w *= kWindowGrowth) {
+    const uint64_t bytes = std::min(w, len - pos);
+    maxChunks = std::max(maxChunks, (bytes + chunkFor(bytes) - 1) / chunkFor(bytes));
+  }
 
   ChunkRec *recs = nullptr;
-  unsigned long long *counter = nullptr;
   StreamSummary *dSum = nullptr;
   TailOut *dTail = nullptr;
-  TRY(cudaMallocAsync(&recs, nChunks * sizeof(ChunkRec), stream));
-  TRY(cudaMallocAsync(&counter, sizeof(unsigned long long), stream));
-  TRY(cudaMallocAsync(&dSum, sizeof(StreamSummary), stream));
-  TRY(cudaMallocAsync(&dTail, sizeof(TailOut), stream));
-  TRY(cudaMemsetAsync(recs, 0, nChunks * sizeof(ChunkRec), stream));
-
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, (nChunks + kMaxThreads - 1) / kMaxThreads));
-  const unsigned vgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount * 4, (nChunks + 255) / 256));
-  walk<<<grid, kMaxThreads, smem, stream>>>(pd, dText, len, static_cast<uint32_t>(chunk), nChunks, recs, 1);
-  ++*launches;
-  for (uint64_t round = 0;; ++round) {
-    unsigned long long bad = 0;
-    TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-    stream_verify_kernel<<<vgrid, 256, 0, stream>>>(recs, nChunks, pd.initV, counter);
-    ++*launches;
-    TRY(cudaMemcpyAsync(&bad, counter, sizeof(bad), cudaMemcpyDeviceToHost, stream));
-    TRY(cudaStreamSynchronize(stream));
-    if (bad == 0)
-      break;
-    if (round > nChunks) {
-      why = "stream stitching did not converge";
-      return RED_B200_EINTERNAL;
-    }
-    walk<<<grid, kMaxThreads, smem, stream>>>(pd, dText, len, static_cast<uint32_t>(chunk), nChunks, recs, 0);
-    ++*launches;
-  }
-  stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, nChunks, dSum);
-  ++*launches;
-  StreamSummary sum;
-  TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
-  TRY(cudaStreamSynchronize(stream));
+  TRY(scratch_alloc(&recs, maxChunks * sizeof(ChunkRec), stream));
+  TRY(scratch_alloc(&dSum, sizeof(StreamSummary), stream));
+  TRY(scratch_alloc(&dTail, sizeof(TailOut), stream));
+  auto release = [&]() {
+    scratch_free(recs, stream);
+    scratch_free(dSum, stream);
+    scratch_free(dTail, stream);
+  };
+  struct Releaser {
+    decltype(release) &fn;
+    ~Releaser() { fn(); }
+  } releaser{release};
 
   auto resultOf = [&](uint32_t v, int32_t &r) -> int {
     uint32_t idx = v / pd.vPerState;
@@ -373,79 +370,130 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     TRY(cudaStreamSynchronize(stream));
     return RED_B200_OK;
   };
+
   const uint64_t none = ~0ull;
-  const uint64_t lastLeave = (sum.lastLeaveChunk != none)
-      ? sum.lastLeaveChunk * chunk + sum.lastLeaveOff : 0;
   out->result = 0;
   out->start = 0;
   out->end = 0;
-  int rc = RED_B200_OK;
+  // carried across windows
+  uint32_t v0 = pd.initV;
+  uint64_t lastLeave = none;     // last position at which the initial state was left
+  uint64_t lastAccEnd = 0;       // one past the last accepting position so far
+  uint32_t lastAccV = kNone;
 
+  StreamSummary init{};
+  init.firstBad = none;
+  int rc = RED_B200_OK;
+  bool decided = false;
+  uint64_t window = firstWindow;
+  for (uint64_t base = 0; (base < len) && !decided; base += window, window *= kWindowGrowth) {
+    const uint64_t bytes = std::min(window, len - base);
+    const uint64_t chunk = chunkFor(bytes);
+    const uint64_t nChunks = (bytes + chunk - 1) / chunk;
+    const uint8_t *wText = dText + base;  // windows are multiples of 16 bytes
+    // a small window is spread over all SMs with few warps each (a lane
+    // walks several times faster when its SM is not full)
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, (nChunks + 31) / 32));
+    const unsigned threads = static_cast<unsigned>(std::min<uint64_t>(
+        kMaxThreads, ((nChunks + grid - 1) / grid + 31) / 32 * 32));
+    const unsigned vgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount * 4, (nChunks + 255) / 256));
+    walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, recs, 1, v0);
+    ++*launches;
+    StreamSummary sum;
+    for (uint64_t round = 0;; ++round) {
+      TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
+      stream_verify_kernel<<<vgrid, 256, 0, stream>>>(recs, nChunks, v0, dSum);
+      stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, nChunks, none, dSum);
+      *launches += 2;
+      TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
+      TRY(cudaStreamSynchronize(stream));
+      // is the walk decided inside the confirmed prefix?
+      const bool early = (style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_FIRST) ||
+                         (style == RED_B200_STY_TANGENT);
+      if ((early && (sum.firstAccChunk != none)) || (sum.reduced && (sum.finalV >= pd.absV))) {
+        decided = true;
+        break;
+      }
+      if (sum.bad == 0)
+        break;
+      if (round > nChunks) {
+        why = "stream stitching did not converge";
+        return RED_B200_EINTERNAL;
+      }
+      walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, recs, 0, v0);
+      ++*launches;
+    }
+
+    const bool early = (style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_FIRST) ||
+                       (style == RED_B200_STY_TANGENT);
+    if (early && (sum.firstAccChunk != none)) {
+      // careful walk from the chunk with the first accepting position
+      const uint64_t c = sum.firstAccChunk;
+      const uint64_t from = base + c * chunk;
+      tail<<<1, kMaxThreads, smem, stream>>>(pd, dText, len, from, sum.firstAccStartV, style, dTail);
+      ++*launches;
+      TailOut t;
+      TRY(cudaMemcpyAsync(&t, dTail, sizeof(t), cudaMemcpyDeviceToHost, stream));
+      TRY(cudaStreamSynchronize(stream));
+      if (t.accepted) {
+        out->result = t.result;
+        out->end = t.end;
+        // the initial state was last left either inside the tail walk, or in
+        // an earlier chunk of this window, or in an earlier window
+        uint64_t leave = t.lastLeave;
+        if ((leave == none) && (c > 0)) {
+          stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, nChunks, c, dSum);
+          ++*launches;
+          StreamSummary before;
+          TRY(cudaMemcpyAsync(&before, dSum, sizeof(before), cudaMemcpyDeviceToHost, stream));
+          TRY(cudaStreamSynchronize(stream));
+          if (before.lastLeaveChunk != none)
+            leave = base + before.lastLeaveChunk * chunk + before.lastLeaveOff;
+        }
+        if (leave == none)
+          leave = lastLeave;
+        out->start = (leave == none) ? 0 : leave;
+      }
+      return RED_B200_OK;
+    }
+
+    // fold the window (its confirmed prefix, which is all of it unless the
+    // walk was decided) into the running outcome
+    if (sum.lastLeaveChunk != none)
+      lastLeave = base + sum.lastLeaveChunk * chunk + sum.lastLeaveOff;
+    if (sum.lastAccChunk != none) {
+      lastAccEnd = base + sum.lastAccChunk * chunk + sum.lastAccEnd;
+      lastAccV = sum.lastAccV;
+    }
+    v0 = sum.finalV;
+    if (v0 >= pd.absV)
+      decided = true;
+  }
+
+  // Instant/First/Tangent come here only without a match.  v0 is the final
+  // state, or a state that can never be left.
+  const bool absorbing = (v0 >= pd.absV) && (v0 < pd.pureV);
   if (style == RED_B200_STY_FULL) {
     // the final state decides (a pure dead end carries result 0)
-    const bool acc = (sum.finalV >= pd.acceptV) && (sum.finalV < pd.pureV);
-    if (acc) {
+    if ((v0 >= pd.acceptV) && (v0 < pd.pureV)) {
       int32_t r = 0;
-      if ((rc = resultOf(sum.finalV, r)) != RED_B200_OK)
+      if ((rc = resultOf(v0, r)) != RED_B200_OK)
         return rc;
       out->result = r;
-      out->start = lastLeave;
+      out->start = (lastLeave == none) ? 0 : lastLeave;
       out->end = len;
     }
   }
   else if (style == RED_B200_STY_LAST) {
-    if (sum.lastAccChunk != none) {
+    if (lastAccV != kNone) {
       int32_t r = 0;
-      if ((rc = resultOf(sum.lastAccV, r)) != RED_B200_OK)
+      if ((rc = resultOf(lastAccV, r)) != RED_B200_OK)
         return rc;
       out->result = r;
-      out->start = lastLeave;
-      out->end = sum.lastAccChunk * chunk + sum.lastAccOff + 1;
+      out->start = (lastLeave == none) ? 0 : lastLeave;
+      out->end = absorbing ? len : lastAccEnd;
     }
   }
-  else if (sum.firstAccChunk != none) {
-    // Instant / First / Tangent: careful walk from the chunk with the first
-    // accepting position
-    const uint64_t c = sum.firstAccChunk;
-    ChunkRec rec;
-    TRY(cudaMemcpyAsync(&rec, recs + c, sizeof(rec), cudaMemcpyDeviceToHost, stream));
-    TRY(cudaStreamSynchronize(stream));
-    tail<<<1, kMaxThreads, smem, stream>>>(pd, dText, len, c * chunk, rec.startV, style, dTail);
-    ++*launches;
-    TailOut t;
-    TRY(cudaMemcpyAsync(&t, dTail, sizeof(t), cudaMemcpyDeviceToHost, stream));
-    TRY(cudaStreamSynchronize(stream));
-    if (t.accepted) {
-      out->result = t.result;
-      out->end = t.end;
-      // the initial state was last left either inside the tail walk or in an
-      // earlier chunk
-      uint64_t leave = t.lastLeave;
-      if ((leave == none) && (c > 0)) {
-        // the latest chunk in front of c in which the initial state was left
-        stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, c, dSum);
-        ++*launches;
-        StreamSummary before;
-        TRY(cudaMemcpyAsync(&before, dSum, sizeof(before), cudaMemcpyDeviceToHost, stream));
-        TRY(cudaStreamSynchronize(stream));
-        if (before.lastLeaveChunk != none)
-          leave = before.lastLeaveChunk * chunk + before.lastLeaveOff;
-      }
-      if (leave == none)
-        leave = 0;
-      out->start = leave;
-    }
-  }
-  // an empty text: the initial state's result (Matcher.h:429, loop not entered)
-  if ((len == 0) && (pd.initResult > 0)) {
-    out->result = pd.initResult;
-    out->start = 0;
-    out->end = 0;
-  }
-  TRY(cudaFreeAsync(recs, stream));
-  TRY(cudaFreeAsync(counter, stream));
-  TRY(cudaFreeAsync(dSum, stream));
-  TRY(cudaFreeAsync(dTail, stream));
 #undef TRY
   return RED_B200_OK;
 }

@@ -80,6 +80,37 @@ def test_stream_dfa_that_never_forgets(gpu_red, redlib, oracle_cls):
         check_stream(gpu_red, oracle_cls, blob, b"ab" * (n // 2) + b"a" * (n % 2), ("parity", n))
 
 
+def test_stream_windows(gpu_red, redlib, vectors, oracle_cls, monkeypatch):
+    """The stream is taken in windows of growing size (32 MB, x8); with a tiny
+    first window a small text crosses many of them: the state, the last
+    accept and the last departure from the initial state carry over, and a
+    walk that is decided stops at its window."""
+    from one_b200 import synth
+    monkeypatch.setenv("RED_B200_STREAM_WINDOW", "8192")
+    union = unz(next(c for c in vectors["cases"] if c["name"] == "union64")["program"])
+    noise = b"\n".join(l for l in synth.make_lines(30000, seed=6) if b"CRON" in l or b"ntpd" in l)
+    assert len(noise) > 400000
+    check_stream(gpu_red, oracle_cls, union, noise, "w-noise")
+    for at in (100, 8191, 8192, 40959, 40960, 300000, len(noise) - 1):
+        check_stream(gpu_red, oracle_cls, union, noise[:at] + b" Quarantined " + noise[at:], ("w-union", at))
+    # tight patterns: non-absorbing accepts, results that change, dead ends
+    p = redlib.Parser()
+    p.add(b"[a-c ]*NewYork[a-c ]*", 1, 0)
+    p.add(b"[a-c ]*NewYork[a-c ]*\\.[a-c .]*", 2, 0)
+    tight = redlib.compileToSerialized(p)
+    rng = np.random.RandomState(8)
+    for n in (9000, 50000, 200000):
+        body = bytes(rng.choice(list(b"abc "), size=n).astype(np.uint8))
+        for at in (10, 8190, n // 2, n - 8):
+            for extra in (b"", b".", b"!"):
+                k = min(at + 9000, n)
+                raw = body[:at] + b"NewYork" + body[at:k] + extra + body[k:]
+                check_stream(gpu_red, oracle_cls, tight, raw, ("w-tight", n, at, extra))
+    parity = redlib.Parser()
+    parity.add(b"((a|b)(a|b))*", 1, 0)
+    check_stream(gpu_red, oracle_cls, redlib.compileToSerialized(parity), b"ab" * 30000 + b"a", "w-parity")
+
+
 def test_large_dfa_uses_global_table(gpu_red, redlib, oracle_cls):
     """BASELINE configs[2]: a union too large for shared memory (L2-resident
     global table, 4-byte entries), first/last styles."""

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Small fixed workload over the paths around the batch matcher (line index,
+long stream, compaction, sliding verbs) - run plainly for timings, and under
+`ncu --metrics gpu__time_duration.sum` for the per-kernel launch list."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from one_b200 import red  # noqa: E402
+
+
+def timed(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+def main():
+    lines = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
+    dev = torch.device("cuda", 0)
+    pool = bench.host_pool(1234)
+    text, starts, lens, n = bench.device_corpus(pool, lines, dev)
+    gb = text.numel() / 1e9
+    ms = timed(lambda: red.split_lines_device(text, capacity=n + 1))
+    print("line index %.2f GB: %.3f ms %.0f GB/s" % (gb, ms, gb / ms * 1e3), flush=True)
+    stream_gb = float(sys.argv[2]) if len(sys.argv) > 2 else 2.0
+    reps = max(1, int(stream_gb / gb))
+    big = text.repeat(reps) if reps > 1 else text
+    bgb = big.numel() / 1e9
+    for name in ("union64", "single_auto"):
+        prog = red.Program(bench.load_program_blob(name))
+        for sty in ("last", "full", "instant"):
+            ms = timed(lambda: prog.match_stream_device(big, "match", sty))
+            print("stream %.2f GB %-11s %-8s: %.3f ms %.0f GB/s -> %s" % (
+                bgb, name, sty, ms, bgb / ms * 1e3, tuple(prog.match_stream_device(big, "match", sty))), flush=True)
+        prog.close()
+    del big
+    prog = red.Program(bench.load_program_blob("union64"))
+    res = torch.empty(n, dtype=torch.int32, device=dev)
+    prog.match_batch_device(text, starts, lens, "match", "instant", out=(res, None, None))
+    ms = timed(lambda: red.compact_matches_device(res))
+    print("compaction of %d results: %.3f ms" % (n, ms), flush=True)
+    prog.close()
+    # sliding verbs: the same 64 phrases with tight ends (a loose-start program
+    # makes search() quadratic by definition, in the reference as well)
+    from one_b200 import synth
+    p = red.Parser()
+    for i, ph in enumerate(synth.PHRASES):
+        p.addAs(synth.LANG_RAW, ph, i + 1, 0)
+    prog = red.Program(red.compileToSerialized(p))
+    m = min(n, 2_000_000)
+    ends = torch.empty(m, dtype=torch.int32, device=dev)
+    nb = int(lens[:m].sum().item())
+    for verb in ("search", "scan"):
+        ms = timed(lambda: prog.match_batch_device(text, starts[:m], lens[:m], verb, "last",
+                                                   out=(res[:m], ends if verb == "search" else None, ends)), reps=2)
+        print("%s/last (64 tight phrases) on %d lines: %.3f ms %.1f GB/s, %d hits" % (
+            verb, m, ms, nb / ms / 1e6, int((res[:m] > 0).sum().item())), flush=True)
+    prog.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,8 @@ def main():
                 env["RED_B200_VARIANT"] = "0"
             elif kv == "v1":
                 env["RED_B200_VARIANT"] = "1"
+            elif kv == "v2":
+                env["RED_B200_VARIANT"] = "2"
             elif kv == "v3":
                 env["RED_B200_VARIANT"] = "3"
             elif kv.startswith("T"):
