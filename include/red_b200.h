@@ -190,6 +190,73 @@ int red_b200_multi_batch_host(const red_b200_program *prog,
                               uint64_t n_lines, int which, uint32_t max_per_line,
                               uint32_t *counts, red_b200_span *spans);
 
+/* ---- replace() ------------------------------------------------------------ */
+
+/* Rewrite every line: each non-overlapping match, found by trying every
+   position of the line in order, is substituted by `repl`; at most
+   max_per_line substitutions per line (reference: replace(),
+   include/Matcher.h:100-125; replaceCore, :643-707; `max` as there).
+   Output: the rewritten lines packed into d_out_text, each followed by the
+   byte out_delim unless out_delim < 0; d_out_starts/d_out_lens index them
+   (lengths exclude the delimiter); d_counts[i] = substitutions made in line i.
+   `repl` is HOST memory.  *out_bytes (host) gets the size of the packed
+   output; if that exceeds out_capacity nothing is written to d_out_text and
+   the call returns RED_B200_ELIMIT - call again with a buffer of *out_bytes.
+   Device pointers otherwise; synchronous on `stream`. */
+int red_b200_replace_batch_device(const red_b200_program *prog,
+                                  const uint8_t *d_text, const uint64_t *d_starts,
+                                  const uint32_t *d_lens, uint64_t n_lines,
+                                  const uint8_t *repl, uint32_t repl_len,
+                                  uint64_t max_per_line, int style, int out_delim,
+                                  uint8_t *d_out_text, uint64_t out_capacity,
+                                  uint64_t *d_out_starts, uint32_t *d_out_lens,
+                                  uint32_t *d_counts, uint64_t *out_bytes,
+                                  void *stream);
+
+/* Same with host buffers (moderate batches).  Synchronous. */
+int red_b200_replace_batch_host(const red_b200_program *prog,
+                                const uint8_t *text, uint64_t text_len,
+                                const uint64_t *starts, const uint32_t *lens,
+                                uint64_t n_lines, const uint8_t *repl, uint32_t repl_len,
+                                uint64_t max_per_line, int style, int out_delim,
+                                uint8_t *out_text, uint64_t out_capacity,
+                                uint64_t *out_starts, uint32_t *out_lens,
+                                uint32_t *counts, uint64_t *out_bytes);
+
+/* One text (the reference's replace(exec, ptr, len, repl, out, max, style)):
+   writes at most out_capacity bytes, *out_len is the rewritten length
+   (RED_B200_ELIMIT if it did not fit), *count the substitutions. */
+int red_b200_replace(const red_b200_program *prog, const void *text, size_t len,
+                     const void *repl, size_t repl_len, uint64_t max, int style,
+                     void *out, size_t out_capacity, size_t *out_len, uint64_t *count);
+
+/* ---- StatefulMatcher -------------------------------------------------------- */
+
+/* The reference's StatefulMatcher (include/Matcher.h:770-794) keeps one DFA
+   state and is fed byte by byte.  Here the caller keeps the state - an opaque
+   u32 per stream, valid only with the program that produced it - and feeds a
+   SEGMENT per stream per call; RED_B200_STATE_FRESH starts a new matcher.
+   d_results[i] is result() after the segment (for an empty segment: of the
+   state as it is).  Optional: d_hit_results[i] / d_hit_ends[i], the result at
+   and the offset one past the last accepting position inside the segment
+   (0 / 0 if none) - what a caller polling advance() per byte would have seen
+   last.  Device pointers; asynchronous on `stream`. */
+#define RED_B200_STATE_FRESH 0xffffffffu
+int red_b200_advance_batch_device(const red_b200_program *prog,
+                                  const uint8_t *d_text, const uint64_t *d_starts,
+                                  const uint32_t *d_lens, uint64_t n_streams,
+                                  uint32_t *d_states, int32_t *d_results,
+                                  int32_t *d_hit_results, uint32_t *d_hit_ends,
+                                  void *stream);
+
+/* Same with host buffers.  Synchronous. */
+int red_b200_advance_batch_host(const red_b200_program *prog,
+                                const uint8_t *text, uint64_t text_len,
+                                const uint64_t *starts, const uint32_t *lens,
+                                uint64_t n_streams, uint32_t *states,
+                                int32_t *results, int32_t *hit_results,
+                                uint32_t *hit_ends);
+
 /* ---- line index and match compaction ----------------------------------- */
 
 /* Split d_text[0..text_len) at `delim` bytes: writes the start offset and the

@@ -670,6 +670,252 @@ int red_b200_multi_batch_host(const red_b200_program *cprog,
   return rc;
 }
 
+int red_b200_replace_batch_device(const red_b200_program *cprog,
+                                  const uint8_t *d_text, const uint64_t *d_starts,
+                                  const uint32_t *d_lens, uint64_t n_lines,
+                                  const uint8_t *repl, uint32_t repl_len,
+                                  uint64_t max_per_line, int style, int out_delim,
+                                  uint8_t *d_out_text, uint64_t out_capacity,
+                                  uint64_t *d_out_starts, uint32_t *d_out_lens,
+                                  uint32_t *d_counts, uint64_t *out_bytes,
+                                  void *stream) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog || !out_bytes)
+    return fail(RED_B200_EAPI, "null argument");
+  *out_bytes = 0;
+  if (!valid_style(style))
+    return fail(RED_B200_EEXEC, "unsupported style");
+  if (out_delim > 255)
+    return fail(RED_B200_EAPI, "delimiter is not a byte");
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!d_text || !d_starts || !d_lens || !d_out_starts || !d_out_lens || !d_counts ||
+      (repl_len && !repl))
+    return fail(RED_B200_EAPI, "null buffer");
+  DeviceGuard guard(prog->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t *dRepl = nullptr;
+  uint64_t *dTotal = nullptr;
+  auto done = [&](int rc) {
+    scratch_free(dRepl, st);
+    scratch_free(dTotal, st);
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = scratch_alloc(&dRepl, repl_len + 1, st)) != cudaSuccess ||
+      (e = scratch_alloc(&dTotal, 8, st)) != cudaSuccess ||
+      (repl_len && (e = cudaMemcpyAsync(dRepl, repl, repl_len, cudaMemcpyHostToDevice, st)) != cudaSuccess))
+    return done(cuda_fail(e, "replace staging"));
+  int launches = 0;
+  const int delim = (out_delim < 0) ? -1 : out_delim;
+  // pass 0: substitutions and rewritten length per line
+  e = launch_batch_replace(prog->dev, prog->smemTable, false, d_text, d_starts, d_lens, n_lines,
+                           style, max_per_line, dRepl, repl_len, delim, d_counts, d_out_lens,
+                           nullptr, nullptr, prog->geo, st, &launches);
+  if (e != cudaSuccess)
+    return done(cuda_fail(e, "replace kernel launch"));
+  std::string why;
+  int rc = exclusive_offsets(d_out_lens, n_lines, delim >= 0 ? 1u : 0u, d_out_starts, dTotal, st, why);
+  if (rc != RED_B200_OK)
+    return done(fail(rc, why));
+  launches += 3;
+  uint64_t total = 0;
+  if ((e = cudaMemcpyAsync(&total, dTotal, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(st)) != cudaSuccess)
+    return done(cuda_fail(e, "replace sizes"));
+  *out_bytes = total;
+  prog->launches += launches;
+  if (total > out_capacity)
+    return done(fail(RED_B200_ELIMIT, "output buffer too small for the rewritten text"));
+  if (total && !d_out_text)
+    return done(fail(RED_B200_EAPI, "null output buffer"));
+  // pass 1: write
+  launches = 0;
+  e = launch_batch_replace(prog->dev, prog->smemTable, true, d_text, d_starts, d_lens, n_lines,
+                           style, max_per_line, dRepl, repl_len, delim, nullptr, nullptr,
+                           d_out_starts, d_out_text, prog->geo, st, &launches);
+  if (e != cudaSuccess)
+    return done(cuda_fail(e, "replace kernel launch"));
+  prog->launches += launches;
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess)  // dRepl is pageable-staged: keep it simple
+    return done(cuda_fail(e, "replace"));
+  return done(RED_B200_OK);
+}
+
+namespace {
+
+// host lines -> device (simple staging for the moderate-batch entry points)
+struct StagedLines {
+  uint8_t *dText = nullptr;
+  uint64_t *dStarts = nullptr;
+  uint32_t *dLens = nullptr;
+  cudaError_t put(const uint8_t *text, uint64_t textLen, const uint64_t *starts,
+                  const uint32_t *lens, uint64_t n) {
+    cudaError_t e;
+    if ((e = cudaMalloc(&dText, textLen + 64)) != cudaSuccess ||
+        (e = cudaMalloc(&dStarts, n * 8 + 8)) != cudaSuccess ||
+        (e = cudaMalloc(&dLens, n * 4 + 4)) != cudaSuccess ||
+        (e = cudaMemcpy(dText, text, textLen, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dStarts, starts, n * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(dLens, lens, n * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+      return e;
+    return cudaSuccess;
+  }
+  ~StagedLines() {
+    cudaFree(dText);
+    cudaFree(dStarts);
+    cudaFree(dLens);
+  }
+};
+
+} // anonymous
+
+int red_b200_replace_batch_host(const red_b200_program *cprog,
+                                const uint8_t *text, uint64_t text_len,
+                                const uint64_t *starts, const uint32_t *lens,
+                                uint64_t n_lines, const uint8_t *repl, uint32_t repl_len,
+                                uint64_t max_per_line, int style, int out_delim,
+                                uint8_t *out_text, uint64_t out_capacity,
+                                uint64_t *out_starts, uint32_t *out_lens,
+                                uint32_t *counts, uint64_t *out_bytes) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog || !out_bytes)
+    return fail(RED_B200_EAPI, "null argument");
+  *out_bytes = 0;
+  if (n_lines == 0)
+    return RED_B200_OK;
+  if (!text || !starts || !lens || !out_starts || !out_lens || !counts)
+    return fail(RED_B200_EAPI, "null buffer");
+  for (uint64_t i = 0; i < n_lines; ++i)
+    if (starts[i] + lens[i] > text_len)
+      return fail(RED_B200_EAPI, "line extends past end of text");
+  DeviceGuard guard(prog->device);
+  StagedLines in;
+  uint8_t *dOut = nullptr;
+  uint64_t *dOutStarts = nullptr;
+  uint32_t *dOutLens = nullptr, *dCounts = nullptr;
+  auto done = [&](int rc) {
+    cudaFree(dOut); cudaFree(dOutStarts); cudaFree(dOutLens); cudaFree(dCounts);
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = in.put(text, text_len, starts, lens, n_lines)) != cudaSuccess ||
+      (e = cudaMalloc(&dOut, out_capacity + 1)) != cudaSuccess ||
+      (e = cudaMalloc(&dOutStarts, n_lines * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&dOutLens, n_lines * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dCounts, n_lines * 4)) != cudaSuccess)
+    return done(cuda_fail(e, "replace staging"));
+  int rc = red_b200_replace_batch_device(prog, in.dText, in.dStarts, in.dLens, n_lines, repl,
+                                         repl_len, max_per_line, style, out_delim, dOut,
+                                         out_capacity, dOutStarts, dOutLens, dCounts, out_bytes,
+                                         nullptr);
+  if ((rc == RED_B200_OK) || (rc == RED_B200_ELIMIT)) {
+    // sizes and counts are valid in both cases
+    if ((e = cudaMemcpy(out_lens, dOutLens, n_lines * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (e = cudaMemcpy(out_starts, dOutStarts, n_lines * 8, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (e = cudaMemcpy(counts, dCounts, n_lines * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        ((rc == RED_B200_OK) && *out_bytes &&
+         (e = cudaMemcpy(out_text, dOut, *out_bytes, cudaMemcpyDeviceToHost)) != cudaSuccess))
+      return done(cuda_fail(e, "replace copy-out"));
+  }
+  return done(rc);
+}
+
+int red_b200_replace(const red_b200_program *prog, const void *text, size_t len,
+                     const void *repl, size_t repl_len, uint64_t max, int style,
+                     void *out, size_t out_capacity, size_t *out_len, uint64_t *count) {
+  if (!out_len || !count)
+    return fail(RED_B200_EAPI, "null argument");
+  *out_len = 0;
+  *count = 0;
+  if (len == 0)
+    return prog ? RED_B200_OK : fail(RED_B200_EAPI, "null program");
+  if (len > 0xffffffffull)
+    return fail(RED_B200_ELIMIT, "text too long for replace (4 GB)");
+  if (repl_len > 0xffffffffull)
+    return fail(RED_B200_ELIMIT, "replacement too long");
+  uint64_t start = 0, outStart = 0, bytes = 0;
+  uint32_t l = static_cast<uint32_t>(len), outLen = 0, cnt = 0;
+  int rc = red_b200_replace_batch_host(prog, static_cast<const uint8_t *>(text), len, &start, &l, 1,
+                                       static_cast<const uint8_t *>(repl),
+                                       static_cast<uint32_t>(repl_len), max, style, -1,
+                                       static_cast<uint8_t *>(out), out_capacity, &outStart,
+                                       &outLen, &cnt, &bytes);
+  *out_len = bytes;
+  *count = cnt;
+  return rc;
+}
+
+int red_b200_advance_batch_device(const red_b200_program *cprog,
+                                  const uint8_t *d_text, const uint64_t *d_starts,
+                                  const uint32_t *d_lens, uint64_t n_streams,
+                                  uint32_t *d_states, int32_t *d_results,
+                                  int32_t *d_hit_results, uint32_t *d_hit_ends,
+                                  void *stream) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if (n_streams == 0)
+    return RED_B200_OK;
+  if (!d_starts || !d_lens || !d_states || !d_results)
+    return fail(RED_B200_EAPI, "null buffer");
+  DeviceGuard guard(prog->device);
+  int launches = 0;
+  cudaError_t err = launch_batch_advance(prog->dev, prog->smemTable, d_text, d_starts, d_lens,
+                                         n_streams, d_states, d_results, d_hit_results,
+                                         d_hit_ends, prog->geo,
+                                         static_cast<cudaStream_t>(stream), &launches);
+  if (err != cudaSuccess)
+    return cuda_fail(err, "advance kernel launch");
+  prog->launches += launches;
+  return RED_B200_OK;
+}
+
+int red_b200_advance_batch_host(const red_b200_program *cprog,
+                                const uint8_t *text, uint64_t text_len,
+                                const uint64_t *starts, const uint32_t *lens,
+                                uint64_t n_streams, uint32_t *states,
+                                int32_t *results, int32_t *hit_results,
+                                uint32_t *hit_ends) {
+  red_b200_program *prog = const_cast<red_b200_program *>(cprog);
+  if (!prog)
+    return fail(RED_B200_EAPI, "null program");
+  if (n_streams == 0)
+    return RED_B200_OK;
+  if (!starts || !lens || !states || !results || (text_len && !text))
+    return fail(RED_B200_EAPI, "null buffer");
+  for (uint64_t i = 0; i < n_streams; ++i)
+    if (starts[i] + lens[i] > text_len)
+      return fail(RED_B200_EAPI, "segment extends past end of text");
+  DeviceGuard guard(prog->device);
+  StagedLines in;
+  uint32_t *dStates = nullptr, *dHitEnds = nullptr;
+  int32_t *dRes = nullptr, *dHit = nullptr;
+  auto done = [&](int rc) {
+    cudaFree(dStates); cudaFree(dHitEnds); cudaFree(dRes); cudaFree(dHit);
+    return rc;
+  };
+  cudaError_t e;
+  static const uint8_t none = 0;
+  if ((e = in.put(text ? text : &none, text_len, starts, lens, n_streams)) != cudaSuccess ||
+      (e = cudaMalloc(&dStates, n_streams * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dRes, n_streams * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dHit, n_streams * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&dHitEnds, n_streams * 4)) != cudaSuccess ||
+      (e = cudaMemcpy(dStates, states, n_streams * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return done(cuda_fail(e, "advance staging"));
+  int rc = red_b200_advance_batch_device(prog, in.dText, in.dStarts, in.dLens, n_streams, dStates,
+                                         dRes, dHit, dHitEnds, nullptr);
+  if (rc == RED_B200_OK) {
+    if ((e = cudaMemcpy(states, dStates, n_streams * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (e = cudaMemcpy(results, dRes, n_streams * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+        (hit_results && (e = cudaMemcpy(hit_results, dHit, n_streams * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) ||
+        (hit_ends && (e = cudaMemcpy(hit_ends, dHitEnds, n_streams * 4, cudaMemcpyDeviceToHost)) != cudaSuccess))
+      rc = cuda_fail(e, "advance copy-out");
+  }
+  return done(rc);
+}
+
 int red_b200_split_lines_device(const uint8_t *d_text, uint64_t text_len,
                                 uint8_t delim, uint64_t capacity,
                                 uint64_t *d_starts, uint32_t *d_lens,

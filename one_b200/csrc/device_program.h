@@ -88,6 +88,23 @@ cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8
                                MultiSpan *spans, const LaunchGeometry &geo,
                                cudaStream_t stream, int *launches);
 
+// replace() per line in two passes (kernels_multi.cu): write = false fills
+// counts/outLens, write = true writes the rewritten lines at outStarts
+cudaError_t launch_batch_replace(const ProgramDev &pd, bool smemTable, bool write,
+                                 const uint8_t *text, const uint64_t *starts,
+                                 const uint32_t *lens, uint64_t nLines, int style,
+                                 uint64_t maxRepl, const uint8_t *repl, uint32_t replLen,
+                                 int delim, uint32_t *counts, uint32_t *outLens,
+                                 const uint64_t *outStarts, uint8_t *outText,
+                                 const LaunchGeometry &geo, cudaStream_t stream, int *launches);
+
+// StatefulMatcher::advance over one segment per line, state carried in states[]
+cudaError_t launch_batch_advance(const ProgramDev &pd, bool smemTable, const uint8_t *text,
+                                 const uint64_t *starts, const uint32_t *lens, uint64_t nLines,
+                                 uint32_t *states, int32_t *results, int32_t *hitResults,
+                                 uint32_t *hitEnds, const LaunchGeometry &geo,
+                                 cudaStream_t stream, int *launches);
+
 // verbs scan/search (sliding start position)
 cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
                                  const BatchArgs &args, int style,

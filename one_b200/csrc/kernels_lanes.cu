@@ -615,7 +615,8 @@ cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
     uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 8;
     want = std::max(1u, std::min(want, 32u));
     const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * perSm * (threads / 32) * 2;
-    while ((want > 1) && ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
+    while (!tune.linesPerLane && (want > 1) &&
+           ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
       want >>= 1;
     while ((want > 1) && (sorted_smem_bytes(threads / 32, want) > room))
       want >>= 1;

@@ -123,6 +123,167 @@ batch_multi_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *sta
   }
 }
 
+/* replace() for one line (reference: replaceCore, Matcher.h:643-707): every
+   position in order; a match is substituted and skipped, anything else is
+   copied through; after maxRepl substitutions the rest is copied.  The leader
+   test of the reference (lookingAt, :663) only avoids walks that would fail on
+   their own, so it is not repeated here.  WRITE = false only measures. */
+template <bool WRITE, class Tab, class ClsT>
+__device__ __forceinline__ uint32_t replace_line(const ProgramDev &pd, const Tab &tab,
+                                                 const ClsT *cls, const uint8_t *p,
+                                                 uint32_t len, int style, uint64_t maxRepl,
+                                                 const uint8_t *repl, uint32_t replLen,
+                                                 uint8_t *out, uint32_t &outLen) {
+  uint32_t cnt = 0, o = 0, pos = 0;
+  while (pos < len) {
+    if (cnt >= maxRepl) {
+      if (WRITE)
+        for (uint32_t ii = pos; ii < len; ++ii)
+          out[o + ii - pos] = __ldg(p + ii);
+      o += len - pos;
+      break;
+    }
+    bool have = false;
+    uint32_t found = 0;
+    uint32_t v = pd.initV;
+    int32_t prev = 0;
+    for (uint32_t idx = pos; idx < len; ++idx) {
+      v = tab.next(v, cls[__ldg(p + idx)]);
+      if ((v >= pd.acceptV) && (v < pd.pureV)) {
+        if (style == STY_FIRST) {
+          const int32_t r = pd.results[state_index(pd, v)];
+          if (prev && (r != prev))
+            break;
+          prev = r;
+        }
+        have = true;
+        found = idx;
+        if (style == STY_INSTANT)
+          break;
+        if (v >= pd.absV) {
+          // can never be left: every later position accepts with this result
+          found = len - 1;
+          break;
+        }
+      }
+      else {
+        if (style == STY_FULL)
+          have = false;
+        if ((((style == STY_FIRST) || (style == STY_TANGENT)) && have) || (v >= pd.pureV))
+          break;
+      }
+    }
+    if (have) {
+      if (WRITE)
+        for (uint32_t ii = 0; ii < replLen; ++ii)
+          out[o + ii] = __ldg(repl + ii);
+      o += replLen;
+      pos = found + 1;
+      ++cnt;
+    }
+    else {
+      if (WRITE)
+        out[o] = __ldg(p + pos);
+      ++o;
+      ++pos;
+    }
+  }
+  outLen = o;
+  return cnt;
+}
+
+/* pass 0 (WRITE = false): counts[line], outLens[line].
+   pass 1 (WRITE = true): the rewritten line at outText + outStarts[line],
+   followed by the delimiter if one is asked for. */
+template <bool SMEM, int K, class ClsT, bool WRITE>
+__global__ void __launch_bounds__(256)
+batch_replace_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *starts,
+                     const uint32_t *lens, uint64_t nLines, int style, uint64_t maxRepl,
+                     const uint8_t *repl, uint32_t replLen, int delim, uint32_t *counts,
+                     uint32_t *outLens, const uint64_t *outStarts, uint8_t *outText) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes
+                     : static_cast<const unsigned char *>(pd.table)};
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t line = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       line < nLines; line += stride) {
+    const uint8_t *p = text + starts[line];
+    const uint32_t len = lens[line];
+    uint32_t outLen = 0;
+    uint8_t *out = WRITE ? outText + outStarts[line] : nullptr;
+    const uint32_t cnt = replace_line<WRITE>(pd, tab, cls, p, len, style, maxRepl, repl,
+                                             replLen, out, outLen);
+    if (WRITE) {
+      if (delim >= 0)
+        out[outLen] = static_cast<uint8_t>(delim);
+    }
+    else {
+      counts[line] = cnt;
+      outLens[line] = outLen;
+    }
+  }
+}
+
+/* StatefulMatcher::advance over a segment per line (Matcher.h:770-794): the
+   state comes from and goes back to states[line]; kStateFresh starts a new
+   matcher.  results[line] is result() after the segment (for an empty segment
+   the result of the state itself); hitResults/hitEnds describe the last
+   accepting position inside the segment (0/0: none). */
+constexpr uint32_t kStateFresh = 0xffffffffu;
+
+template <bool SMEM, int K, class ClsT>
+__global__ void __launch_bounds__(256)
+batch_advance_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *starts,
+                     const uint32_t *lens, uint64_t nLines, uint32_t *states,
+                     int32_t *results, int32_t *hitResults, uint32_t *hitEnds) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes
+                     : static_cast<const unsigned char *>(pd.table)};
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t line = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       line < nLines; line += stride) {
+    const uint8_t *p = text + starts[line];
+    const uint32_t len = lens[line];
+    uint32_t v = states[line];
+    if (v == kStateFresh)
+      v = pd.initV;
+    uint32_t hitV = kNone, hitEnd = 0;
+    for (uint32_t idx = 0; idx < len; ++idx) {
+      v = tab.next(v, cls[__ldg(p + idx)]);
+      if (v >= pd.acceptV) {
+        if (v >= pd.absV) {
+          // never left again: pure dead end, or accepting for the rest
+          if (v < pd.pureV) {
+            hitV = v;
+            hitEnd = len;
+          }
+          break;
+        }
+        hitV = v;
+        hitEnd = idx + 1;
+      }
+    }
+    states[line] = v;
+    results[line] = ((v >= pd.acceptV) && (v < pd.pureV)) ? pd.results[state_index(pd, v)] : 0;
+    if (hitResults)
+      hitResults[line] = (hitV != kNone) ? pd.results[state_index(pd, hitV)] : 0;
+    if (hitEnds)
+      hitEnds[line] = hitEnd;
+  }
+}
+
 template <bool SMEM, int K, class ClsT>
 cudaError_t launch_multi(const ProgramDev &pd, const uint8_t *text, const uint64_t *starts,
                          const uint32_t *lens, uint64_t nLines, int which,
@@ -143,6 +304,22 @@ cudaError_t launch_multi(const ProgramDev &pd, const uint8_t *text, const uint64
   return cudaGetLastError();
 }
 
+template <bool SMEM, int K, class ClsT, class Kern, class... Args>
+cudaError_t launch_line_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
+                               const LaunchGeometry &geo, cudaStream_t stream, Args... args) {
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  cudaError_t err = cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess)
+    return err;
+  uint64_t perSm = SMEM ? std::max<uint64_t>(1, std::min<uint64_t>(4, (200u << 10) / smem)) : 4;
+  uint64_t grid = std::min<uint64_t>((nLines + 255) / 256, static_cast<uint64_t>(geo.smCount) * perSm);
+  if (grid == 0)
+    return cudaSuccess;
+  kern<<<static_cast<unsigned>(grid), 256, smem, stream>>>(pd, args...);
+  return cudaGetLastError();
+}
+
 } // anonymous
 
 cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8_t *text,
@@ -153,6 +330,68 @@ cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8
   const bool cls8 = pd.clsMaxOffset < 256;
   cudaError_t err;
 #define GO(S, KK, CT) launch_multi<S, KK, CT>(pd, text, starts, lens, nLines, which, maxPerLine, counts, spans, geo, stream)
+  if (smemTable) {
+    if (pd.unitShift == 0)
+      err = cls8 ? GO(true, 1, uint8_t) : GO(true, 1, uint16_t);
+    else if (pd.unitShift == 1)
+      err = cls8 ? GO(true, 2, uint8_t) : GO(true, 2, uint16_t);
+    else if (pd.unitShift == 8)
+      err = GO(true, 9, uint16_t);
+    else
+      err = cudaErrorInvalidValue;
+  }
+  else
+    err = cls8 ? GO(false, 0, uint8_t) : GO(false, 0, uint16_t);
+#undef GO
+  if ((err == cudaSuccess) && launches && nLines)
+    *launches += 1;
+  return err;
+}
+
+} // namespace red_b200
+
+namespace red_b200 {
+
+cudaError_t launch_batch_replace(const ProgramDev &pd, bool smemTable, bool write,
+                                 const uint8_t *text, const uint64_t *starts,
+                                 const uint32_t *lens, uint64_t nLines, int style,
+                                 uint64_t maxRepl, const uint8_t *repl, uint32_t replLen,
+                                 int delim, uint32_t *counts, uint32_t *outLens,
+                                 const uint64_t *outStarts, uint8_t *outText,
+                                 const LaunchGeometry &geo, cudaStream_t stream, int *launches) {
+  const bool cls8 = pd.clsMaxOffset < 256;
+  cudaError_t err;
+#define GO2(S, KK, CT, W) launch_line_kernel<S, KK, CT>(batch_replace_kernel<S, KK, CT, W>, pd, nLines, geo, stream, \
+    text, starts, lens, nLines, style, maxRepl, repl, replLen, delim, counts, outLens, outStarts, outText)
+#define GO(S, KK, CT) (write ? GO2(S, KK, CT, true) : GO2(S, KK, CT, false))
+  if (smemTable) {
+    if (pd.unitShift == 0)
+      err = cls8 ? GO(true, 1, uint8_t) : GO(true, 1, uint16_t);
+    else if (pd.unitShift == 1)
+      err = cls8 ? GO(true, 2, uint8_t) : GO(true, 2, uint16_t);
+    else if (pd.unitShift == 8)
+      err = GO(true, 9, uint16_t);
+    else
+      err = cudaErrorInvalidValue;
+  }
+  else
+    err = cls8 ? GO(false, 0, uint8_t) : GO(false, 0, uint16_t);
+#undef GO
+#undef GO2
+  if ((err == cudaSuccess) && launches && nLines)
+    *launches += 1;
+  return err;
+}
+
+cudaError_t launch_batch_advance(const ProgramDev &pd, bool smemTable, const uint8_t *text,
+                                 const uint64_t *starts, const uint32_t *lens, uint64_t nLines,
+                                 uint32_t *states, int32_t *results, int32_t *hitResults,
+                                 uint32_t *hitEnds, const LaunchGeometry &geo,
+                                 cudaStream_t stream, int *launches) {
+  const bool cls8 = pd.clsMaxOffset < 256;
+  cudaError_t err;
+#define GO(S, KK, CT) launch_line_kernel<S, KK, CT>(batch_advance_kernel<S, KK, CT>, pd, nLines, geo, stream, \
+    text, starts, lens, nLines, states, results, hitResults, hitEnds)
   if (smemTable) {
     if (pd.unitShift == 0)
       err = cls8 ? GO(true, 1, uint8_t) : GO(true, 1, uint16_t);

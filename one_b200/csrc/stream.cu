@@ -208,6 +208,93 @@ __global__ void write_matches_kernel(const int32_t *results, uint64_t n,
   }
 }
 
+/* exclusive scan of n u32 items (each plus `extra`) into u64 offsets, in
+   blocks of 1024 items: block sums, one-block scan of the sums, re-scan. */
+constexpr int kScanBlockItems = 1024;
+
+__global__ void __launch_bounds__(256)
+block_sums_kernel(const uint32_t *items, uint64_t n, uint32_t extra, uint64_t *blockSums) {
+  __shared__ unsigned long long warpSums[8];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlockItems;
+  unsigned long long sum = 0;
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t i = base + k * 256 + threadIdx.x;
+    if (i < n)
+      sum += static_cast<unsigned long long>(items[i]) + extra;
+  }
+  for (int d = 16; d > 0; d >>= 1)
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0)
+    warpSums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w)
+      t += warpSums[w];
+    blockSums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_sums_kernel(uint64_t *blockSums, uint64_t nBlocks, uint64_t *total) {
+  __shared__ uint64_t partial[kScanThreads];
+  const uint64_t per = (nBlocks + kScanThreads - 1) / kScanThreads;
+  const uint64_t lo = min(nBlocks, per * threadIdx.x);
+  const uint64_t hi = min(nBlocks, lo + per);
+  uint64_t sum = 0;
+  for (uint64_t i = lo; i < hi; ++i)
+    sum += blockSums[i];
+  partial[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < kScanThreads; d <<= 1) {
+    uint64_t add = (threadIdx.x >= d) ? partial[threadIdx.x - d] : 0;
+    __syncthreads();
+    partial[threadIdx.x] += add;
+    __syncthreads();
+  }
+  uint64_t run = partial[threadIdx.x] - sum;
+  for (uint64_t i = lo; i < hi; ++i) {
+    const uint64_t v = blockSums[i];
+    blockSums[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == kScanThreads - 1)
+    *total = partial[kScanThreads - 1];
+}
+
+__global__ void __launch_bounds__(256)
+block_offsets_kernel(const uint32_t *items, uint64_t n, uint32_t extra,
+                     const uint64_t *blockSums, uint64_t *offsets) {
+  __shared__ unsigned long long warpSums[8];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlockItems;
+  // thread t owns items base + 4t .. base + 4t + 3
+  unsigned long long v[4], sum = 0;
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t i = base + threadIdx.x * 4ull + k;
+    v[k] = (i < n) ? static_cast<unsigned long long>(items[i]) + extra : 0;
+    sum += v[k];
+  }
+  unsigned long long incl = sum;
+  const unsigned lane = threadIdx.x & 31;
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d)
+      incl += up;
+  }
+  if (lane == 31)
+    warpSums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned long long run = blockSums[blockIdx.x] + incl - sum;
+  for (unsigned w = 0; w < (threadIdx.x >> 5); ++w)
+    run += warpSums[w];
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t i = base + threadIdx.x * 4ull + k;
+    if (i < n)
+      offsets[i] = run;
+    run += v[k];
+  }
+}
+
 int grid_for(uint64_t nSegs, int threads) {
   uint64_t warpsPerBlock = threads / 32;
   uint64_t blocks = (nSegs + warpsPerBlock - 1) / warpsPerBlock;
@@ -359,6 +446,26 @@ int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
     why = "line index capacity too small";
     return RED_B200_ELIMIT;
   }
+  return RED_B200_OK;
+}
+
+int exclusive_offsets(const uint32_t *dItems, uint64_t n, uint32_t extra,
+                      uint64_t *dOffsets, uint64_t *dTotal, cudaStream_t stream,
+                      std::string &why) {
+  if (n == 0) {
+    TRY(cudaMemsetAsync(dTotal, 0, 8, stream));
+    return RED_B200_OK;
+  }
+  const uint64_t nBlocks = (n + kScanBlockItems - 1) / kScanBlockItems;
+  uint64_t *blockSums = nullptr;
+  TRY(scratch_alloc(&blockSums, nBlocks * 8, stream));
+  block_sums_kernel<<<static_cast<unsigned>(nBlocks), 256, 0, stream>>>(dItems, n, extra, blockSums);
+  scan_block_sums_kernel<<<1, kScanThreads, 0, stream>>>(blockSums, nBlocks, dTotal);
+  block_offsets_kernel<<<static_cast<unsigned>(nBlocks), 256, 0, stream>>>(dItems, n, extra, blockSums, dOffsets);
+  cudaError_t e = cudaGetLastError();
+  scratch_free(blockSums, stream);
+  if (e != cudaSuccess)
+    return cuda_why(e, "exclusive_offsets", why);
   return RED_B200_OK;
 }
 

@@ -51,6 +51,11 @@ int split_lines(const uint8_t *dText, uint64_t len, uint8_t delim,
                 uint64_t capacity, uint64_t *dStarts, uint32_t *dLens,
                 uint64_t *nLinesOut, cudaStream_t stream, std::string &why);
 
+// offsets[i] = sum over j < i of (items[j] + extra); *dTotal = the whole sum
+int exclusive_offsets(const uint32_t *dItems, uint64_t n, uint32_t extra,
+                      uint64_t *dOffsets, uint64_t *dTotal, cudaStream_t stream,
+                      std::string &why);
+
 int compact_matches(const int32_t *dResults, uint64_t n, uint64_t *dIndices,
                     uint64_t *dCount, cudaStream_t stream, std::string &why);
 

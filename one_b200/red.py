@@ -38,6 +38,9 @@ LINE_MATCH_DTYPE = np.dtype([("line_start", "<u8"), ("line_len", "<u4"), ("resul
 
 SPAN_DTYPE = np.dtype([("result", "<i4"), ("start", "<u4"), ("end", "<u4")])
 
+STATE_FRESH = 0xffffffff  # RED_B200_STATE_FRESH: a StatefulMatcher that has seen no input
+_E_LIMIT = -3
+
 Outcome = namedtuple("Outcome", ["result", "start", "end"])
 
 
@@ -127,6 +130,14 @@ def lib():
         L.red_b200_match_stream_device.argtypes = [vp, vp, u64, i32, i32, C.POINTER(_Outcome), vp]
         L.red_b200_multi_batch_device.argtypes = [vp, vp, vp, vp, u64, i32, C.c_uint32, vp, vp, vp]
         L.red_b200_multi_batch_host.argtypes = [vp, vp, u64, vp, vp, u64, i32, C.c_uint32, vp, vp]
+        L.red_b200_replace_batch_device.argtypes = [vp, vp, vp, vp, u64, vp, C.c_uint32, u64, i32, i32,
+                                                    vp, u64, vp, vp, vp, C.POINTER(u64), vp]
+        L.red_b200_replace_batch_host.argtypes = [vp, vp, u64, vp, vp, u64, vp, C.c_uint32, u64, i32, i32,
+                                                  vp, u64, vp, vp, vp, C.POINTER(u64)]
+        L.red_b200_replace.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, u64, i32, vp, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.POINTER(u64)]
+        L.red_b200_advance_batch_device.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp, vp]
+        L.red_b200_advance_batch_host.argtypes = [vp, vp, u64, vp, vp, u64, vp, vp, vp, vp]
         L.red_b200_grep_host.argtypes = [vp, vp, u64, C.c_uint8, i32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
         L.red_b200_compile.argtypes = [i32, C.POINTER(C.c_char_p), vp, vp, vp, vp, i32, u64,
                                        C.POINTER(vp), C.POINTER(u64)]
@@ -342,6 +353,70 @@ class Program:
         c, s = self.multi_batch_host(t, [0], [len(t)], "match_all", cap)
         return [Outcome(int(x["result"]), int(x["start"]), int(x["end"])) for x in s[0][:min(int(c[0]), cap)]]
 
+    def replace_batch_host(self, text, starts, lens, repl, max_per_line=(1 << 63), style=styLast,
+                           out_delim=-1):
+        """replace() per line (Matcher.h:100-125).  -> (out_text uint8[], out_starts uint64[n],
+        out_lens uint32[n], counts uint32[n]); every rewritten line is followed by the byte
+        `out_delim` unless it is < 0."""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        repl = np.frombuffer(_bytes(repl), dtype=np.uint8)
+        n = len(starts)
+        ostarts = np.zeros(n, dtype=np.uint64)
+        olens = np.zeros(n, dtype=np.uint32)
+        counts = np.zeros(n, dtype=np.uint32)
+        need = C.c_uint64()
+        cap = int(lens.sum()) + n + 64
+        while True:
+            out = np.zeros(max(1, cap), dtype=np.uint8)
+            rc = lib().red_b200_replace_batch_host(self._h, text.ctypes.data, text.size, starts.ctypes.data,
+                                                   lens.ctypes.data, n, repl.ctypes.data if repl.size else None,
+                                                   repl.size, int(max_per_line), _style(style), int(out_delim),
+                                                   out.ctypes.data, cap, ostarts.ctypes.data,
+                                                   olens.ctypes.data, counts.ctypes.data, C.byref(need))
+            if (rc == _E_LIMIT) and (need.value > cap):
+                cap = need.value
+                continue
+            _check(rc)
+            return out[:need.value], ostarts, olens, counts
+
+    def replace(self, text, repl, max=(1 << 63), style=styLast):  # noqa: A002 (reference name)
+        """replace(exec, text, repl, out, max, style) -> (count, rewritten text)."""
+        t = np.frombuffer(_bytes(text), dtype=np.uint8)
+        out, _, olens, counts = self.replace_batch_host(t, [0], [len(t)], repl, max, style)
+        return int(counts[0]), out[:int(olens[0])].tobytes()
+
+    def advance_batch_host(self, text, starts, lens, states=None):
+        """StatefulMatcher::advance over one segment per stream (Matcher.h:770-794).
+        states: uint32[n] from a previous call, or None for fresh matchers.
+        -> (states, results int32[n], hit_results int32[n], hit_ends uint32[n])"""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = len(starts)
+        st = np.full(n, STATE_FRESH, dtype=np.uint32) if states is None \
+            else np.array(states, dtype=np.uint32, copy=True)
+        res = np.zeros(n, dtype=np.int32)
+        hit = np.zeros(n, dtype=np.int32)
+        hend = np.zeros(n, dtype=np.uint32)
+        _check(lib().red_b200_advance_batch_host(self._h, text.ctypes.data if text.size else None, text.size,
+                                                 starts.ctypes.data, lens.ctypes.data, n, st.ctypes.data,
+                                                 res.ctypes.data, hit.ctypes.data, hend.ctypes.data))
+        return st, res, hit, hend
+
+    def advance_batch_device(self, text, starts, lens, states, results, hit_results=None,
+                             hit_ends=None, stream=None):
+        """As advance_batch_host on torch CUDA tensors; `states` (int32/uint32 view) is updated
+        in place.  Asynchronous."""
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(text.device).cuda_stream
+        _check(lib().red_b200_advance_batch_device(
+            self._h, text.data_ptr(), starts.data_ptr(), lens.data_ptr(), starts.numel(),
+            states.data_ptr(), results.data_ptr(),
+            hit_results.data_ptr() if hit_results is not None else None,
+            hit_ends.data_ptr() if hit_ends is not None else None, st or None))
+
     def grep_host(self, text, delim=b"\n", style=styInstant, capacity=None):
         """Log blob in (uint8 ndarray / bytes), matching lines out.
 
@@ -366,6 +441,30 @@ class Program:
         _check(lib().red_b200_match_stream_device(self._h, text.data_ptr(), text.numel(),
                                                   _verb(verb), _style(style), C.byref(oc), st or None))
         return Outcome(oc.result, oc.start, oc.end)
+
+
+class StatefulMatcher:
+    """Matcher.h:770-794: one DFA state, fed piece by piece.  advance() takes a
+    byte (as the reference) or a whole bytes object; result() is the result
+    of the current state."""
+
+    def __init__(self, program):
+        self.program = program.program if isinstance(program, Red) else program
+        self._state = None
+        _, res, _, _ = self.program.advance_batch_host(np.zeros(0, np.uint8), [0], [0])
+        self._result = int(res[0])
+
+    def advance(self, data):
+        if isinstance(data, int):
+            data = bytes([data])
+        t = np.frombuffer(_bytes(data), dtype=np.uint8)
+        st, res, _, _ = self.program.advance_batch_host(t, [0], [len(t)], self._state)
+        self._state = st
+        self._result = int(res[0])
+        return self._result
+
+    def result(self):
+        return self._result
 
 
 def split_lines_device(text, delim=b"\n", capacity=None, stream=None):

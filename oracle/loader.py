@@ -84,8 +84,17 @@ class Oracle:
             lib.red_oracle_collect.restype = C.c_uint64
             lib.red_oracle_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                                C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.red_oracle_replace.restype = C.c_uint64
+            lib.red_oracle_replace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                               C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                               C.POINTER(C.c_uint64)]
+            lib.red_oracle_advance.restype = C.c_int32
+            lib.red_oracle_advance.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64,
+                                               C.c_void_p]
             cls._lib = lib
         return cls._lib
+
+    FRESH = 0xffffffffffffffff
 
     def __init__(self, prog: bytes):
         lib = self.lib()
@@ -155,6 +164,29 @@ class Oracle:
         return [(int(res[i]), int(st[i]), int(en[i])) for i in range(n)]
 
 
+    def replace(self, text: bytes, repl: bytes, maxn, style):
+        """-> (count, rewritten text)  (Matcher.h replace)"""
+        cap = len(text) + (len(text) + 1) * max(1, len(repl))
+        out = np.zeros(max(1, cap), dtype=np.uint8)
+        olen = C.c_uint64()
+        cnt = self.lib().red_oracle_replace(self._h, _u8ptr(text), len(text), _u8ptr(repl), len(repl),
+                                            maxn, STYLES.get(style, style), out.ctypes.data, cap,
+                                            C.byref(olen))
+        assert olen.value <= cap
+        return int(cnt), out[:olen.value].tobytes()
+
+    def advance(self, state, data: bytes, per_byte=False):
+        """StatefulMatcher: feed `data` from `state` (Oracle.FRESH = new matcher).
+        -> (new state, result() after the last byte[, per-byte results])"""
+        st = C.c_uint64(state)
+        pb = np.zeros(max(1, len(data)), dtype=np.int32) if per_byte else None
+        res = self.lib().red_oracle_advance(self._h, C.byref(st), _u8ptr(data), len(data),
+                                            pb.ctypes.data if per_byte else None)
+        if per_byte:
+            return st.value, int(res), pb[:len(data)].tolist()
+        return st.value, int(res)
+
+
 class RefError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(msg)
@@ -189,6 +221,7 @@ class RefLib:
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
             lib.ref_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+            lib.ref_stateful.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
             cls._lib = lib
         return cls._lib
 
@@ -265,6 +298,14 @@ class RefLib:
         buf = C.string_at(out.value, outlen.value)
         self.lib().ref_free(out)
         return cnt.value, buf
+
+    def stateful(self, text: bytes):
+        """A fresh StatefulMatcher fed `text`: [result() before input, advance() per byte...]"""
+        res = np.zeros(len(text) + 1, dtype=np.int32)
+        rc = self.lib().ref_stateful(self._h, _u8ptr(text), len(text), res.ctypes.data)
+        if rc != 0:
+            self._raise(rc)
+        return res.tolist()
 
     def multi(self, text: bytes, which, cap=4096):
         """which: 'match_all' (Matcher.h matchAll) or 'collect' (Red::collect)."""

@@ -13,6 +13,8 @@
      - leader helpers                include/Matcher.h:333-360
      - check / match / scan / search include/Matcher.h:363-641
      - replace / matchAll            include/Matcher.h:643-767
+     - StatefulMatcher               include/Matcher.h:770-794,
+                                     lib/Matcher.cpp:106-158
      - Red::collect                  lib/Red.cpp:108-122
 
    Parity pin: tests/test_oracle_golden.py checks this file against
@@ -447,5 +449,124 @@ uint64_t red_oracle_match_all(const red_oracle_prog *pg, const void *text,
   case 1: return match_all_1(pg, t, len, cap, results, starts, ends);
   case 2: return match_all_2(pg, t, len, cap, results, starts, ends);
   default: return match_all_4(pg, t, len, cap, results, starts, ends);
+  }
+}
+
+/* replace(): rewrite the text, substituting `repl` for each non-overlapping
+   match found by trying every position in order (replaceCore,
+   Matcher.h:643-707; the runtime-style entry points use the leader,
+   lib/Matcher.cpp:72-92).  Unlike matchCore the inner walk keeps no start
+   position, Full forgets a match as soon as a later state rejects, and a text
+   position is only ever consumed as part of a match or copied through.
+   Writes at most cap bytes to out; *out_len is the full length.  Returns the
+   number of replacements. */
+#define DEFINE_REPLACE(SFX, T)                                                \
+  static uint64_t replace_##SFX(const red_oracle_prog *pg, const uint8_t *t,  \
+                                uint64_t len, const uint8_t *repl,            \
+                                uint64_t repl_len, uint64_t max, int style,   \
+                                uint8_t *out, uint64_t cap,                   \
+                                uint64_t *out_len) {                          \
+    uint64_t cnt = 0, o = 0, pos = 0;                                         \
+    while (pos < len) {                                                       \
+      if (cnt >= max) {                                                       \
+        for (; pos < len; ++pos, ++o)                                         \
+          if (o < cap) out[o] = t[pos];                                       \
+        break;                                                                \
+      }                                                                       \
+      int have = 0;                                                           \
+      uint64_t found = 0;                                                     \
+      if (leader_at(pg, t, pos, len, NULL)) {                                 \
+        uint64_t s = pg->initialOff;                                          \
+        int32_t prev = 0;                                                     \
+        for (uint64_t idx = pos; idx < len; ++idx) {                          \
+          s = step_##SFX(pg, s, pg->equiv[t[idx]]);                           \
+          T head = rowhead_##SFX(pg, s);                                      \
+          int32_t result = res_##SFX(head);                                   \
+          if (result > 0) {                                                   \
+            if (style == STY_FIRST) {                                         \
+              if (prev && (result != prev))                                   \
+                break;                                                        \
+              prev = result;                                                  \
+            }                                                                 \
+            have = 1;                                                         \
+            found = idx;                                                      \
+            if (style == STY_INSTANT)                                         \
+              break;                                                          \
+          }                                                                   \
+          else {                                                              \
+            if (style == STY_FULL)                                            \
+              have = 0;                                                       \
+            if ((((style == STY_FIRST) || (style == STY_TANGENT)) && have) || \
+                pure_dead_##SFX(head))                                        \
+              break;                                                          \
+          }                                                                   \
+        }                                                                     \
+      }                                                                       \
+      if (have) {                                                             \
+        for (uint64_t ii = 0; ii < repl_len; ++ii, ++o)                       \
+          if (o < cap) out[o] = repl[ii];                                     \
+        pos = found + 1;                                                      \
+        ++cnt;                                                                \
+      }                                                                       \
+      else {                                                                  \
+        if (o < cap) out[o] = t[pos];                                         \
+        ++o;                                                                  \
+        ++pos;                                                                \
+      }                                                                       \
+    }                                                                         \
+    *out_len = o;                                                             \
+    return cnt;                                                               \
+  }
+
+DEFINE_REPLACE(1, uint8_t)
+DEFINE_REPLACE(2, uint16_t)
+DEFINE_REPLACE(4, uint32_t)
+
+uint64_t red_oracle_replace(const red_oracle_prog *pg, const void *text,
+                            uint64_t len, const void *repl, uint64_t repl_len,
+                            uint64_t max, int style, void *out, uint64_t cap,
+                            uint64_t *out_len) {
+  const uint8_t *t = (const uint8_t *)text;
+  const uint8_t *r = (const uint8_t *)repl;
+  switch (pg->fmt) {
+  case 1: return replace_1(pg, t, len, r, repl_len, max, style, (uint8_t *)out, cap, out_len);
+  case 2: return replace_2(pg, t, len, r, repl_len, max, style, (uint8_t *)out, cap, out_len);
+  default: return replace_4(pg, t, len, r, repl_len, max, style, (uint8_t *)out, cap, out_len);
+  }
+}
+
+/* StatefulMatcher (Matcher.h:770-794): the state is carried by the caller.
+   *state is a byte offset from base; pass RED_ORACLE_FRESH to start from the
+   initial state (the constructor, lib/Matcher.cpp:106-139).  Feeds n bytes;
+   per_byte[i] (if not NULL) is what advance() returned for byte i.  Returns
+   result() after the last byte - for n == 0 the result of the state itself. */
+#define RED_ORACLE_FRESH (~(uint64_t)0)
+
+#define DEFINE_ADVANCE(SFX, T)                                                \
+  static int32_t advance_##SFX(const red_oracle_prog *pg, uint64_t *state,    \
+                               const uint8_t *t, uint64_t n,                  \
+                               int32_t *per_byte) {                           \
+    uint64_t s = (*state == RED_ORACLE_FRESH) ? pg->initialOff : *state;      \
+    int32_t result = res_##SFX(rowhead_##SFX(pg, s));                         \
+    for (uint64_t ii = 0; ii < n; ++ii) {                                     \
+      s = step_##SFX(pg, s, pg->equiv[t[ii]]);                                \
+      result = res_##SFX(rowhead_##SFX(pg, s));                               \
+      if (per_byte) per_byte[ii] = result;                                    \
+    }                                                                         \
+    *state = s;                                                               \
+    return result;                                                            \
+  }
+
+DEFINE_ADVANCE(1, uint8_t)
+DEFINE_ADVANCE(2, uint16_t)
+DEFINE_ADVANCE(4, uint32_t)
+
+int32_t red_oracle_advance(const red_oracle_prog *pg, uint64_t *state,
+                           const void *bytes, uint64_t n, int32_t *per_byte) {
+  const uint8_t *t = (const uint8_t *)bytes;
+  switch (pg->fmt) {
+  case 1: return advance_1(pg, state, t, n, per_byte);
+  case 2: return advance_2(pg, state, t, n, per_byte);
+  default: return advance_4(pg, state, t, n, per_byte);
   }
 }

@@ -13,6 +13,7 @@
      check/match/scan/search  (include/Matcher.h:74-94)
      replace / matchAll       (include/Matcher.h:96-129)
      Red::collect             (include/Red.h:109)
+     StatefulMatcher          (include/Matcher.h:770-794)
  */
 
 #include <cstdint>
@@ -178,6 +179,19 @@ int ref_replace(void *h, const char *text, uint64_t len, const char *repl,
     memcpy(mem, out.data(), out.size());
     *outBuf = mem;
     *outLen = out.size();
+    return 0;
+  }
+  catch (const std::exception &ex) { return fail(ex); }
+}
+
+/* A fresh StatefulMatcher fed the text byte by byte: results[0] is result()
+   before any input, results[1 + i] what advance(text[i]) returned. */
+int ref_stateful(void *h, const char *text, uint64_t len, int32_t *results) {
+  try {
+    StatefulMatcher sm(static_cast<RefProg *>(h)->exec);
+    results[0] = sm.result();
+    for (uint64_t ii = 0; ii < len; ++ii)
+      results[1 + ii] = sm.advance(static_cast<Byte>(text[ii]));
     return 0;
   }
   catch (const std::exception &ex) { return fail(ex); }

@@ -71,3 +71,10 @@ def gpu_red(redlib):
     if redlib.device_count() < 1:
         pytest.fail("-m gpu tests need an sm_100 GPU and found none")
     return redlib
+
+
+@pytest.fixture(scope="session")
+def extra_vectors():
+    """replace() / StatefulMatcher outputs of the reference (tools/gen_golden.py)."""
+    with open(os.path.join(GOLDEN, "ref_extra.json")) as f:
+        return json.load(f)

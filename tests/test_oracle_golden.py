@@ -124,3 +124,43 @@ def test_match_all_and_collect_vectors(oracle_cls):
             assert [list(x) for x in o.collect(t)] == co, (case["name"], t)
             n += 1
     assert n > 100
+
+
+def test_replace_and_stateful_vectors(extra_vectors, oracle_cls):
+    """replace() (Matcher.h:643-707) and StatefulMatcher (Matcher.h:770-794)
+    against the reference's outputs, plus the literal expectations of
+    test/matcher.cpp:648-690 and :797-818."""
+    n = 0
+    for case in extra_vectors["cases"]:
+        o = oracle_cls(unz(case["program"]))
+        repls = [unb64(r) for r in case["repls"]]
+        for t, rep, sf in zip(case["texts"], case["replace"], case["stateful"]):
+            t = unb64(t)
+            for key, (cnt, out) in rep.items():
+                sty, mx, ri = key.split("/")
+                assert o.replace(t, repls[int(ri)], int(mx), sty) == (cnt, unb64(out)), (case["name"], t, key)
+                n += 1
+            st, res, per = o.advance(oracle_cls.FRESH, t, per_byte=True)
+            assert [o.advance(oracle_cls.FRESH, b"")[1]] + per == sf, (case["name"], t)
+            # feeding in pieces carries the state
+            st2, _ = o.advance(oracle_cls.FRESH, t[:len(t) // 2])
+            assert o.advance(st2, t[len(t) // 2:]) == (st, res)
+    assert n > 4000
+
+    def prog_of(name):
+        return oracle_cls(unz(next(c for c in extra_vectors["cases"] if c["name"] == name)["program"]))
+    o = prog_of("matcher_cpp_replace")
+    assert o.replace(b"fooac", b"bar", 9999, "last") == (1, b"foobar")
+    assert o.replace(b"fooacz", b"bar", 9999, "last") == (1, b"foobarz")
+    assert o.replace(b"xacyabbcz", b",", 9999, "tangent") == (2, b"x,y,z")
+    o = prog_of("matcher_cpp_replaceStyles")
+    assert o.replace(b"#123defg!", b"xyz", 1, "instant") == (1, b"#xyz23defg!")
+    assert o.replace(b"#123defg!", b"xyz", 9999, "instant") == (3, b"#xyzxyzxyzdefg!")
+    assert o.replace(b"#123defg!", b"xyz", 9999, "first") == (1, b"#xyzdefg!")
+    assert o.replace(b"#123defg!", b"xyz", 9999, "tangent") == (1, b"#xyzefg!")
+    assert o.replace(b"#123defg!", b"xyz", 9999, "last") == (1, b"#xyz!")
+    assert o.replace(b"#123defg!", b"xyz", 9999, "full") == (0, b"#123defg!")
+    assert o.replace(b"#123defg", b"xyz", 9999, "full") == (1, b"#xyz")
+    o = prog_of("matcher_cpp_charByChar")
+    assert o.advance(oracle_cls.FRESH, b"")[1] == 0
+    assert o.advance(oracle_cls.FRESH, b"aleex", per_byte=True)[2] == [0, 0, 1, 1, 2]

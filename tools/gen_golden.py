@@ -322,9 +322,58 @@ def gen_multi():
     print("ref_multi.json: %d cases, %d bytes" % (len(cases), os.path.getsize(path)))
 
 
+def gen_extra():
+    """replace() (Matcher.h:100-125) and StatefulMatcher (Matcher.h:770) outputs."""
+    rng = np.random.RandomState(77)
+    cases = []
+
+    def add(name, rules, texts, repls=(b"X", b"", b"<long replacement>")):
+        prog = RefLib.compile(rules)
+        ref = RefLib(prog)
+        rep = []
+        for t in texts:
+            per = {}
+            for sty in ("instant", "first", "tangent", "last", "full"):
+                for mx in (1, 2, 9999):
+                    for ri, r in enumerate(repls):
+                        cnt, out = ref.replace(t, r, mx, sty)
+                        per["%s/%d/%d" % (sty, mx, ri)] = [cnt, b64(out)]
+            rep.append(per)
+        cases.append({"name": name, "rules": [rule_json(r) for r in rules], "program": zb64(prog),
+                      "texts": [b64(t) for t in texts], "repls": [b64(r) for r in repls],
+                      "replace": rep, "stateful": [ref.stateful(t) for t in texts]})
+
+    # the expectations of test/matcher.cpp (replace, replaceStyles, charByChar)
+    add("matcher_cpp_replace", [("ab*c", 1, 0)], [b"fooac", b"fooacz", b"xacyabbcz", b"", b"abc", b"ab"],
+        repls=(b"bar", b",", b""))
+    add("matcher_cpp_replaceStyles", [("[0-9]+", 1, 0), ("[0-9]+d", 2, 0), ("[0-9]+defg", 3, 0)],
+        [b"#123defg!", b"#123defg", b"1d2d3", b"", b"defg"], repls=(b"xyz", b"", b"0"))
+    add("matcher_cpp_charByChar", [("ale+", 1, 0), ("ale*x", 2, 0)], [b"aleex", b"alx", b"aleexx", b"", b"a"])
+    cities = [("tokyo", 1, F_IGNORE_CASE), ("new", 2, F_IGNORE_CASE), ("new york", 3, F_IGNORE_CASE),
+              ("york", 4, F_IGNORE_CASE), ("sao paulo", 5, F_IGNORE_CASE), ("ab+", 6, 0)]
+    texts = [bytes(rng.choice(list(b"new york tokyoabb NEW sao paulo"), size=rng.randint(0, 60)).astype(np.uint8))
+             for _ in range(40)]
+    texts += [b"I love New York and Tokyo, not Sao Paulo.", b"newnewnew yorkyork", b"abbbabab"]
+    add("cities", cities, texts)
+    add("leader", [("foo[0-9]+", 1, 0)], [b"foo1", b"xfoo12foo3", b"foofoo9", b"", b"fo", b"foo", b"fofoo77x"])
+    add("loose", [("a+", 1, F_LOOSE_START), ("b+", 2, F_LOOSE_START | F_LOOSE_END)],
+        [b".aa..b.bb..abba.", b"", b"ab", b"....", b"bbbb", b"a.b"])
+    add("nullable", [("a*", 1, 0), ("a*b", 2, 0)], [b"", b"aaa", b"aab", b"baab", b"xaax"])
+    add("union64_lines", synth.rules_union64(), synth.make_lines(40, seed=9), repls=(b"#", b""))
+    doc = {"generator": "tools/gen_golden.py", "cases": cases}
+    path = os.path.join(OUT_DIR, "ref_extra.json")
+    with open(path, "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("ref_extra.json: %d cases, %d bytes" % (len(cases), os.path.getsize(path)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--extra-only" in sys.argv:
+        gen_extra()
+        sys.exit(0)
     if "--multi-only" not in sys.argv:
         gen_kat()
         gen_vectors()
     gen_multi()
+    gen_extra()
