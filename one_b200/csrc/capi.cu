@@ -258,6 +258,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.clsMaxOffset = *std::max_element(img.clsOffset.begin(), img.clsOffset.end());
   pd.initResult = img.initResult;
   pd.byteRows = img.byteRows ? 1 : 0;
+  pd.hasFinalStates = img.finalReachable ? 1 : 0;
 
   // cudaMemcpy from pageable memory may return before the DMA has landed, and
   // the kernels run on non-blocking streams that do not order against the
@@ -347,10 +348,12 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
                                prog->tune, ctr, stream, &launches);
     }
   }
-  else
+  else {
+    unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
     err = launch_batch_sliding(prog->dev, prog->smemTable, args, style,
                                verb == RED_B200_VERB_SEARCH, prog->geo, stream,
-                               &launches);
+                               &launches, ctr, prog->tune.simpleWalk);
+  }
   if (err != cudaSuccess)
     return cuda_fail(err, "batch kernel launch");
   prog->launches += launches;

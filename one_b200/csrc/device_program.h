@@ -28,6 +28,7 @@ struct ProgramDev {
   uint32_t clsMaxOffset;  // largest value in clsOffset
   int32_t initResult;
   uint32_t byteRows;    // 1: 256-column rows indexed by the raw byte (unitShift 8)
+  uint32_t hasFinalStates;  // 1: a state >= absV is reachable from the initial state
 };
 
 struct BatchArgs {
@@ -110,6 +111,9 @@ cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
                                  const BatchArgs &args, int style,
                                  bool wantPositions,
                                  const LaunchGeometry &geo,
-                                 cudaStream_t stream, int *launches);
+                                 cudaStream_t stream, int *launches,
+                                 unsigned long long *counter = nullptr,  // zeroable device word: enables
+                                                                         // the warp-per-line kernel
+                                 bool simple = false);                   // force the lane-per-line kernel
 
 } // namespace red_b200

@@ -315,15 +315,114 @@ batch_sliding_kernel(const ProgramDev pd, const BatchArgs args) {
   }
 }
 
+/* The same verbs with a WARP per line: lane l tries start position base + l,
+   32 positions at a time; the lowest lane whose walk matched wins (the
+   attempts are independent, so this is the reference's "first start position
+   that matches").  Most walks die within a byte or two, so a round is a few
+   steps with all lanes busy in the first, and the byte loads of a step are
+   coalesced (adjacent lanes read adjacent bytes).  Not used for scan() on a
+   program with a leader: there the reference skips start positions
+   sequentially (see slide_line). */
+template <int STYLE, bool SEARCH, bool SMEM, int K, class ClsT>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
+                          unsigned long long *lineCounter) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes
+                     : static_cast<const unsigned char *>(pd.table)};
+  const uint32_t lane = threadIdx.x & 31;
+  constexpr uint32_t kBatch = 8;  // lines claimed at a time
+  for (;;) {
+    unsigned long long first = 0;
+    if (lane == 0)
+      first = atomicAdd(lineCounter, static_cast<unsigned long long>(kBatch));
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first >= args.nLines)
+      break;
+    const uint64_t last = min(args.nLines, static_cast<uint64_t>(first) + kBatch);
+    for (uint64_t line = first; line < last; ++line) {
+      const uint8_t *p = args.text + __ldg(args.starts + line);
+      const uint32_t len = __ldg(args.lens + line);
+      int32_t result = 0;
+      uint32_t start = 0, end = 0;
+      if (len == 0) {
+        // empty text: the initial state's result, positions 0
+        Walk<STYLE, SEARCH> wk;
+        wk.begin(pd);
+        wk.finish(pd, 0, result, start, end);
+        start = 0;
+        end = 0;
+      }
+      for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t pos = base + lane;
+        int32_t r = 0;
+        uint32_t s = 0, e = 0;
+        if (pos < len) {
+          Walk<STYLE, SEARCH> wk;
+          wk.begin(pd);
+          wk.mstart = pos;
+          wk.mend = pos;
+          for (uint32_t idx = pos; idx < len; ++idx)
+            if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
+              break;
+          wk.finish(pd, len, r, s, e);
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, r > 0);
+        if (hits) {
+          const int w = __ffs(hits) - 1;
+          result = __shfl_sync(0xffffffffu, r, w);
+          start = __shfl_sync(0xffffffffu, s, w);
+          end = __shfl_sync(0xffffffffu, e, w);
+          break;
+        }
+      }
+      if (lane == 0) {
+        args.results[line] = result;
+        if (args.matchStarts)
+          args.matchStarts[line] = start;
+        if (args.matchEnds)
+          args.matchEnds[line] = end;
+      }
+    }
+  }
+}
+
 template <int STYLE, bool SEARCH, bool SMEM, int K, class ClsT>
 cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
-                         const LaunchGeometry &geo, cudaStream_t stream) {
+                         const LaunchGeometry &geo, cudaStream_t stream,
+                         unsigned long long *counter, bool simple) {
   auto kern = batch_sliding_kernel<STYLE, SEARCH, SMEM, K, ClsT>;
   size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
   cudaError_t err = cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess)
     return err;
+  if (counter && !simple && (SEARCH || (pd.leaderLen == 0))) {
+    auto wkern = batch_sliding_warp_kernel<STYLE, SEARCH, SMEM, K, ClsT>;
+    err = cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return err;
+    if (args.nLines == 0)
+      return cudaSuccess;
+    err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+    if (err != cudaSuccess)
+      return err;
+    // one CTA per SM when the table takes most of the shared memory
+    const uint64_t perSmW = (SMEM && (smem > (100u << 10))) ? 1 : 2;
+    const int wthreads = (perSmW == 1) ? kMaxThreads : 512;
+    const uint64_t warpsNeeded = (args.nLines + 7) / 8;
+    const uint64_t wgrid = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * perSmW,
+                                              (warpsNeeded + wthreads / 32 - 1) / (wthreads / 32));
+    wkern<<<static_cast<unsigned>(wgrid), wthreads, smem, stream>>>(pd, args, counter);
+    return cudaGetLastError();
+  }
   const int threads = 256;  // lines differ wildly in cost: smaller tiles
   uint64_t tiles = (args.nLines + threads - 1) / threads;
   uint64_t perSm = SMEM ? std::max<uint64_t>(1, std::min<uint64_t>(4, (200u << 10) / smem)) : 4;
@@ -337,33 +436,34 @@ cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
 template <int STYLE, bool SEARCH>
 cudaError_t slide_table(const ProgramDev &pd, bool smemTable,
                         const BatchArgs &args, const LaunchGeometry &geo,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, unsigned long long *counter, bool simple) {
   const bool cls8 = pd.clsMaxOffset < 256;
   if (smemTable) {
     if (pd.unitShift == 0)
-      return cls8 ? launch_slide<STYLE, SEARCH, true, 1, uint8_t>(pd, args, geo, stream)
-                  : launch_slide<STYLE, SEARCH, true, 1, uint16_t>(pd, args, geo, stream);
+      return cls8 ? launch_slide<STYLE, SEARCH, true, 1, uint8_t>(pd, args, geo, stream, counter, simple)
+                  : launch_slide<STYLE, SEARCH, true, 1, uint16_t>(pd, args, geo, stream, counter, simple);
     if (pd.unitShift == 1)
-      return cls8 ? launch_slide<STYLE, SEARCH, true, 2, uint8_t>(pd, args, geo, stream)
-                  : launch_slide<STYLE, SEARCH, true, 2, uint16_t>(pd, args, geo, stream);
+      return cls8 ? launch_slide<STYLE, SEARCH, true, 2, uint8_t>(pd, args, geo, stream, counter, simple)
+                  : launch_slide<STYLE, SEARCH, true, 2, uint16_t>(pd, args, geo, stream, counter, simple);
     if (pd.unitShift == 8)
-      return launch_slide<STYLE, SEARCH, true, 9, uint16_t>(pd, args, geo, stream);
+      return launch_slide<STYLE, SEARCH, true, 9, uint16_t>(pd, args, geo, stream, counter, simple);
     return cudaErrorInvalidValue;
   }
-  return cls8 ? launch_slide<STYLE, SEARCH, false, 0, uint8_t>(pd, args, geo, stream)
-              : launch_slide<STYLE, SEARCH, false, 0, uint16_t>(pd, args, geo, stream);
+  return cls8 ? launch_slide<STYLE, SEARCH, false, 0, uint8_t>(pd, args, geo, stream, counter, simple)
+              : launch_slide<STYLE, SEARCH, false, 0, uint16_t>(pd, args, geo, stream, counter, simple);
 }
 
 template <bool SEARCH>
 cudaError_t slide_style(const ProgramDev &pd, bool smemTable,
                         const BatchArgs &args, int style,
-                        const LaunchGeometry &geo, cudaStream_t stream) {
+                        const LaunchGeometry &geo, cudaStream_t stream,
+                        unsigned long long *counter, bool simple) {
   switch (style) {
-  case STY_INSTANT: return slide_table<STY_INSTANT, SEARCH>(pd, smemTable, args, geo, stream);
-  case STY_FIRST:   return slide_table<STY_FIRST, SEARCH>(pd, smemTable, args, geo, stream);
-  case STY_TANGENT: return slide_table<STY_TANGENT, SEARCH>(pd, smemTable, args, geo, stream);
-  case STY_LAST:    return slide_table<STY_LAST, SEARCH>(pd, smemTable, args, geo, stream);
-  case STY_FULL:    return slide_table<STY_FULL, SEARCH>(pd, smemTable, args, geo, stream);
+  case STY_INSTANT: return slide_table<STY_INSTANT, SEARCH>(pd, smemTable, args, geo, stream, counter, simple);
+  case STY_FIRST:   return slide_table<STY_FIRST, SEARCH>(pd, smemTable, args, geo, stream, counter, simple);
+  case STY_TANGENT: return slide_table<STY_TANGENT, SEARCH>(pd, smemTable, args, geo, stream, counter, simple);
+  case STY_LAST:    return slide_table<STY_LAST, SEARCH>(pd, smemTable, args, geo, stream, counter, simple);
+  case STY_FULL:    return slide_table<STY_FULL, SEARCH>(pd, smemTable, args, geo, stream, counter, simple);
   default:          return cudaErrorInvalidValue;
   }
 }
@@ -387,10 +487,11 @@ cudaError_t launch_batch_sliding(const ProgramDev &pd, bool smemTable,
                                  const BatchArgs &args, int style,
                                  bool wantPositions,
                                  const LaunchGeometry &geo,
-                                 cudaStream_t stream, int *launches) {
+                                 cudaStream_t stream, int *launches,
+                                 unsigned long long *counter, bool simple) {
   cudaError_t err = wantPositions
-      ? slide_style<true>(pd, smemTable, args, style, geo, stream)
-      : slide_style<false>(pd, smemTable, args, style, geo, stream);
+      ? slide_style<true>(pd, smemTable, args, style, geo, stream, counter, simple)
+      : slide_style<false>(pd, smemTable, args, style, geo, stream, counter, simple);
   if ((err == cudaSuccess) && launches && args.nLines)
     *launches += 1;
   return err;

@@ -201,6 +201,31 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   img.initResult = pp.result[pp.initialState];
   img.leader = pp.leader;
 
+  // can a walk from the initial state ever reach a state it cannot leave
+  // (absorbing accept or pure dead end)?  The long-stream matcher uses this:
+  // if not, nothing can decide a Last/Full walk before the end of the text.
+  {
+    std::vector<char> seen(n, 0);
+    std::vector<uint32_t> todo{pp.initialState};
+    seen[pp.initialState] = 1;
+    img.finalReachable = false;
+    while (!todo.empty()) {
+      const uint32_t st = todo.back();
+      todo.pop_back();
+      if (oldToNew[st] >= firstAbsorb) {
+        img.finalReachable = true;
+        break;
+      }
+      for (uint32_t c = 0; c < C; ++c) {
+        const uint32_t nx = pp.next[static_cast<size_t>(st) * C + c];
+        if (!seen[nx]) {
+          seen[nx] = 1;
+          todo.push_back(nx);
+        }
+      }
+    }
+  }
+
   // The reference stops walking the moment it enters a pure dead end
   // (Matcher.h:405, 478) and never looks at that row's exits.  Making those
   // rows absorbing in the image is the same semantics, and lets a kernel step

@@ -85,6 +85,7 @@ struct DeviceImage {
   uint32_t pureCount = 0;
   int32_t maxResult = 0;
   bool byteRows = false;    // rows indexed by the raw byte (256 columns), identity class map
+  bool finalReachable = true;  // a state that can never be left is reachable from the initial one
   std::vector<uint16_t> clsOffset;   // 256: class * entryBytes
   std::vector<uint16_t> table16;     // mode smem
   std::vector<uint32_t> table32;     // mode global

@@ -67,7 +67,10 @@ struct ChunkRec {
 struct StreamSummary {
   unsigned long long bad;        // unconfirmed chunks (written by the verify kernel)
   unsigned long long firstBad;   // first of them, or ~0
-  uint64_t firstAccChunk, lastAccChunk, lastLeaveChunk;  // ~0 = none
+  // reduce kernel, by atomics: smallest chunk index with an accept (~0 none),
+  // largest index + 1 with an accept / with a departure from the initial state
+  unsigned long long firstAccChunk, lastAccP1, lastLeaveP1;
+  unsigned int done;             // blocks of the reduce kernel that have finished
   uint32_t firstAccStartV;
   uint32_t lastAccEnd, lastAccV, lastLeaveOff;
   uint32_t finalV;
@@ -190,17 +193,17 @@ __global__ void stream_verify_kernel(ChunkRec *recs, uint64_t nChunks,
 }
 
 /* over the confirmed prefix: first/last chunk with an accepting position, last
-   chunk in which the initial state was left, final state.  One block.
+   chunk in which the initial state was left, final state.  Any grid; the
+   block that finishes last fills in the per-chunk details.
    upTo = ~0: the prefix in front of sum->firstBad (after the verify kernel). */
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 stream_reduce_kernel(const ChunkRec *recs, uint64_t nChunks, uint64_t upTo,
                      StreamSummary *sum) {
-  __shared__ unsigned long long sFirst[32], sLast[32], sLeave[32];
   const uint64_t n = (upTo != ~0ull) ? min(upTo, nChunks)
                                      : min(static_cast<uint64_t>(sum->firstBad), nChunks);
-  // f: smallest chunk index with an accept; l, lv: largest index + 1 (0 = none)
   unsigned long long f = ~0ull, l = 0, lv = 0;
-  for (uint64_t c = threadIdx.x; c < n; c += blockDim.x) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < n; c += stride) {
     if (recs[c].accV != kNone) {
       f = min(f, static_cast<unsigned long long>(c));
       l = c + 1;
@@ -215,25 +218,22 @@ stream_reduce_kernel(const ChunkRec *recs, uint64_t nChunks, uint64_t upTo,
     lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
   }
   if ((threadIdx.x & 31) == 0) {
-    sFirst[threadIdx.x >> 5] = f;
-    sLast[threadIdx.x >> 5] = l;
-    sLeave[threadIdx.x >> 5] = lv;
+    if (f != ~0ull)
+      atomicMin(&sum->firstAccChunk, f);
+    if (l)
+      atomicMax(&sum->lastAccP1, l);
+    if (lv)
+      atomicMax(&sum->lastLeaveP1, lv);
   }
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const unsigned warps = (blockDim.x + 31) >> 5;
-    f = (threadIdx.x < warps) ? sFirst[threadIdx.x] : ~0ull;
-    l = (threadIdx.x < warps) ? sLast[threadIdx.x] : 0;
-    lv = (threadIdx.x < warps) ? sLeave[threadIdx.x] : 0;
-    for (int d = 16; d > 0; d >>= 1) {
-      f = min(f, __shfl_xor_sync(0xffffffffu, f, d));
-      l = max(l, __shfl_xor_sync(0xffffffffu, l, d));
-      lv = max(lv, __shfl_xor_sync(0xffffffffu, lv, d));
-    }
-    if (threadIdx.x == 0) {
-      sum->firstAccChunk = f;
-      sum->lastAccChunk = l ? l - 1 : ~0ull;
-      sum->lastLeaveChunk = lv ? lv - 1 : ~0ull;
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&sum->done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      f = atomicMin(&sum->firstAccChunk, ~0ull);
+      l = atomicMax(&sum->lastAccP1, 0ull);
+      lv = atomicMax(&sum->lastLeaveP1, 0ull);
       sum->firstAccStartV = (f != ~0ull) ? recs[f].startV : 0;
       sum->lastAccEnd = l ? recs[l - 1].accEnd : 0;
       sum->lastAccV = l ? recs[l - 1].accV : 0;
@@ -342,6 +342,12 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     if (w >= 4096)
       firstWindow = w & ~uint64_t(15);
   }
+  // Last/Full on a program without states that can never be left: nothing can
+  // end the walk early, so the whole text is one window
+  const bool earlyStyle = (style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_FIRST) ||
+                          (style == RED_B200_STY_TANGENT);
+  if (!earlyStyle && !pd.hasFinalStates && !getenv("RED_B200_STREAM_WINDOW"))
+    firstWindow = (len + 15) & ~uint64_t(15);
   uint64_t maxChunks = 0;
   for (uint64_t pos = 0, w = firstWindow; pos < len; pos += w, w *= kWindowGrowth) {
     const uint64_t bytes = std::min(w, len - pos);
@@ -383,6 +389,7 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
 
   StreamSummary init{};
   init.firstBad = none;
+  init.firstAccChunk = none;
   int rc = RED_B200_OK;
   bool decided = false;
   uint64_t window = firstWindow;
@@ -397,13 +404,14 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     const unsigned threads = static_cast<unsigned>(std::min<uint64_t>(
         kMaxThreads, ((nChunks + grid - 1) / grid + 31) / 32 * 32));
     const unsigned vgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount * 4, (nChunks + 255) / 256));
+    const unsigned rgrid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(geo.smCount, (nChunks + 1023) / 1024)));
     walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, recs, 1, v0);
     ++*launches;
     StreamSummary sum;
     for (uint64_t round = 0;; ++round) {
       TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
       stream_verify_kernel<<<vgrid, 256, 0, stream>>>(recs, nChunks, v0, dSum);
-      stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, nChunks, none, dSum);
+      stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(recs, nChunks, none, dSum);
       *launches += 2;
       TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
       TRY(cudaStreamSynchronize(stream));
@@ -442,13 +450,14 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
         // an earlier chunk of this window, or in an earlier window
         uint64_t leave = t.lastLeave;
         if ((leave == none) && (c > 0)) {
-          stream_reduce_kernel<<<1, 1024, 0, stream>>>(recs, nChunks, c, dSum);
+          TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
+          stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(recs, nChunks, c, dSum);
           ++*launches;
           StreamSummary before;
           TRY(cudaMemcpyAsync(&before, dSum, sizeof(before), cudaMemcpyDeviceToHost, stream));
           TRY(cudaStreamSynchronize(stream));
-          if (before.lastLeaveChunk != none)
-            leave = base + before.lastLeaveChunk * chunk + before.lastLeaveOff;
+          if (before.lastLeaveP1 != 0)
+            leave = base + (before.lastLeaveP1 - 1) * chunk + before.lastLeaveOff;
         }
         if (leave == none)
           leave = lastLeave;
@@ -459,10 +468,10 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
 
     // fold the window (its confirmed prefix, which is all of it unless the
     // walk was decided) into the running outcome
-    if (sum.lastLeaveChunk != none)
-      lastLeave = base + sum.lastLeaveChunk * chunk + sum.lastLeaveOff;
-    if (sum.lastAccChunk != none) {
-      lastAccEnd = base + sum.lastAccChunk * chunk + sum.lastAccEnd;
+    if (sum.lastLeaveP1 != 0)
+      lastLeave = base + (sum.lastLeaveP1 - 1) * chunk + sum.lastLeaveOff;
+    if (sum.lastAccP1 != 0) {
+      lastAccEnd = base + (sum.lastAccP1 - 1) * chunk + sum.lastAccEnd;
       lastAccV = sum.lastAccV;
     }
     v0 = sum.finalV;

@@ -136,6 +136,34 @@ def test_simple_walk_variant_agrees(gpu_red, vectors, oracle_cls, monkeypatch):
     prog.close()
 
 
+def test_sliding_kernels_agree(gpu_red, redlib, vectors, oracle_cls, monkeypatch):
+    """scan/search: the warp-per-line kernel (32 start positions at a time) and the
+    lane-per-line kernel (RED_B200_SIMPLE_WALK=1; also what scan() uses on a program
+    with a leader) against the oracle, on tight and loose programs."""
+    from one_b200 import synth
+    lines = synth.make_lines(6000, seed=23) + [b"", b"x", b"Failed", b"a" * 700 + b"Failed password" + b"b" * 300]
+    text, starts, lens = synth.pack_lines(lines)
+    p = redlib.Parser()
+    for i, ph in enumerate(synth.PHRASES):
+        p.addAs(synth.LANG_RAW, ph, i + 1, 0)
+    tight = redlib.compileToSerialized(p)
+    blobs = [("tight64", tight)] + [(n, unz(next(c for c in vectors["cases"] if c["name"] == n)["program"]))
+                                    for n in ("single_auto", "leader_class", "newyork", "nullable")]
+    for name, blob in blobs:
+        orc = oracle_cls(blob)
+        for simple in ("0", "1"):
+            monkeypatch.setenv("RED_B200_SIMPLE_WALK", simple)
+            prog = gpu_red.Program(blob)
+            monkeypatch.delenv("RED_B200_SIMPLE_WALK")
+            for verb in ("scan", "search"):
+                for sty in STYLES:
+                    res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
+                    eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
+                    assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), \
+                        (name, simple, verb, sty)
+            prog.close()
+
+
 def test_table_layouts_agree(gpu_red, vectors, oracle_cls, monkeypatch):
     """Small DFAs use byte-indexed rows (one load per byte); the class-compressed
     layout and the v1 tile kernel must give the same answers."""
