@@ -354,6 +354,143 @@ batch_tile_kernel(const ProgramDev pd, const BatchArgs args,
   }
 }
 
+/* batch_tile32_kernel: the tile schedule with 32-byte text loads
+   (LDG.E.256, sm_100).  A lane's text load costs one L1 data-pipe wavefront
+   whatever its width (every lane is in a different 128-byte line), and those
+   wavefronts are a quarter of the LSU pipe's work in the 16-byte version
+   (ncu: l1tex__data_pipe_lsu_wavefronts_mem_lgds vs _mem_shared); loading 32
+   bytes at a time halves them.  Each 32-byte block is walked as two 16-byte
+   chunks by the same engine. */
+struct Text32 {
+  uint4 lo, hi;
+};
+__device__ __forceinline__ Text32 ldg256(const void *p) {
+  Text32 t;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(t.lo.x), "=r"(t.lo.y), "=r"(t.lo.z), "=r"(t.lo.w),
+                 "=r"(t.hi.x), "=r"(t.hi.y), "=r"(t.hi.z), "=r"(t.hi.w)
+               : "l"(p));
+  return t;
+}
+
+template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_tile32_kernel(const ProgramDev pd, const BatchArgs args,
+                    unsigned long long *blockCounter) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint32_t leadLen = LEADER ? pd.leaderLen : 0;
+
+  auto claim = [&]() -> uint64_t {
+    unsigned long long t = 0;
+    if (lane == 0)
+      t = atomicAdd(blockCounter, 1ull);
+    return __shfl_sync(kFull, t, 0) * 32ull + lane;
+  };
+  uint64_t nLine = claim();
+  const uint8_t *nPtr = nullptr;
+  uint32_t nLen = 0;
+  Text32 nFirst;
+  nFirst.lo = nFirst.hi = make_uint4(0, 0, 0, 0);
+  auto fetchMeta = [&]() {
+    if (nLine < n) {
+      nPtr = args.text + __ldg(args.starts + nLine);
+      nLen = __ldg(args.lens + nLine);
+    }
+  };
+  auto fetchFirst = [&]() {
+    if ((nLine < n) && (nLen > leadLen)) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(nPtr + leadLen);
+      nFirst = ldg256(reinterpret_cast<const void *>(a & ~uintptr_t(31)));
+    }
+  };
+  fetchMeta();
+  fetchFirst();
+
+  while (__any_sync(kFull, nLine < n)) {
+    const uint64_t line = nLine;
+    bool active = line < n;
+    const uint8_t *p = nPtr;
+    uint32_t len = active ? nLen : 0;
+    Text32 cur = nFirst, nxt = nFirst;
+    Walk<STYLE, WANT_START> wk;
+    wk.begin(pd);
+    bool noResult = false;
+    if (LEADER && active) {
+      // check() with the leader (Matcher.h:369-376)
+      bool viable = true;
+      for (uint32_t ii = 0; ii < leadLen; ++ii)
+        if ((ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + ii)])) {
+          viable = false;
+          break;
+        }
+      p += leadLen;
+      len = viable ? len - leadLen : 0;
+      wk.v = pd.leaderV;
+      noResult = !viable;
+    }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t skip = active ? static_cast<uint32_t>(a & 31) : 0;
+    const char *blk = reinterpret_cast<const char *>(a - skip);
+    const uint32_t total = skip + len;
+    const uint32_t lineLen = len;
+
+    nLine = claim();
+    fetchMeta();
+    bool wantFirst = true;
+
+    uint32_t k = 0;
+    while (__any_sync(kFull, active)) {
+      uint32_t mask32 = 0;
+      bool lastBlock = true;
+      if (active) {
+        const uint32_t rem = total - k * 32;
+        const uint32_t lo = (k == 0) ? skip : 0;
+        const uint32_t hi = min(32u, rem);
+        lastBlock = rem <= 32;
+        if (!lastBlock)
+          nxt = ldg256(blk + (k + 1) * 32);
+        mask32 = (0xffffffffu >> (32 - hi)) & (0xffffffffu << lo);
+      }
+      if (wantFirst && (k == 1)) {
+        fetchFirst();
+        wantFirst = false;
+      }
+      const uint32_t pos0 = k * 32 - skip;
+      bool stopped = process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur.lo, mask32 & 0xffffu,
+                                                      pos0, wk, active);
+      if (!stopped)
+        stopped = process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur.hi, mask32 >> 16,
+                                                   pos0 + 16, wk, active);
+      if (stopped || lastBlock)
+        active = false;
+      ++k;
+      cur = nxt;
+    }
+    if (wantFirst)
+      fetchFirst();
+
+    if (line < n) {
+      int32_t result = 0;
+      uint32_t start = 0, end = 0;
+      if (!(LEADER && noResult))
+        wk.finish(pd, lineLen, result, start, end);
+      args.results[line] = result;
+      if (WANT_START)
+        args.matchStarts[line] = start;
+      if (args.matchEnds)
+        args.matchEnds[line] = end;
+    }
+  }
+}
+
 /* batch_sorted_kernel (default when positions are tracked; RED_B200_VARIANT=4
    forces it): the tile schedule with tiles of SIMILAR
    lines.  In a tile every lane waits for the longest line; with consecutive
@@ -638,6 +775,20 @@ cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
     uint64_t sctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * perSm,
                                         (groups + threads / 32 - 1) / (threads / 32));
     sk<<<static_cast<unsigned>(sctas), threads, total, stream>>>(pd, args, counter, tiles, sortOffset);
+    return cudaGetLastError();
+  }
+  if (tune.variant == 5) {
+    auto tk = (args.checkLeader && !WANT_START)
+        ? batch_tile32_kernel<STYLE, false, SMEM, K, ClsT, true>
+        : batch_tile32_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
+    err = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return err;
+    uint64_t tiles32 = (args.nLines + 31) / 32;
+    uint64_t tctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * perSm,
+                                        (tiles32 + threads / 32 - 1) / (threads / 32));
+    tk<<<static_cast<unsigned>(tctas), threads, smem, stream>>>(pd, args, counter);
     return cudaGetLastError();
   }
   if (tune.variant != 3) {
