@@ -259,6 +259,16 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.initResult = img.initResult;
   pd.byteRows = img.byteRows ? 1 : 0;
   pd.hasFinalStates = img.finalReachable ? 1 : 0;
+  pd.hotBytes = 0;
+  if (!prog->smemTable) {
+    // rows of the shallowest states (the renumbering keeps the serialized,
+    // breadth-first order inside each group) go to shared memory as well:
+    // what fits beside the class table and the sort scratch
+    size_t room = prop.sharedMemPerBlockOptin - (24u << 10);
+    if (const char *env = getenv("RED_B200_HOT_ROWS_BYTES"))
+      room = std::min<size_t>(room, strtoull(env, nullptr, 0));
+    pd.hotBytes = static_cast<uint32_t>(std::min<size_t>(room, padded) & ~size_t(15));
+  }
 
   // cudaMemcpy from pageable memory may return before the DMA has landed, and
   // the kernels run on non-blocking streams that do not order against the

@@ -207,7 +207,15 @@ template <bool SMEM, int K, class ClsT> struct Engine {
 
   // smem: 256-byte aligned start of the staged tables
   static __device__ __forceinline__ Tab table(const ProgramDev &pd, const unsigned char *smem) {
-    return Tab{SMEM ? smem + kClsBytes : static_cast<const unsigned char *>(pd.table)};
+    if constexpr (SMEM) {
+      return Tab{smem + kClsBytes};
+    }
+    else {
+      Tab t{static_cast<const unsigned char *>(pd.table)};
+      t.hotAddr = smem_u32(smem + kClsBytes);
+      t.hotBytes = pd.hotBytes;
+      return t;
+    }
   }
   static __device__ __forceinline__ Fast fast(const ProgramDev &pd, const unsigned char *smem) {
     Fast f;
@@ -231,6 +239,13 @@ template <bool SMEM, int K, class ClsT> struct Engine {
     stage_classes<ClsT>(pd, smem);
     if (SMEM)
       stage_table(pd, smem + kClsBytes);
+    else if (pd.hotBytes) {
+      // mirror of the hottest rows of the global table (a multiple of 16 bytes)
+      const uint4 *src = reinterpret_cast<const uint4 *>(pd.table);
+      uint4 *d = reinterpret_cast<uint4 *>(smem + kClsBytes);
+      for (uint32_t ii = threadIdx.x; ii < (pd.hotBytes >> 4); ii += blockDim.x)
+        d[ii] = __ldg(src + ii);
+    }
     __syncthreads();
     return smem;
   }

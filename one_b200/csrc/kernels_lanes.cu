@@ -51,31 +51,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 batch_lanes_kernel(const ProgramDev pd, const BatchArgs args,
                    unsigned long long *blockCounter, const uint32_t T) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  unsigned char *smem = smemRaw + ((256u - (smem_u32(smemRaw) & 255u)) & 255u);
-  stage_classes<ClsT>(pd, smem);
-  if (SMEM)
-    stage_table(pd, smem + kClsBytes);
-  __syncthreads();
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
   const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
-  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
-  const Tab tab{SMEM ? smem + kClsBytes
-                     : static_cast<const unsigned char *>(pd.table)};
-  constexpr bool kPtx = SMEM && (sizeof(ClsT) == 1);
-  constexpr bool kByte = SMEM && (K == 9);
-  using Fast = typename std::conditional<kByte, SmemFastByte,
-      typename std::conditional<kPtx, SmemFast8<K>, GenericFast<Tab, ClsT>>::type>::type;
-  Fast fast;
-  if constexpr (kByte) {
-    fast.tBase = smem_u32(smem + kClsBytes);
-  }
-  else if constexpr (kPtx) {
-    fast.clsBase = smem_u32(smem);
-    fast.tBase = smem_u32(smem + kClsBytes);
-  }
-  else {
-    fast.tab = tab;
-    fast.cls = cls;
-  }
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
 
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t perBlock = 32ull * T;
@@ -221,31 +201,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 batch_tile_kernel(const ProgramDev pd, const BatchArgs args,
                   unsigned long long *blockCounter) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  unsigned char *smem = smemRaw + ((256u - (smem_u32(smemRaw) & 255u)) & 255u);
-  stage_classes<ClsT>(pd, smem);
-  if (SMEM)
-    stage_table(pd, smem + kClsBytes);
-  __syncthreads();
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
   const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
-  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
-  const Tab tab{SMEM ? smem + kClsBytes
-                     : static_cast<const unsigned char *>(pd.table)};
-  constexpr bool kPtx = SMEM && (sizeof(ClsT) == 1);
-  constexpr bool kByte = SMEM && (K == 9);
-  using Fast = typename std::conditional<kByte, SmemFastByte,
-      typename std::conditional<kPtx, SmemFast8<K>, GenericFast<Tab, ClsT>>::type>::type;
-  Fast fast;
-  if constexpr (kByte) {
-    fast.tBase = smem_u32(smem + kClsBytes);
-  }
-  else if constexpr (kPtx) {
-    fast.clsBase = smem_u32(smem);
-    fast.tBase = smem_u32(smem + kClsBytes);
-  }
-  else {
-    fast.tab = tab;
-    fast.cls = cls;
-  }
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
 
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
@@ -717,7 +677,7 @@ cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
   auto kern = (args.checkLeader && !WANT_START)
       ? batch_lanes_kernel<STYLE, false, SMEM, K, ClsT, true>
       : batch_lanes_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
-  size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : 0);
+  size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : pd.hotBytes);
   cudaError_t err = cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess)
@@ -765,7 +725,7 @@ cudaError_t launch_lanes(const ProgramDev &pd, const BatchArgs &args,
         ? batch_sorted_kernel<STYLE, false, SMEM, K, ClsT, true>
         : batch_sorted_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
     // the sort scratch sits behind the tables (+256: worst-case alignment pad)
-    const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : 0) + 15) & ~15u);
+    const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : pd.hotBytes) + 15) & ~15u);
     const size_t total = smem + sorted_smem_bytes(threads / 32, tiles) + 16;
     err = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(total));

@@ -321,7 +321,7 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
       return fail(e_, #expr);                    \
   } while (0)
 
-  const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : 0);
+  const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : pd.hotBytes);
   auto walk = stream_walk_kernel<SMEM, K, ClsT>;
   auto tail = stream_tail_kernel<SMEM, K, ClsT>;
   TRY(cudaFuncSetAttribute(walk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

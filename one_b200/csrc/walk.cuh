@@ -24,12 +24,24 @@ template <int K> struct SmemTable {
   }
 };
 
-// u32 entries in global memory (L1/L2 resident); byte offset of row = v * 4
+// u32 entries in global memory (L2 resident); byte offset of row = v * 4.
+// The first hotBytes of the table - the rows of the states nearest the
+// initial state, where a walk over real text spends nearly all of its time -
+// may be mirrored in shared memory (hotBytes = 0: no mirror).  A lookup in L1
+// costs a wavefront per distinct 128-byte line among the lanes, in shared
+// memory only per bank conflict.
 struct GlobalTable {
   const unsigned char *base;
+  uint32_t hotAddr = 0;   // shared-memory address of the mirror
+  uint32_t hotBytes = 0;
   __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
-    return __ldg(reinterpret_cast<const uint32_t *>(
-        base + ((static_cast<size_t>(v) << 2) + co)));
+    const uint32_t off = (v << 2) + co;
+    if (off < hotBytes) {
+      uint32_t r;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(hotAddr + off));
+      return r;
+    }
+    return __ldg(reinterpret_cast<const uint32_t *>(base + off));
   }
 };
 

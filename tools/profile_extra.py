@@ -45,8 +45,36 @@ def main():
                 bgb, name, sty, ms, bgb / ms * 1e3, tuple(prog.match_stream_device(big, "match", sty))), flush=True)
         prog.close()
     del big
-    prog = red.Program(bench.load_program_blob("union64"))
     res = torch.empty(n, dtype=torch.int32, device=dev)
+    ends0 = torch.empty(n, dtype=torch.int32, device=dev)
+    nbytes = int(lens.sum().item())
+    # every style on the union64 program (bench.py times Instant)
+    prog = red.Program(bench.load_program_blob("union64"))
+    for sty in ("instant", "first", "tangent", "last", "full"):
+        ms = timed(lambda: prog.match_batch_device(text, starts, lens, "match", sty, out=(res, None, ends0)))
+        print("union64 match/%-8s: %.3f ms %.0f GB/s" % (sty, ms, nbytes / ms / 1e6), flush=True)
+    prog.close()
+    # BASELINE configs[2]: 2000 keywords, table in global memory; hot rows mirrored in shared memory or not
+    from one_b200 import synth as _synth
+    p = red.Parser()
+    for pat, r, f, lang in _synth.rules_keywords(2000):
+        p.addAs(lang, pat, r, f)
+    t0 = time.time()
+    big_blob = red.compileToSerialized(p)
+    print("compile 2000 keywords: %.1f s" % (time.time() - t0), flush=True)
+    for hot in ("0", None):
+        if hot is None:
+            os.environ.pop("RED_B200_HOT_ROWS_BYTES", None)
+        else:
+            os.environ["RED_B200_HOT_ROWS_BYTES"] = hot
+        prog = red.Program(big_blob)
+        for sty in ("instant", "first", "last"):
+            ms = timed(lambda: prog.match_batch_device(text, starts, lens, "match", sty, out=(res, None, ends0)))
+            print("keywords2000 (%d states, global table, hot rows %s) match/%-8s: %.3f ms %.0f GB/s" % (
+                prog.info["state_count"], "off" if hot == "0" else "on", sty, ms, nbytes / ms / 1e6), flush=True)
+        prog.close()
+    os.environ.pop("RED_B200_HOT_ROWS_BYTES", None)
+    prog = red.Program(bench.load_program_blob("union64"))
     prog.match_batch_device(text, starts, lens, "match", "instant", out=(res, None, None))
     ms = timed(lambda: red.compact_matches_device(res))
     print("compaction of %d results: %.3f ms" % (n, ms), flush=True)
@@ -69,5 +97,25 @@ def main():
     prog.close()
 
 
+def stream16():
+    """BASELINE configs[3]: one 16 GB stream."""
+    dev = torch.device("cuda", 0)
+    pool = bench.host_pool(1234)
+    text, starts, lens, n = bench.device_corpus(pool, 5_000_000, dev)
+    reps = int(16e9 / text.numel()) + 1
+    big = text.repeat(reps)
+    del text
+    gb = big.numel() / 1e9
+    prog = red.Program(bench.load_program_blob("union64"))
+    for sty in ("last", "full", "instant"):
+        ms = timed(lambda: prog.match_stream_device(big, "match", sty), reps=2)
+        print("stream %.2f GB union64 %-8s: %.3f ms %.0f GB/s -> %s" % (
+            gb, sty, ms, gb / ms * 1e3, tuple(prog.match_stream_device(big, "match", sty))), flush=True)
+    prog.close()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "stream16":
+        stream16()
+        sys.exit(0)
     main()
