@@ -1,0 +1,288 @@
+/* kernels_sorted.cu - the tile schedule over length-sorted groups of lines
+   (default when start positions are tracked). */
+
+#include "lanes_dispatch.cuh"
+
+namespace red_b200 {
+
+namespace {
+
+using namespace dev;
+
+/* batch_sorted_kernel (default when positions are tracked; RED_B200_VARIANT=4
+   forces it): the tile schedule with tiles of SIMILAR
+   lines.  In a tile every lane waits for the longest line; with consecutive
+   lines of a log one instruction serves 20 of 32 lanes on average (ncu:
+   profiles/), and the shared-memory pipe that bounds the kernel is busy with
+   mostly-empty wavefronts.  Here a warp claims a GROUP of 32*T consecutive
+   lines, buckets them by length in 16-byte chunks (a counting sort in its
+   slice of shared memory: two passes of shared-memory atomics, 2 per line),
+   and walks the group as T tiles of lines with (nearly) the same chunk count.
+   Outcomes go to the line's own slot, so the order of the results is
+   untouched.  The next group is claimed and its index entries pulled into L2
+   a whole group ahead; it is sorted just before the last tile of the current
+   group is walked, so the prefetch chain (index entry -> first chunk) never
+   drains. */
+constexpr uint32_t kNoIdx = 0xffffu;
+
+// bytes of shared memory the sort needs per CTA of `warps` warps
+inline size_t sorted_smem_bytes(int warps, uint32_t T) {
+  return static_cast<size_t>(warps) * (32u * T * 2u + 32u * 4u);
+}
+
+template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
+                    unsigned long long *groupCounter, const uint32_t T,
+                    const uint32_t sortOffset) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t nWarps = blockDim.x >> 5;
+  // sort scratch of this warp: bucket counters, then the sorted line offsets
+  uint32_t *hist = reinterpret_cast<uint32_t *>(smem + sortOffset) + warp * 32;
+  uint16_t *order = reinterpret_cast<uint16_t *>(smem + sortOffset + nWarps * 128) + warp * 32 * T;
+
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint32_t leadLen = LEADER ? pd.leaderLen : 0;
+  const uint64_t perGroup = 32ull * T;
+
+  auto claimGroup = [&]() -> uint64_t {
+    unsigned long long g = 0;
+    if (lane == 0)
+      g = atomicAdd(groupCounter, 1ull);
+    return __shfl_sync(kFull, g, 0) * perGroup;
+  };
+  // pull a group's index entries into L2 ahead of use
+  auto prefetchGroup = [&](uint64_t base) {
+    if (base >= n)
+      return;
+    const uint64_t cnt = min(n - base, perGroup);
+    const char *ls = reinterpret_cast<const char *>(args.lens + base);
+    const char *ss = reinterpret_cast<const char *>(args.starts + base);
+    for (uint64_t o = lane * 128ull; o < cnt * 4; o += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ls + o));
+    for (uint64_t o = lane * 128ull; o < cnt * 8; o += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ss + o));
+  };
+  auto bucketOf = [&](uint32_t len) -> uint32_t { return min(31u, (len + 15u) >> 4); };
+  // counting sort of the group's lines by chunk count -> order[]
+  auto prepare = [&](uint64_t base) {
+    const uint32_t cnt = static_cast<uint32_t>(min(n - base, perGroup));
+    hist[lane] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < cnt; i += 32)
+      atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+    __syncwarp();
+    // exclusive scan of the 32 counters
+    const uint32_t c = hist[lane];
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d)
+        incl += up;
+    }
+    __syncwarp();
+    hist[lane] = incl - c;
+    __syncwarp();
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      const uint32_t pos = atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+      order[pos] = static_cast<uint16_t>(i);
+    }
+    for (uint32_t i = cnt + lane; i < perGroup; i += 32)
+      order[i] = kNoIdx;
+    __syncwarp();
+  };
+
+  uint64_t gBase = claimGroup();
+  uint64_t gNext = claimGroup();
+  uint32_t t = 0;
+  bool more = gBase < n;
+  if (more)
+    prepare(gBase);
+  prefetchGroup(gNext);
+
+  // next tile: its line for this lane (~0: none), with the first chunk
+  uint64_t nLine = ~0ull;
+  const uint8_t *nPtr = nullptr;
+  uint32_t nLen = 0;
+  uint4 nFirst = make_uint4(0, 0, 0, 0);
+  auto pickTile = [&]() {
+    const uint32_t idx = order[t * 32 + lane];
+    nLine = (idx != kNoIdx) ? gBase + idx : ~0ull;
+  };
+  auto fetchMeta = [&]() {
+    if (nLine != ~0ull) {
+      nPtr = args.text + __ldg(args.starts + nLine);
+      nLen = __ldg(args.lens + nLine);
+    }
+  };
+  auto fetchFirst = [&]() {
+    if ((nLine != ~0ull) && (nLen > leadLen)) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(nPtr + leadLen);
+      nFirst = __ldg(reinterpret_cast<const uint4 *>(a & ~uintptr_t(15)));
+    }
+  };
+  if (more) {
+    pickTile();
+    fetchMeta();
+    fetchFirst();
+  }
+
+  while (more) {
+    // the prefetched tile becomes the current one
+    const uint64_t line = nLine;
+    bool active = line != ~0ull;
+    const uint8_t *p = nPtr;
+    uint32_t len = active ? nLen : 0;
+    uint4 cur = nFirst, nxt = nFirst;
+    Walk<STYLE, WANT_START> wk;
+    wk.begin(pd);
+    bool noResult = false;
+    if (LEADER && active) {
+      // check() with the leader (Matcher.h:369-376)
+      bool viable = true;
+      for (uint32_t ii = 0; ii < leadLen; ++ii)
+        if ((ii >= len) || (pd.leader[ii] != pd.equiv[__ldg(p + ii)])) {
+          viable = false;
+          break;
+        }
+      p += leadLen;
+      len = viable ? len - leadLen : 0;
+      wk.v = pd.leaderV;
+      noResult = !viable;
+    }
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t skip = active ? static_cast<uint32_t>(a & 15) : 0;
+    const uint4 *blk = reinterpret_cast<const uint4 *>(a - skip);
+    const uint32_t total = skip + len;
+    const uint32_t lineLen = len;
+
+    // move on to the tile after this one (sorting the next group when this
+    // was the last tile of its group) and ask for its index entries now; its
+    // first chunks are requested one iteration later, when the entries are in
+    if (++t == T) {
+      t = 0;
+      gBase = gNext;
+      more = gBase < n;
+      if (more) {
+        prepare(gBase);
+        gNext = claimGroup();
+        prefetchGroup(gNext);
+      }
+    }
+    nLine = ~0ull;
+    if (more) {
+      pickTile();
+      fetchMeta();
+    }
+    bool wantFirst = true;
+
+    uint32_t k = 0;
+    while (__any_sync(kFull, active)) {
+      uint32_t lo = 0, hi = 0;
+      bool lastChunk = true;
+      if (active) {
+        const uint32_t rem = total - k * 16;
+        lo = (k == 0) ? skip : 0;
+        hi = min(16u, rem);
+        lastChunk = rem <= 16;
+        if (!lastChunk)
+          nxt = __ldg(blk + k + 1);
+      }
+      if (wantFirst && (k == 1)) {
+        fetchFirst();
+        wantFirst = false;
+      }
+      const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
+      const uint32_t pos0 = k * 16 - skip;
+      const bool stopped =
+          process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur, mask, pos0, wk, active);
+      if (stopped || lastChunk)
+        active = false;
+      ++k;
+      cur = nxt;
+    }
+    if (wantFirst)
+      fetchFirst();
+
+    if (line != ~0ull) {
+      int32_t result = 0;
+      uint32_t start = 0, end = 0;
+      if (!(LEADER && noResult))
+        wk.finish(pd, lineLen, result, start, end);
+      args.results[line] = result;
+      if (WANT_START)
+        args.matchStarts[line] = start;
+      if (args.matchEnds)
+        args.matchEnds[line] = end;
+    }
+  }
+}
+
+// set by SortedLauncher::go when it launched (per host thread)
+thread_local bool gSortedLaunched = false;
+
+struct SortedLauncher {
+  template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT>
+  static cudaError_t go(const ProgramDev &pd, const BatchArgs &args, const LaunchGeometry &geo,
+                        const BatchTuning &tune, unsigned long long *counter, cudaStream_t stream) {
+    const LaunchShape sh = launch_shape<SMEM>(pd, tune);
+    // tiles per group: what fits beside the table, and not so many that a
+    // small batch leaves SMs without a group
+    const size_t room = (static_cast<size_t>(geo.maxSmemOptin) > sh.smem + 16)
+        ? static_cast<size_t>(geo.maxSmemOptin) - sh.smem - 16 : 0;
+    uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 8;
+    want = std::max(1u, std::min(want, 32u));
+    const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * sh.perSm * (sh.threads / 32) * 2;
+    while (!tune.linesPerLane && (want > 1) &&
+           ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
+      want >>= 1;
+    while ((want > 1) && (sorted_smem_bytes(sh.threads / 32, want) > room))
+      want >>= 1;
+    if (sorted_smem_bytes(sh.threads / 32, want) > room)
+      return cudaSuccess;  // does not fit: the caller falls back to plain tiles
+    const uint32_t tiles = want;
+    auto sk = (args.checkLeader && !WANT_START)
+        ? batch_sorted_kernel<STYLE, false, SMEM, K, ClsT, true>
+        : batch_sorted_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
+    // the sort scratch sits behind the tables
+    const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : pd.hotBytes) + 15) & ~15u);
+    const size_t total = sh.smem + sorted_smem_bytes(sh.threads / 32, tiles) + 16;
+    cudaError_t err = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(total));
+    if (err != cudaSuccess)
+      return err;
+    const uint64_t groups = (args.nLines + 32ull * tiles - 1) / (32ull * tiles);
+    const uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * sh.perSm,
+                                             (groups + sh.threads / 32 - 1) / (sh.threads / 32));
+    sk<<<static_cast<unsigned>(ctas), sh.threads, total, stream>>>(pd, args, counter, tiles, sortOffset);
+    gSortedLaunched = true;
+    return cudaGetLastError();
+  }
+};
+
+} // anonymous
+
+cudaError_t launch_family_sorted(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
+                                 const LaunchGeometry &geo, const BatchTuning &tune,
+                                 unsigned long long *counter, cudaStream_t stream, bool *fits) {
+  *fits = false;
+  if (args.nLines == 0) {
+    *fits = true;
+    return cudaSuccess;
+  }
+  gSortedLaunched = false;
+  cudaError_t err = dispatch_family<SortedLauncher>(pd, smemTable, args, style, geo, tune, counter, stream);
+  *fits = gSortedLaunched;
+  return err;
+}
+
+} // namespace red_b200

@@ -38,7 +38,7 @@ def main():
                 env["RED_B200_VARIANT"] = "1"
             elif kv == "v2":
                 env["RED_B200_VARIANT"] = "2"
-            elif kv in ("v4", "v5"):
+            elif kv in ("v4",):
                 env["RED_B200_VARIANT"] = kv[1:]
             elif kv == "v3":
                 env["RED_B200_VARIANT"] = "3"
