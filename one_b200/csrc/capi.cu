@@ -264,7 +264,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     // rows of the shallowest states (the renumbering keeps the serialized,
     // breadth-first order inside each group) go to shared memory as well:
     // what fits beside the class table and the sort scratch
-    size_t room = prop.sharedMemPerBlockOptin - (24u << 10);
+    size_t room = prop.sharedMemPerBlockOptin - (27u << 10);
     if (const char *env = getenv("RED_B200_HOT_ROWS_BYTES"))
       room = std::min<size_t>(room, strtoull(env, nullptr, 0));
     pd.hotBytes = static_cast<uint32_t>(std::min<size_t>(room, padded) & ~size_t(15));
@@ -337,7 +337,7 @@ int red_b200_program_get_info(const red_b200_program *prog,
 
 /* kernels launched through this program so far (bench.py's gpu_launches) */
 long red_b200_program_launch_count(const red_b200_program *prog) {
-  return prog ? prog->launches : 0;
+  return prog ? prog->launches.load() : 0;
 }
 
 static int launch_batch(red_b200_program *prog, const BatchArgs &args,

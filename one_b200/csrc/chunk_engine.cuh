@@ -168,6 +168,10 @@ process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT
                           stopped = true;
                         }
                       }
+                      // without start tracking mstart is free: it reports how
+                      // many bytes the walk consumed (kernels_tile2.cu)
+                      if (!WANT_START && stopped)
+                        wk.mstart = pos0 + 4 * q + jj + 1;
                     }
                   }
                 }
@@ -176,8 +180,11 @@ process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT
                 wk.v = fast.dec(eq);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                  if (!stopped && (nib & (1u << jj)))
+                  if (!stopped && (nib & (1u << jj))) {
                     stopped = wk.step(pd, tab, cls[byte_of(word, jj)], pos0 + 4 * q + jj);
+                    if (!WANT_START && stopped)
+                      wk.mstart = pos0 + 4 * q + jj + 1;
+                  }
                 }
               }
             }

@@ -2,6 +2,7 @@
 
 #pragma once
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -36,12 +37,12 @@ struct red_b200_program {
   void *dResults = nullptr;
   void *dLeader = nullptr;
   unsigned long long *dCounters = nullptr;  // kCounters block counters, used round-robin
-  unsigned nextCounter = 0;
+  std::atomic<unsigned> nextCounter{0};  // launches may come from several host threads
   BatchTuning tune;
   std::mutex mu;        // guards the lazily created host pipeline
   HostPipe *pipe = nullptr;
   GrepPipe *grep = nullptr;   // lazily created by red_b200_grep_host
-  long launches = 0;    // kernels launched through this program (for bench)
+  std::atomic<long> launches{0};  // kernels launched through this program (for bench)
 };
 
 
