@@ -381,6 +381,34 @@ class Program:
             _check(rc)
             return out[:need.value], ostarts, olens, counts
 
+    def replace_batch_device(self, text, starts, lens, repl, max_per_line=(1 << 63), style=styLast,
+                             out_delim=-1, stream=None):
+        """replace() per line on torch CUDA tensors.  -> (out_text, out_starts, out_lens, counts)
+        as CUDA tensors.  Synchronous (the output size has to come back)."""
+        import torch
+        dev = text.device
+        n = starts.numel()
+        repl = np.frombuffer(_bytes(repl), dtype=np.uint8)
+        ostarts = torch.empty(n, dtype=torch.int64, device=dev)
+        olens = torch.empty(n, dtype=torch.int32, device=dev)
+        counts = torch.empty(n, dtype=torch.int32, device=dev)
+        need = C.c_uint64()
+        st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        cap = int(lens.sum().item()) + n + 64  # enough unless the replacement is longer than the matches
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        while True:
+            rc = lib().red_b200_replace_batch_device(self._h, text.data_ptr(), starts.data_ptr(), lens.data_ptr(), n,
+                                                     repl.ctypes.data if repl.size else None, repl.size,
+                                                     int(max_per_line), _style(style), int(out_delim),
+                                                     out.data_ptr(), cap, ostarts.data_ptr(), olens.data_ptr(),
+                                                     counts.data_ptr(), C.byref(need), st or None)
+            if (rc == _E_LIMIT) and (need.value > cap):
+                cap = need.value
+                out = torch.empty(cap, dtype=torch.uint8, device=dev)
+                continue
+            _check(rc)
+            return out[:need.value], ostarts, olens, counts
+
     def replace(self, text, repl, max=(1 << 63), style=styLast):  # noqa: A002 (reference name)
         """replace(exec, text, repl, out, max, style) -> (count, rewritten text)."""
         t = np.frombuffer(_bytes(text), dtype=np.uint8)

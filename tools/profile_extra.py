@@ -94,6 +94,23 @@ def main():
                                                    out=(res[:m], ends if verb == "search" else None, ends)), reps=2)
         print("%s/last (64 tight phrases) on %d lines: %.3f ms %.1f GB/s, %d hits" % (
             verb, m, ms, nb / ms / 1e6, int((res[:m] > 0).sum().item())), flush=True)
+    # replace(): every phrase -> "<X>", all occurrences, rewritten lines packed with newlines
+    ms = timed(lambda: prog.replace_batch_device(text, starts[:m], lens[:m], b"<X>", 1 << 40, "last", 10), reps=2)
+    out, ostarts, olens, counts = prog.replace_batch_device(text, starts[:m], lens[:m], b"<X>", 1 << 40, "last", 10)
+    print("replace/last (64 tight phrases) on %d lines: %.3f ms %.1f GB/s in, %d substitutions, %.1f MB out" % (
+        m, ms, nb / ms / 1e6, int(counts.sum().item()), out.numel() / 1e6), flush=True)
+    # StatefulMatcher: every line fed as two segments with the state carried
+    half = (lens[:m] // 2).to(torch.int32)
+    rest = lens[:m] - half
+    st = torch.full((m,), -1, dtype=torch.int32, device=dev)   # RED_B200_STATE_FRESH
+    r2 = torch.empty(m, dtype=torch.int32, device=dev)
+
+    def feed():
+        st.fill_(-1)
+        prog.advance_batch_device(text, starts[:m], half, st, r2)
+        prog.advance_batch_device(text, starts[:m] + half.to(torch.int64), rest, st, r2)
+    ms = timed(feed, reps=2)
+    print("advance (2 segments per line, state carried) on %d lines: %.3f ms %.1f GB/s" % (m, ms, nb / ms / 1e6), flush=True)
     prog.close()
 
 
