@@ -81,7 +81,7 @@ template <int STYLE, bool WANT_START, class Fast, class Tab, class ClsT>
 __device__ __forceinline__ bool
 process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT *cls,
               const uint4 &cur, const uint32_t mask, const uint32_t pos0,
-              Walk<STYLE, WANT_START> &wk, const bool cValid) {
+              Walk<STYLE, WANT_START> &wk, const bool cValid, const bool allFull = false) {
   bool stopped = false;
   // A lane with nothing in this chunk (its line is over, or it has no line)
   // stays out altogether: its lookups would be pure noise in the shared-memory
@@ -97,27 +97,52 @@ process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT
         uint32_t mq0 = 0, mq1 = 0, mq2 = 0, mq3 = 0;
         uint32_t cp0 = 0, cp1 = 0, cp2 = 0;
         uint32_t msFast = wk.mstart;
+        if (allFull) {
+          // every lane of the warp that is in this chunk owns all 16 bytes
+          // (interior chunks of length-sorted tiles): no per-byte selects
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t word = word_of(cur, q);
-          uint32_t m = 0;
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t word = word_of(cur, q);
+            uint32_t m = 0;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = 4 * q + jj;
-            const bool act = (mask & (1u << j)) != 0;
-            const uint32_t ne = fast.step(e, word, jj);
-            if (WANT_START) {
-              if (act && (e == eInit) && (ne != eInit))
-                msFast = pos0 + j;
-            }
-            if (act)
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint32_t ne = fast.step(e, word, jj);
+              if (WANT_START) {
+                if ((e == eInit) && (ne != eInit))
+                  msFast = pos0 + 4 * q + jj;
+              }
               e = ne;
-            m = max(m, e);
+              m = max(m, e);
+            }
+            if (q == 0) { mq0 = m; cp0 = e; }
+            if (q == 1) { mq1 = m; cp1 = e; }
+            if (q == 2) { mq2 = m; cp2 = e; }
+            if (q == 3) { mq3 = m; }
           }
-          if (q == 0) { mq0 = m; cp0 = e; }
-          if (q == 1) { mq1 = m; cp1 = e; }
-          if (q == 2) { mq2 = m; cp2 = e; }
-          if (q == 3) { mq3 = m; }
+        }
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t word = word_of(cur, q);
+            uint32_t m = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = 4 * q + jj;
+              const bool act = (mask & (1u << j)) != 0;
+              const uint32_t ne = fast.step(e, word, jj);
+              if (WANT_START) {
+                if (act && (e == eInit) && (ne != eInit))
+                  msFast = pos0 + j;
+              }
+              if (act)
+                e = ne;
+              m = max(m, e);
+            }
+            if (q == 0) { mq0 = m; cp0 = e; }
+            if (q == 1) { mq1 = m; cp1 = e; }
+            if (q == 2) { mq2 = m; cp2 = e; }
+            if (q == 3) { mq3 = m; }
+          }
         }
         const uint32_t eLimit = fast.encLimit(wk.limit);
         const uint32_t ePure = fast.enc(pd.pureV);

@@ -218,15 +218,13 @@ cudaError_t launch_family_lanes(const ProgramDev &pd, bool smemTable, const Batc
 }
 
 /* Entry point for check/match batches: picks the schedule.
-     variant 0 (default)  plain tiles; with start positions the two-phase
-                          version (kernels_tile2.cu: starts only for matched
-                          lines)
-     variant 2            plain tiles always (start tracking in every step)
+     variant 0 (default)  length-sorted tiles (kernels_sorted.cu); with start
+                          positions in two phases (starts only for matched
+                          lines).  Plain tiles when the sort scratch does not
+                          fit beside the table.
+     variant 2            plain tiles (start tracking in every step)
      variant 3            persistent lanes
-     variant 4            length-sorted tiles always (measured:
-                          profiles/r1_sorted_sweep.txt - +14-17% where start
-                          tracking makes a step expensive, +1-5% otherwise at
-                          x1.7 the DRAM traffic)                            */
+   Measured: profiles/r1_sorted_sweep.txt, r1_start_sweep.txt.             */
 cudaError_t launch_batch_lanes(const ProgramDev &pd, bool smemTable,
                                const BatchArgs &args, int style,
                                const LaunchGeometry &geo,
@@ -235,13 +233,7 @@ cudaError_t launch_batch_lanes(const ProgramDev &pd, bool smemTable,
                                cudaStream_t stream, int *launches) {
   cudaError_t err = cudaSuccess;
   bool done = false;
-  if ((tune.variant == 0) && args.matchStarts && !args.checkLeader) {
-    err = launch_family_tile2(pd, smemTable, args, style, geo, tune, counter, stream);
-    done = (err != cudaErrorInvalidConfiguration);
-    if (!done)
-      (void)cudaGetLastError();
-  }
-  if (!done && (tune.variant == 4)) {
+  if ((tune.variant == 0) || (tune.variant == 4)) {
     bool fits = false;
     err = launch_family_sorted(pd, smemTable, args, style, geo, tune, counter, stream, &fits);
     done = fits || (err != cudaSuccess);

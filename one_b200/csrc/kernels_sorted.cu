@@ -25,6 +25,9 @@ using namespace dev;
    drains. */
 constexpr uint32_t kNoIdx = 0xffffu;
 
+constexpr uint32_t kQueue = 64;  // start-position queue entries per warp (< 32 waiting + <= 32 new)
+inline size_t queue_smem_bytes(int warps) { return static_cast<size_t>(warps) * kQueue * 12; }
+
 // bytes of shared memory the sort needs per CTA of `warps` warps
 inline size_t sorted_smem_bytes(int warps, uint32_t T) {
   return static_cast<size_t>(warps) * (32u * T * 2u + 32u * 4u);
@@ -34,7 +37,7 @@ template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
                     unsigned long long *groupCounter, const uint32_t T,
-                    const uint32_t sortOffset) {
+                    const uint32_t sortOffset, const uint32_t queueOffset) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   using Eng = Engine<SMEM, K, ClsT>;
   unsigned char *smem = Eng::stage(pd, smemRaw);
@@ -52,6 +55,71 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   const uint32_t leadLen = LEADER ? pd.leaderLen : 0;
   const uint64_t perGroup = 32ull * T;
+
+  // WANT_START: two phases.  The walk itself never tracks the start position
+  // (three more instructions in every step of every line); it notes how many
+  // bytes the reference's loop would have consumed, and the lines that matched
+  // are queued per warp; whenever 32 of them wait (and at the end) each lane
+  // takes one and walks its consumed bytes again, keeping only the last
+  // position at which the initial state was left (Matcher.h:436-439).
+  // Unmatched lines - the bulk of a log - pay nothing.
+  // (line, bytes consumed) of matched lines waiting for their start position
+  uint64_t *qLine = reinterpret_cast<uint64_t *>(smem + queueOffset) + warp * kQueue;
+  uint32_t *qLen = reinterpret_cast<uint32_t *>(smem + queueOffset + nWarps * kQueue * 8) + warp * kQueue;
+  uint32_t qCount = 0;
+
+  // phase 2 for entries [base, base + cnt) of the queue, one per lane: walk
+  // the consumed part of the line again, keeping only the last position at
+  // which the initial state was left (Matcher.h:436-439)
+  auto drain = [&](uint32_t base, uint32_t cnt) {
+    bool act = lane < cnt;
+    const uint64_t dl = act ? qLine[base + lane] : 0;
+    const uint32_t used = act ? qLen[base + lane] : 0;
+    const uint8_t *dp = args.text + (act ? __ldg(args.starts + dl) : 0);
+    const uintptr_t da = reinterpret_cast<uintptr_t>(dp);
+    const uint32_t dskip = act ? static_cast<uint32_t>(da & 15) : 0;
+    const uint4 *dblk = reinterpret_cast<const uint4 *>(da - dskip);
+    const uint32_t dtotal = dskip + used;
+    const uint32_t eInit = fast.enc(pd.initV);
+    uint32_t e = eInit, ms = 0;
+    bool live = act && (used > 0);
+    uint4 dcur = make_uint4(0, 0, 0, 0), dnxt = dcur;
+    if (live)
+      dcur = __ldg(dblk);
+    uint32_t dk = 0;
+    while (__any_sync(kFull, live)) {
+      uint32_t lo = 0, hi = 0;
+      bool lastChunk = true;
+      if (live) {
+        const uint32_t rem = dtotal - dk * 16;
+        lo = (dk == 0) ? dskip : 0;
+        hi = min(16u, rem);
+        lastChunk = rem <= 16;
+        if (!lastChunk)
+          dnxt = __ldg(dblk + dk + 1);
+      }
+      const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
+      const uint32_t pos0 = dk * 16 - dskip;
+      if (mask != 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool on = (mask & (1u << j)) != 0;
+          const uint32_t ne = fast.step(e, word_of(dcur, j >> 2), j & 3);
+          if (on && (e == eInit) && (ne != eInit))
+            ms = pos0 + j;
+          if (on)
+            e = ne;
+        }
+      }
+      if (lastChunk)
+        live = false;
+      ++dk;
+      dcur = dnxt;
+    }
+    if (act)
+      args.matchStarts[dl] = ms;
+  };
+
 
   auto claimGroup = [&]() -> uint64_t {
     unsigned long long g = 0;
@@ -71,14 +139,21 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     for (uint64_t o = lane * 128ull; o < cnt * 8; o += 32 * 128)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ss + o));
   };
-  auto bucketOf = [&](uint32_t len) -> uint32_t { return min(31u, (len + 15u) >> 4); };
+  // bucket = chunks the line spans from its 16-byte aligned start (what a lane
+  // will actually walk); lines of one bucket finish in the same iteration
+  auto bucketOf = [&](uint64_t i) -> uint32_t {
+    const uint32_t len = __ldg(args.lens + i);
+    const uint32_t skip = static_cast<uint32_t>(
+        (reinterpret_cast<uintptr_t>(args.text) + __ldg(args.starts + i)) & 15);
+    return min(31u, (skip + len + 15u) >> 4);
+  };
   // counting sort of the group's lines by chunk count -> order[]
   auto prepare = [&](uint64_t base) {
     const uint32_t cnt = static_cast<uint32_t>(min(n - base, perGroup));
     hist[lane] = 0;
     __syncwarp();
     for (uint32_t i = lane; i < cnt; i += 32)
-      atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+      atomicAdd(&hist[bucketOf(base + i)], 1u);
     __syncwarp();
     // exclusive scan of the 32 counters
     const uint32_t c = hist[lane];
@@ -93,7 +168,7 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     hist[lane] = incl - c;
     __syncwarp();
     for (uint32_t i = lane; i < cnt; i += 32) {
-      const uint32_t pos = atomicAdd(&hist[bucketOf(__ldg(args.lens + base + i))], 1u);
+      const uint32_t pos = atomicAdd(&hist[bucketOf(base + i)], 1u);
       order[pos] = static_cast<uint16_t>(i);
     }
     for (uint32_t i = cnt + lane; i < perGroup; i += 32)
@@ -143,9 +218,10 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     const uint8_t *p = nPtr;
     uint32_t len = active ? nLen : 0;
     uint4 cur = nFirst, nxt = nFirst;
-    Walk<STYLE, WANT_START> wk;
+    Walk<STYLE, false> wk;
     wk.begin(pd);
     bool noResult = false;
+    bool ranOut = true;  // the walk consumed the whole line
     if (LEADER && active) {
       // check() with the leader (Matcher.h:369-376)
       bool viable = true;
@@ -203,8 +279,12 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
       }
       const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
       const uint32_t pos0 = k * 16 - skip;
+      // interior chunks of equally long lines: nobody needs the byte mask
+      const bool allFull = __all_sync(kFull, (mask == 0xffffu) || (mask == 0));
       const bool stopped =
-          process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur, mask, pos0, wk, active);
+          process_chunk<STYLE, false>(pd, fast, tab, cls, cur, mask, pos0, wk, active, allFull);
+      if (stopped)
+        ranOut = false;
       if (stopped || lastChunk)
         active = false;
       ++k;
@@ -213,18 +293,38 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     if (wantFirst)
       fetchFirst();
 
+    int32_t result = 0;
     if (line != ~0ull) {
-      int32_t result = 0;
       uint32_t start = 0, end = 0;
+      const uint32_t consumed = ranOut ? lineLen : wk.mstart;
       if (!(LEADER && noResult))
         wk.finish(pd, lineLen, result, start, end);
       args.results[line] = result;
-      if (WANT_START)
-        args.matchStarts[line] = start;
+      if (WANT_START && (result <= 0))
+        args.matchStarts[line] = 0;
       if (args.matchEnds)
         args.matchEnds[line] = end;
+      wk.mstart = consumed;  // queued below
+    }
+    if (WANT_START) {
+      const bool hit = (line != ~0ull) && (result > 0);
+      const unsigned hits = __ballot_sync(kFull, hit);
+      if (hit) {
+        const uint32_t at = qCount + __popc(hits & ((1u << lane) - 1));
+        qLine[at] = line;
+        qLen[at] = wk.mstart;
+      }
+      qCount += __popc(hits);
+      __syncwarp();
+      if (qCount >= 32) {
+        drain(qCount - 32, 32);
+        qCount -= 32;
+        __syncwarp();
+      }
     }
   }
+  if (WANT_START && qCount)
+    drain(0, qCount);
 }
 
 // set by SortedLauncher::go when it launched (per host thread)
@@ -237,9 +337,17 @@ struct SortedLauncher {
     const LaunchShape sh = launch_shape<SMEM>(pd, tune);
     // tiles per group: what fits beside the table, and not so many that a
     // small batch leaves SMs without a group
-    const size_t room = (static_cast<size_t>(geo.maxSmemOptin) > sh.smem + 16)
-        ? static_cast<size_t>(geo.maxSmemOptin) - sh.smem - 16 : 0;
-    uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 8;
+    const size_t queueBytes = WANT_START ? queue_smem_bytes(sh.threads / 32) + 16 : 0;
+    const size_t room = (static_cast<size_t>(geo.maxSmemOptin) > sh.smem + 16 + queueBytes)
+        ? static_cast<size_t>(geo.maxSmemOptin) - sh.smem - 16 - queueBytes : 0;
+    // Tiles per group.  Measured on B200, 20 M lines (profiles/r1_sorted_T_traffic.txt):
+    //   T  GB/s   DRAM bytes / algorithmic
+    //   2  1298   1.01
+    //   4  1369   1.13
+    //   8  1396   1.71   (148 x 32 groups of 26 KB outlive the L2: the 64-byte
+    //                     pieces two neighbouring lines share are fetched twice)
+    // 4 keeps the traffic near the algorithmic minimum for 2% of the speed.
+    uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 4;
     want = std::max(1u, std::min(want, 32u));
     const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * sh.perSm * (sh.threads / 32) * 2;
     while (!tune.linesPerLane && (want > 1) &&
@@ -255,7 +363,9 @@ struct SortedLauncher {
         : batch_sorted_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
     // the sort scratch sits behind the tables
     const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : pd.hotBytes) + 15) & ~15u);
-    const size_t total = sh.smem + sorted_smem_bytes(sh.threads / 32, tiles) + 16;
+    const uint32_t queueOffset = static_cast<uint32_t>(
+        (sortOffset + sorted_smem_bytes(sh.threads / 32, tiles) + 15) & ~size_t(15));
+    const size_t total = sh.smem + sorted_smem_bytes(sh.threads / 32, tiles) + 16 + queueBytes;
     cudaError_t err = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(total));
     if (err != cudaSuccess)
@@ -263,7 +373,7 @@ struct SortedLauncher {
     const uint64_t groups = (args.nLines + 32ull * tiles - 1) / (32ull * tiles);
     const uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * sh.perSm,
                                              (groups + sh.threads / 32 - 1) / (sh.threads / 32));
-    sk<<<static_cast<unsigned>(ctas), sh.threads, total, stream>>>(pd, args, counter, tiles, sortOffset);
+    sk<<<static_cast<unsigned>(ctas), sh.threads, total, stream>>>(pd, args, counter, tiles, sortOffset, queueOffset);
     gSortedLaunched = true;
     return cudaGetLastError();
   }

@@ -89,11 +89,6 @@ cudaError_t launch_family_lanes(const ProgramDev &pd, bool smemTable, const Batc
 cudaError_t launch_family_tile(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
                                const LaunchGeometry &geo, const BatchTuning &tune,
                                unsigned long long *counter, cudaStream_t stream);
-// match() with start positions in two phases (kernels_tile2.cu);
-// cudaErrorInvalidConfiguration: the queue does not fit beside the table
-cudaError_t launch_family_tile2(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
-                                const LaunchGeometry &geo, const BatchTuning &tune,
-                                unsigned long long *counter, cudaStream_t stream);
 // false in *fits: the sort scratch does not fit beside the table (nothing launched)
 cudaError_t launch_family_sorted(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
                                  const LaunchGeometry &geo, const BatchTuning &tune,
