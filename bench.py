@@ -187,6 +187,39 @@ def run_reference_sample(blob, pool, cores, target_s=4.0, max_lines=20_000_000):
             "lines_per_s": lps, "seconds": elapsed, "matched": int((res[0] > 0).sum())}, nbytes, len(starts)
 
 
+def bind_to_gpu_numa_node(local):
+    """Several ranks on one host: keep this rank's threads - and with them the
+    pinned staging memory they first touch - on the NUMA node its GPU hangs
+    off, so that the host-to-device copies of the e2e leg do not cross sockets.
+    Best effort: silently does nothing where sysfs does not say."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes
+            rt = ctypes.CDLL("libcudart.so")
+            buf = ctypes.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, local) != 0:
+                return
+            bdf = buf.value.decode()
+        if isinstance(bdf, int):
+            return
+        path = "/sys/bus/pci/devices/%s/numa_node" % bdf.lower()
+        node = int(open(path).read().strip())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001 - purely an optimisation
+        return
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +232,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--program", default="union64")
     args = ap.parse_args()
+
+    # stdout carries exactly one JSON line.  Libraries write banners to fd 1
+    # behind Python's back (NCCL prints its version there): send fd 1 to stderr
+    # for the run and keep the real stdout for the result.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,7 +272,7 @@ def main():
                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": steps[0]["cores"],
                                 "kind": steps[0]["kind"], "sample": steps[0]["sample"]},
                "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(out)
         return
 
     import torch
@@ -240,6 +284,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL's own banner/debug lines go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -405,7 +450,8 @@ def main():
                       "parallelism": "lines sharded by rank, no data-path collective"},
            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(out))
+    if rank == 0:
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
