@@ -218,7 +218,9 @@ cudaError_t launch_family_lanes(const ProgramDev &pd, bool smemTable, const Batc
 }
 
 /* Entry point for check/match batches: picks the schedule.
-     variant 0 (default)  length-sorted tiles (kernels_sorted.cu); with start
+     variant 0 (default)  length-sorted tiles (kernels_sorted.cu: a pre-sort
+                          kernel, then the batch kernel; variant 4 sorts per
+                          warp inside the batch kernel instead); with start
                           positions in two phases (starts only for matched
                           lines).  Plain tiles when the sort scratch does not
                           fit beside the table.
@@ -232,20 +234,20 @@ cudaError_t launch_batch_lanes(const ProgramDev &pd, bool smemTable,
                                unsigned long long *counter,
                                cudaStream_t stream, int *launches) {
   cudaError_t err = cudaSuccess;
-  bool done = false;
-  if ((tune.variant == 0) || (tune.variant == 4)) {
-    bool fits = false;
-    err = launch_family_sorted(pd, smemTable, args, style, geo, tune, counter, stream, &fits);
-    done = fits || (err != cudaSuccess);
-  }
-  if (!done) {
+  int kernels = 0;
+  if (args.nLines == 0)
+    return cudaSuccess;
+  if ((tune.variant == 0) || (tune.variant == 4))
+    err = launch_family_sorted(pd, smemTable, args, style, geo, tune, counter, stream, &kernels);
+  if ((err == cudaSuccess) && (kernels == 0)) {
     if (tune.variant == 3)
       err = launch_family_lanes(pd, smemTable, args, style, geo, tune, counter, stream);
     else
       err = launch_family_tile(pd, smemTable, args, style, geo, tune, counter, stream);
+    kernels = 1;
   }
-  if ((err == cudaSuccess) && launches && args.nLines)
-    *launches += 1;
+  if ((err == cudaSuccess) && launches)
+    *launches += kernels;
   return err;
 }
 

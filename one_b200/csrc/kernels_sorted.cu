@@ -2,6 +2,7 @@
    (default when start positions are tracked). */
 
 #include "lanes_dispatch.cuh"
+#include "stream.h"
 
 namespace red_b200 {
 
@@ -33,11 +34,67 @@ inline size_t sorted_smem_bytes(int warps, uint32_t T) {
   return static_cast<size_t>(warps) * (32u * T * 2u + 32u * 4u);
 }
 
+/* Pre-sort (the default): a small kernel sorts the line numbers of every block
+   of kSortBlock consecutive lines by chunk count and writes them, relative to
+   the block, as u16 (2 bytes per line of extra traffic).  The batch kernel then
+   takes its tiles as 32 consecutive entries of that array: with ~400 lines per
+   bucket and block nearly every tile is of one chunk count, where the
+   per-warp sort of 128 lines spreads a tile over two or three.  Tiles are
+   handed out in order, so the tiles in flight at any time come from a few
+   dozen adjacent blocks: neighbouring lines are walked at about the same time
+   and the DRAM traffic stays at the algorithmic minimum. */
+constexpr uint32_t kSortBlock = 4096;
+
+__global__ void __launch_bounds__(256)
+block_sort_kernel(const BatchArgs args, uint16_t *order) {
+  __shared__ uint32_t hist[32];
+  __shared__ uint16_t sorted[kSortBlock];
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint64_t nBlocks = (args.nLines + kSortBlock - 1) / kSortBlock;
+  auto bucketOf = [&](uint64_t i) -> uint32_t {
+    const uint32_t len = __ldg(args.lens + i);
+    const uint32_t skip = static_cast<uint32_t>(
+        (reinterpret_cast<uintptr_t>(args.text) + __ldg(args.starts + i)) & 15);
+    return min(31u, (skip + len + 15u) >> 4);
+  };
+  for (uint64_t blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
+    const uint64_t base = blk * kSortBlock;
+    const uint32_t cnt = (base < n) ? static_cast<uint32_t>(min(n - base, static_cast<uint64_t>(kSortBlock))) : 0;
+    if (threadIdx.x < 32)
+      hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+      atomicAdd(&hist[bucketOf(base + i)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const uint32_t c = hist[threadIdx.x];
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, incl, d);
+        if (threadIdx.x >= d)
+          incl += up;
+      }
+      hist[threadIdx.x] = incl - c;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint32_t pos = atomicAdd(&hist[bucketOf(base + i)], 1u);
+      sorted[pos] = static_cast<uint16_t>(i);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kSortBlock; i += blockDim.x)
+      order[base + i] = (i < cnt) ? sorted[i] : static_cast<uint16_t>(kNoIdx);
+    __syncthreads();
+  }
+}
+
 template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT, bool LEADER>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
                     unsigned long long *groupCounter, const uint32_t T,
-                    const uint32_t sortOffset, const uint32_t queueOffset) {
+                    const uint32_t sortOffset, const uint32_t queueOffset,
+                    const uint16_t *gOrder) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   using Eng = Engine<SMEM, K, ClsT>;
   unsigned char *smem = Eng::stage(pd, smemRaw);
@@ -176,13 +233,22 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     __syncwarp();
   };
 
+  // pre-sorted mode (gOrder): T is 1, a group is one tile of the sorted array;
+  // its entries are loaded a tile ahead
+  auto loadOrder = [&](uint64_t base) -> uint32_t {
+    return (gOrder && (base < (n + kSortBlock - 1) / kSortBlock * kSortBlock)) ? __ldg(gOrder + base + lane) : kNoIdx;
+  };
   uint64_t gBase = claimGroup();
   uint64_t gNext = claimGroup();
+  uint32_t idxNow = loadOrder(gBase), idxNext = loadOrder(gNext);
   uint32_t t = 0;
-  bool more = gBase < n;
-  if (more)
+  // in pre-sorted mode the padded tail of the last block is part of the array
+  const uint64_t nEnd = gOrder ? (n + kSortBlock - 1) / kSortBlock * kSortBlock : n;
+  bool more = gBase < nEnd;
+  if (more && !gOrder)
     prepare(gBase);
-  prefetchGroup(gNext);
+  if (!gOrder)
+    prefetchGroup(gNext);
 
   // next tile: its line for this lane (~0: none), with the first chunk
   uint64_t nLine = ~0ull;
@@ -190,8 +256,15 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
   uint32_t nLen = 0;
   uint4 nFirst = make_uint4(0, 0, 0, 0);
   auto pickTile = [&]() {
-    const uint32_t idx = order[t * 32 + lane];
-    nLine = (idx != kNoIdx) ? gBase + idx : ~0ull;
+    if (gOrder) {
+      nLine = (idxNow != kNoIdx) ? (gBase & ~static_cast<uint64_t>(kSortBlock - 1)) + idxNow : ~0ull;
+      if (nLine >= n)
+        nLine = ~0ull;
+    }
+    else {
+      const uint32_t idx = order[t * 32 + lane];
+      nLine = (idx != kNoIdx) ? gBase + idx : ~0ull;
+    }
   };
   auto fetchMeta = [&]() {
     if (nLine != ~0ull) {
@@ -247,11 +320,16 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     if (++t == T) {
       t = 0;
       gBase = gNext;
-      more = gBase < n;
+      idxNow = idxNext;
+      more = gBase < nEnd;
       if (more) {
-        prepare(gBase);
+        if (!gOrder)
+          prepare(gBase);
         gNext = claimGroup();
-        prefetchGroup(gNext);
+        if (gOrder)
+          idxNext = (gNext < nEnd) ? __ldg(gOrder + gNext + lane) : kNoIdx;
+        else
+          prefetchGroup(gNext);
       }
     }
     nLine = ~0ull;
@@ -327,55 +405,73 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     drain(0, qCount);
 }
 
-// set by SortedLauncher::go when it launched (per host thread)
-thread_local bool gSortedLaunched = false;
+// set by SortedLauncher::go (per host thread): kernels it launched (0: it did not fit)
+thread_local int gSortedKernels = 0;
 
 struct SortedLauncher {
   template <int STYLE, bool WANT_START, bool SMEM, int K, class ClsT>
   static cudaError_t go(const ProgramDev &pd, const BatchArgs &args, const LaunchGeometry &geo,
                         const BatchTuning &tune, unsigned long long *counter, cudaStream_t stream) {
     const LaunchShape sh = launch_shape<SMEM>(pd, tune);
-    // tiles per group: what fits beside the table, and not so many that a
-    // small batch leaves SMs without a group
-    const size_t queueBytes = WANT_START ? queue_smem_bytes(sh.threads / 32) + 16 : 0;
+    const int warps = sh.threads / 32;
+    const size_t queueBytes = WANT_START ? queue_smem_bytes(warps) + 16 : 0;
     const size_t room = (static_cast<size_t>(geo.maxSmemOptin) > sh.smem + 16 + queueBytes)
         ? static_cast<size_t>(geo.maxSmemOptin) - sh.smem - 16 - queueBytes : 0;
-    // Tiles per group.  Measured on B200, 20 M lines (profiles/r1_sorted_T_traffic.txt):
+    // variant 4: the per-warp sort inside the kernel, T tiles per group.
+    // Measured on B200, 20 M lines (profiles/r1_sorted_T_traffic.txt):
     //   T  GB/s   DRAM bytes / algorithmic
     //   2  1298   1.01
     //   4  1369   1.13
     //   8  1396   1.71   (148 x 32 groups of 26 KB outlive the L2: the 64-byte
     //                     pieces two neighbouring lines share are fetched twice)
-    // 4 keeps the traffic near the algorithmic minimum for 2% of the speed.
-    uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 4;
-    want = std::max(1u, std::min(want, 32u));
-    const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * sh.perSm * (sh.threads / 32) * 2;
-    while (!tune.linesPerLane && (want > 1) &&
-           ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
-      want >>= 1;
-    while ((want > 1) && (sorted_smem_bytes(sh.threads / 32, want) > room))
-      want >>= 1;
-    if (sorted_smem_bytes(sh.threads / 32, want) > room)
+    const bool presort = (tune.variant != 4);
+    uint32_t tiles = 1;
+    if (!presort) {
+      uint32_t want = tune.linesPerLane ? static_cast<uint32_t>(tune.linesPerLane) : 4;
+      want = std::max(1u, std::min(want, 32u));
+      const uint64_t groupsWanted = static_cast<uint64_t>(geo.smCount) * sh.perSm * warps * 2;
+      while (!tune.linesPerLane && (want > 1) &&
+             ((args.nLines + 32ull * want - 1) / (32ull * want) < groupsWanted))
+        want >>= 1;
+      while ((want > 1) && (sorted_smem_bytes(warps, want) > room))
+        want >>= 1;
+      tiles = want;
+    }
+    const size_t sortBytes = presort ? 0 : sorted_smem_bytes(warps, tiles);
+    if (sortBytes > room)
       return cudaSuccess;  // does not fit: the caller falls back to plain tiles
-    const uint32_t tiles = want;
+    if (WANT_START && (room == 0))
+      return cudaSuccess;
     auto sk = (args.checkLeader && !WANT_START)
         ? batch_sorted_kernel<STYLE, false, SMEM, K, ClsT, true>
         : batch_sorted_kernel<STYLE, WANT_START, SMEM, K, ClsT, false>;
-    // the sort scratch sits behind the tables
+    // the sort scratch sits behind the tables, the start queue behind that
     const uint32_t sortOffset = static_cast<uint32_t>((kClsBytes + (SMEM ? pd.tableBytes : pd.hotBytes) + 15) & ~15u);
-    const uint32_t queueOffset = static_cast<uint32_t>(
-        (sortOffset + sorted_smem_bytes(sh.threads / 32, tiles) + 15) & ~size_t(15));
-    const size_t total = sh.smem + sorted_smem_bytes(sh.threads / 32, tiles) + 16 + queueBytes;
+    const uint32_t queueOffset = static_cast<uint32_t>((sortOffset + sortBytes + 15) & ~size_t(15));
+    const size_t total = sh.smem + sortBytes + 16 + queueBytes;
     cudaError_t err = cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(total));
     if (err != cudaSuccess)
       return err;
+    uint16_t *order = nullptr;
+    if (presort) {
+      const uint64_t nBlocks = (args.nLines + kSortBlock - 1) / kSortBlock;
+      err = scratch_alloc(&order, nBlocks * kSortBlock * sizeof(uint16_t), stream);
+      if (err != cudaSuccess)
+        return err;
+      const unsigned sgrid = static_cast<unsigned>(std::min<uint64_t>(nBlocks, static_cast<uint64_t>(geo.smCount) * 8));
+      block_sort_kernel<<<sgrid, 256, 0, stream>>>(args, order);
+      gSortedKernels += 1;
+    }
     const uint64_t groups = (args.nLines + 32ull * tiles - 1) / (32ull * tiles);
     const uint64_t ctas = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * sh.perSm,
-                                             (groups + sh.threads / 32 - 1) / (sh.threads / 32));
-    sk<<<static_cast<unsigned>(ctas), sh.threads, total, stream>>>(pd, args, counter, tiles, sortOffset, queueOffset);
-    gSortedLaunched = true;
-    return cudaGetLastError();
+                                             (groups + warps - 1) / warps);
+    sk<<<static_cast<unsigned>(ctas), sh.threads, total, stream>>>(pd, args, counter, tiles, sortOffset,
+                                                                  queueOffset, order);
+    gSortedKernels += 1;
+    err = cudaGetLastError();
+    scratch_free(order, stream);
+    return err;
   }
 };
 
@@ -383,15 +479,13 @@ struct SortedLauncher {
 
 cudaError_t launch_family_sorted(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
                                  const LaunchGeometry &geo, const BatchTuning &tune,
-                                 unsigned long long *counter, cudaStream_t stream, bool *fits) {
-  *fits = false;
-  if (args.nLines == 0) {
-    *fits = true;
+                                 unsigned long long *counter, cudaStream_t stream, int *kernels) {
+  *kernels = 0;
+  if (args.nLines == 0)
     return cudaSuccess;
-  }
-  gSortedLaunched = false;
+  gSortedKernels = 0;
   cudaError_t err = dispatch_family<SortedLauncher>(pd, smemTable, args, style, geo, tune, counter, stream);
-  *fits = gSortedLaunched;
+  *kernels = gSortedKernels;
   return err;
 }
 

@@ -89,9 +89,10 @@ cudaError_t launch_family_lanes(const ProgramDev &pd, bool smemTable, const Batc
 cudaError_t launch_family_tile(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
                                const LaunchGeometry &geo, const BatchTuning &tune,
                                unsigned long long *counter, cudaStream_t stream);
-// false in *fits: the sort scratch does not fit beside the table (nothing launched)
+// *kernels: kernels launched (pre-sort + batch); 0 = the scratch does not fit
+// beside the table, nothing was launched
 cudaError_t launch_family_sorted(const ProgramDev &pd, bool smemTable, const BatchArgs &args, int style,
                                  const LaunchGeometry &geo, const BatchTuning &tune,
-                                 unsigned long long *counter, cudaStream_t stream, bool *fits);
+                                 unsigned long long *counter, cudaStream_t stream, int *kernels);
 
 } // namespace red_b200
