@@ -49,22 +49,36 @@ __global__ void __launch_bounds__(256)
 block_sort_kernel(const BatchArgs args, uint16_t *order) {
   __shared__ uint32_t hist[32];
   __shared__ uint16_t sorted[kSortBlock];
+  constexpr int kPer = kSortBlock / 256;  // lines per thread, strided: coalesced loads
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   const uint64_t nBlocks = (args.nLines + kSortBlock - 1) / kSortBlock;
-  auto bucketOf = [&](uint64_t i) -> uint32_t {
-    const uint32_t len = __ldg(args.lens + i);
-    const uint32_t skip = static_cast<uint32_t>(
-        (reinterpret_cast<uintptr_t>(args.text) + __ldg(args.starts + i)) & 15);
-    return min(31u, (skip + len + 15u) >> 4);
-  };
+  const uintptr_t textLow = reinterpret_cast<uintptr_t>(args.text) & 15;
   for (uint64_t blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
     const uint64_t base = blk * kSortBlock;
     const uint32_t cnt = (base < n) ? static_cast<uint32_t>(min(n - base, static_cast<uint64_t>(kSortBlock))) : 0;
     if (threadIdx.x < 32)
       hist[threadIdx.x] = 0;
+    // all index loads of the thread are issued before the first is used
+    uint32_t len[kPer];
+    uint32_t low[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t i = threadIdx.x + 256 * k;
+      len[k] = (i < cnt) ? __ldg(args.lens + base + i) : 0;
+      low[k] = (i < cnt) ? static_cast<uint32_t>(__ldg(args.starts + base + i)) : 0;
+    }
+    uint8_t bucket[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      // chunks the line spans from its 16-byte aligned start: what a lane walks
+      const uint32_t skip = static_cast<uint32_t>((textLow + low[k]) & 15);
+      bucket[k] = static_cast<uint8_t>(min(31u, (skip + len[k] + 15u) >> 4));
+    }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-      atomicAdd(&hist[bucketOf(base + i)], 1u);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (threadIdx.x + 256 * k < cnt)
+        atomicAdd(&hist[bucket[k]], 1u);
     __syncthreads();
     if (threadIdx.x < 32) {
       const uint32_t c = hist[threadIdx.x];
@@ -78,13 +92,18 @@ block_sort_kernel(const BatchArgs args, uint16_t *order) {
       hist[threadIdx.x] = incl - c;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const uint32_t pos = atomicAdd(&hist[bucketOf(base + i)], 1u);
-      sorted[pos] = static_cast<uint16_t>(i);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t i = threadIdx.x + 256 * k;
+      if (i < cnt)
+        sorted[atomicAdd(&hist[bucket[k]], 1u)] = static_cast<uint16_t>(i);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < kSortBlock; i += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t i = threadIdx.x + 256 * k;
       order[base + i] = (i < cnt) ? sorted[i] : static_cast<uint16_t>(kNoIdx);
+    }
     __syncthreads();
   }
 }
