@@ -359,7 +359,9 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
     bool wantFirst = true;
 
     uint32_t k = 0;
-    while (__any_sync(kFull, active)) {
+    // one iteration with everything a partial chunk needs (head, tail, lines
+    // of different length in one tile)
+    auto genericStep = [&]() {
       uint32_t lo = 0, hi = 0;
       bool lastChunk = true;
       if (active) {
@@ -376,7 +378,6 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
       }
       const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
       const uint32_t pos0 = k * 16 - skip;
-      // interior chunks of equally long lines: nobody needs the byte mask
       const bool allFull = __all_sync(kFull, (mask == 0xffffu) || (mask == 0));
       const bool stopped =
           process_chunk<STYLE, false>(pd, fast, tab, cls, cur, mask, pos0, wk, active, allFull);
@@ -386,7 +387,32 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
         active = false;
       ++k;
       cur = nxt;
+    };
+    // The tile's lines span (nearly) the same number of chunks.  Chunks
+    // 1 .. kMin-2 are whole for every lane still walking, so between the head
+    // and the tail runs a loop without masks, votes or per-lane bookkeeping.
+    const uint32_t kMin = __reduce_min_sync(kFull, active ? ((total + 15u) >> 4) : 0xffffffffu);
+    if (__any_sync(kFull, active))
+      genericStep();  // the head chunk
+    if ((kMin != 0xffffffffu) && (kMin >= 3)) {
+      if (wantFirst) {
+        fetchFirst();
+        wantFirst = false;
+      }
+      for (; k + 1 < kMin; ++k) {
+        if (active)
+          nxt = __ldg(blk + k + 1);
+        const bool stopped = process_chunk<STYLE, false>(
+            pd, fast, tab, cls, cur, active ? 0xffffu : 0u, k * 16 - skip, wk, active, true);
+        if (stopped) {
+          ranOut = false;
+          active = false;
+        }
+        cur = nxt;
+      }
     }
+    while (__any_sync(kFull, active))
+      genericStep();
     if (wantFirst)
       fetchFirst();
 
