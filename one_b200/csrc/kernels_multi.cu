@@ -16,6 +16,7 @@
 #include "walk.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace red_b200 {
@@ -230,6 +231,111 @@ batch_replace_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *s
   }
 }
 
+/* replace() with a WARP per line: the 32 lanes try 32 consecutive start
+   positions at once; the lowest lane whose walk found a match wins (the
+   attempts are independent, so this is the reference's "first position that
+   matches"), the text in front of it is copied through and the search goes on
+   behind the match.  Most walks die within a byte or two and the byte loads of
+   a step are coalesced; copying is done by the whole warp.  Same two passes
+   as the lane-per-line kernel (measure, then write). */
+template <bool SMEM, int K, class ClsT, bool WRITE>
+__global__ void __launch_bounds__(512)
+batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *starts,
+                          const uint32_t *lens, uint64_t nLines, int style, uint64_t maxRepl,
+                          const uint8_t *repl, uint32_t replLen, int delim, uint32_t *counts,
+                          uint32_t *outLens, const uint64_t *outStarts, uint8_t *outText) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes
+                     : static_cast<const unsigned char *>(pd.table)};
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t line = warp; line < nLines; line += nWarps) {
+    const uint8_t *p = text + __ldg(starts + line);
+    const uint32_t len = __ldg(lens + line);
+    uint8_t *out = WRITE ? outText + __ldg(outStarts + line) : nullptr;
+    uint32_t cnt = 0, o = 0, pos = 0;
+    auto copyThrough = [&](uint32_t from, uint32_t to) {  // text[from, to) -> out + o
+      if (WRITE)
+        for (uint32_t ii = from + lane; ii < to; ii += 32)
+          out[o + ii - from] = __ldg(p + ii);
+      o += to - from;
+    };
+    while (pos < len) {
+      if (cnt >= maxRepl) {
+        copyThrough(pos, len);
+        break;
+      }
+      // lane l: is there a match starting at pos + l, and where does it end
+      const uint32_t at = pos + lane;
+      bool have = false;
+      uint32_t found = 0;
+      if (at < len) {
+        uint32_t v = pd.initV;
+        int32_t prev = 0;
+        for (uint32_t idx = at; idx < len; ++idx) {
+          v = tab.next(v, cls[__ldg(p + idx)]);
+          if ((v >= pd.acceptV) && (v < pd.pureV)) {
+            if (style == STY_FIRST) {
+              const int32_t r = pd.results[state_index(pd, v)];
+              if (prev && (r != prev))
+                break;
+              prev = r;
+            }
+            have = true;
+            found = idx;
+            if (style == STY_INSTANT)
+              break;
+            if (v >= pd.absV) {
+              found = len - 1;
+              break;
+            }
+          }
+          else {
+            if (style == STY_FULL)
+              have = false;
+            if ((((style == STY_FIRST) || (style == STY_TANGENT)) && have) || (v >= pd.pureV))
+              break;
+          }
+        }
+      }
+      const unsigned hits = __ballot_sync(0xffffffffu, have);
+      if (hits) {
+        const int w = __ffs(hits) - 1;
+        const uint32_t end = __shfl_sync(0xffffffffu, found, w) + 1;
+        copyThrough(pos, pos + w);
+        if (WRITE)
+          for (uint32_t ii = lane; ii < replLen; ii += 32)
+            out[o + ii] = __ldg(repl + ii);
+        o += replLen;
+        pos = end;
+        ++cnt;
+      }
+      else {
+        const uint32_t to = min(len, pos + 32);
+        copyThrough(pos, to);
+        pos = to;
+      }
+    }
+    if (lane == 0) {
+      if (WRITE) {
+        if (delim >= 0)
+          out[o] = static_cast<uint8_t>(delim);
+      }
+      else {
+        counts[line] = cnt;
+        outLens[line] = o;
+      }
+    }
+  }
+}
+
 /* StatefulMatcher::advance over a segment per line (Matcher.h:770-794): the
    state comes from and goes back to states[line]; kStateFresh starts a new
    matcher.  results[line] is result() after the segment (for an empty segment
@@ -320,6 +426,23 @@ cudaError_t launch_line_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
   return cudaGetLastError();
 }
 
+// one warp per line, 512 threads per CTA
+template <bool SMEM, int K, class ClsT, class Kern, class... Args>
+cudaError_t launch_warp_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
+                               const LaunchGeometry &geo, cudaStream_t stream, Args... args) {
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  cudaError_t err = cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess)
+    return err;
+  const uint64_t perSm = (SMEM && (smem > (100u << 10))) ? 1 : 2;
+  const uint64_t grid = std::min<uint64_t>((nLines + 15) / 16, static_cast<uint64_t>(geo.smCount) * perSm);
+  if (grid == 0)
+    return cudaSuccess;
+  kern<<<static_cast<unsigned>(grid), 512, smem, stream>>>(pd, args...);
+  return cudaGetLastError();
+}
+
 } // anonymous
 
 cudaError_t launch_batch_multi(const ProgramDev &pd, bool smemTable, const uint8_t *text,
@@ -361,8 +484,12 @@ cudaError_t launch_batch_replace(const ProgramDev &pd, bool smemTable, bool writ
                                  const LaunchGeometry &geo, cudaStream_t stream, int *launches) {
   const bool cls8 = pd.clsMaxOffset < 256;
   cudaError_t err;
-#define GO2(S, KK, CT, W) launch_line_kernel<S, KK, CT>(batch_replace_kernel<S, KK, CT, W>, pd, nLines, geo, stream, \
-    text, starts, lens, nLines, style, maxRepl, repl, replLen, delim, counts, outLens, outStarts, outText)
+  const bool perLane = getenv("RED_B200_REPLACE_LANE_PER_LINE") != nullptr;  // the first kernel, for A/B
+#define GO2(S, KK, CT, W) (perLane \
+    ? launch_line_kernel<S, KK, CT>(batch_replace_kernel<S, KK, CT, W>, pd, nLines, geo, stream, \
+        text, starts, lens, nLines, style, maxRepl, repl, replLen, delim, counts, outLens, outStarts, outText) \
+    : launch_warp_kernel<S, KK, CT>(batch_replace_warp_kernel<S, KK, CT, W>, pd, nLines, geo, stream, \
+        text, starts, lens, nLines, style, maxRepl, repl, replLen, delim, counts, outLens, outStarts, outText))
 #define GO(S, KK, CT) (write ? GO2(S, KK, CT, true) : GO2(S, KK, CT, false))
   if (smemTable) {
     if (pd.unitShift == 0)

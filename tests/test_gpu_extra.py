@@ -63,6 +63,24 @@ def test_replace_corpus_vs_oracle(gpu_red, vectors, oracle_cls):
         prog.close()
 
 
+def test_replace_lane_per_line_kernel_agrees(gpu_red, extra_vectors, monkeypatch):
+    """The first replace kernel (one lane per line), kept for A/B behind
+    RED_B200_REPLACE_LANE_PER_LINE: same answers as the warp-per-line default."""
+    monkeypatch.setenv("RED_B200_REPLACE_LANE_PER_LINE", "1")
+    for case in extra_vectors["cases"]:
+        prog = gpu_red.Program(unz(case["program"]))
+        texts = [unb64(t) for t in case["texts"]]
+        repls = [unb64(r) for r in case["repls"]]
+        blob, starts, lens = pack(texts)
+        for sty in STYLES:
+            out, ostarts, olens, counts = prog.replace_batch_host(blob, starts, lens, repls[0], 9999, sty)
+            for i, per in enumerate(case["replace"]):
+                cnt, exp = per["%s/9999/0" % sty]
+                got = out[int(ostarts[i]):int(ostarts[i]) + int(olens[i])].tobytes()
+                assert (int(counts[i]), got) == (cnt, unb64(exp)), (case["name"], texts[i], sty)
+        prog.close()
+
+
 def test_stateful_golden_vectors(gpu_red, extra_vectors):
     for case in extra_vectors["cases"]:
         prog = gpu_red.Program(unz(case["program"]))
