@@ -91,6 +91,21 @@ __device__ __forceinline__ void walk_bytes(const ProgramDev &pd, const typename 
   if (active)
     cur = __ldg(blk);
   uint32_t k = 0;
+  // every block but a lane's last is whole: a loop without masks or votes up
+  // to the shortest lane's last block, then the general one
+  const uint32_t kMin = __reduce_min_sync(0xffffffffu, active ? nblk : 0xffffffffu);
+  if (kMin != 0xffffffffu) {
+    for (; k + 1 < kMin; ++k) {
+      if (active)
+        nxt = __ldg(blk + k + 1);
+      const bool stopped = process_chunk<STYLE, WANT_START>(pd, fast, tab, cls, cur,
+                                                            active ? 0xffffu : 0u, k * 16, wk,
+                                                            active, true);
+      if (stopped)
+        active = false;
+      cur = nxt;
+    }
+  }
   while (__any_sync(0xffffffffu, active)) {
     uint32_t hi = 0;
     bool last = true;
