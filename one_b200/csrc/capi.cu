@@ -262,9 +262,12 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.hotBytes = 0;
   if (!prog->smemTable) {
     // rows of the shallowest states (the renumbering keeps the serialized,
-    // breadth-first order inside each group) go to shared memory as well:
-    // what fits beside the class table and the sort scratch
-    size_t room = prop.sharedMemPerBlockOptin - (27u << 10);
+    // breadth-first order inside each group) go to shared memory as well.
+    // Not all of it: what shared memory takes, L1 loses, and the rest of the
+    // table and the text live there.  Measured on B200 (2000 keywords, 2.2 MB
+    // table, tools/hot_rows_sweep.py): no mirror 886 GB/s, 16 KB 1017,
+    // 96 KB 1046, 160 KB 1070, 203 KB 847.
+    size_t room = prop.sharedMemPerBlockOptin - (68u << 10);
     if (const char *env = getenv("RED_B200_HOT_ROWS_BYTES"))
       room = std::min<size_t>(room, strtoull(env, nullptr, 0));
     pd.hotBytes = static_cast<uint32_t>(std::min<size_t>(room, padded) & ~size_t(15));
