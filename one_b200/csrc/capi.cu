@@ -96,16 +96,38 @@ struct HostPipe {
   int32_t *dRes[kSlots]{};
   uint32_t *dMs[kSlots]{};
   uint32_t *dMe[kSlots]{};
+  // optimistic chunks: the device word the kernels take their line count from
+  // (all ones = the chunk's span held every line, 0 = it did not: nothing was
+  // walked), and where it is copied back to (pinned)
+  uint64_t *dN[kSlots]{};
+  uint64_t *hN = nullptr;
+  uint64_t slotFirst[kSlots]{}, slotCount[kSlots]{};
+  bool slotOptimistic[kSlots]{};
 
   void release() {
     for (int s = 0; s < kSlots; ++s) {
       if (stream[s]) cudaStreamDestroy(stream[s]);
       if (done[s]) cudaEventDestroy(done[s]);
       cudaFree(dText[s]); cudaFree(dStarts[s]); cudaFree(dLens[s]);
-      cudaFree(dRes[s]); cudaFree(dMs[s]); cudaFree(dMe[s]);
+      cudaFree(dRes[s]); cudaFree(dMs[s]); cudaFree(dMe[s]); cudaFree(dN[s]);
     }
+    if (hN) cudaFreeHost(hN);
   }
 };
+
+/* Every line of the chunk inside [lo, hi)?  If not, *dN becomes 0 and the
+   kernels that follow on the stream walk nothing. */
+__global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, uint64_t count,
+                                  uint64_t lo, uint64_t hi, unsigned long long *dN) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  bool bad = false;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint64_t a = starts[i], b = a + lens[i];
+    bad |= (a < lo) || (b > hi) || (b < a);
+  }
+  if (__any_sync(0xffffffffu, bad) && ((threadIdx.x & 31) == 0))
+    atomicMin(dN, 0ull);
+}
 
 extern "C" {
 
@@ -443,7 +465,9 @@ static int ensure_pipe(red_b200_program *prog, size_t textCap, size_t lineCap) {
     CUDA_TRY(cudaMalloc(&pp->dRes[s], lineCap * 4));
     CUDA_TRY(cudaMalloc(&pp->dMs[s], lineCap * 4));
     CUDA_TRY(cudaMalloc(&pp->dMe[s], lineCap * 4));
+    CUDA_TRY(cudaMalloc(&pp->dN[s], 8));
   }
+  CUDA_TRY(cudaHostAlloc(&pp->hN, HostPipe::kSlots * 8, cudaHostAllocDefault));
   return RED_B200_OK;
 }
 
@@ -482,85 +506,165 @@ int red_b200_match_batch_host(const red_b200_program *cprog,
   if (const char *env = getenv("RED_B200_HOST_CHUNK_BYTES"))
     textTarget = std::max<size_t>(1 << 16, strtoull(env, nullptr, 0));
 
-  /* Chunks are planned one at a time, while the GPU works on the previous
-     ones: the plan is a min/max over the lines' extents, taken in blocks of
-     4096 lines so that the loop stays branch-free. */
+  /* Planning a chunk exactly is a min/max over its lines' extents - 12 bytes
+     of index per line through the host's caches, which with several ranks on
+     one host starves the copies.  Lines are normally in text order, so a
+     chunk is planned OPTIMISTICALLY in O(log n): the span runs from the first
+     line's start to the last line's end, the count is found by bisection on
+     the starts, and a kernel checks on the device, in front of the matcher,
+     that every line really lies inside the span.  If not, nothing of that
+     chunk is walked (the kernels take their line count from a device word the
+     check zeroes) and the chunk is redone with the exact plan afterwards. */
   const uint64_t kBlock = 4096;
-  uint64_t first = 0;
-  int rc = RED_B200_OK;
-  for (size_t ci = 0; first < n_lines; ++ci) {
-    uint64_t lo = ~0ull, hi = 0, count = 0;
-    while (first + count < n_lines) {
-      const uint64_t m = std::min<uint64_t>(kBlock, n_lines - first - count);
-      const uint64_t *sp = starts + first + count;
-      const uint32_t *lp = lens + first + count;
-      uint64_t blo = ~0ull, bhi = 0;
-      for (uint64_t k = 0; k < m; ++k) {
-        const uint64_t a0 = sp[k], a1 = sp[k] + lp[k];
-        blo = a0 < blo ? a0 : blo;
-        bhi = a1 > bhi ? a1 : bhi;
+  const bool optimistic = getenv("RED_B200_EXACT_PLAN") == nullptr;
+  std::vector<std::pair<uint64_t, uint64_t>> redo;  // (first, count) of chunks that failed the check
+  auto endOf = [&](uint64_t i) { return starts[i] + lens[i]; };
+
+  // runs lines [from, from + todo): optimistic chunks if allowed, else exact ones
+  auto run = [&](uint64_t from, uint64_t todo, bool allowOptimistic) -> int {
+    uint64_t first = from;
+    const uint64_t stop = from + todo;
+    int rc = RED_B200_OK;
+    for (size_t ci = 0; first < stop; ++ci) {
+      uint64_t lo = ~0ull, hi = 0, count = 0;
+      bool opt = false;
+      if (allowOptimistic) {
+        lo = starts[first];
+        uint64_t c = std::min<uint64_t>(lineTarget, stop - first);
+        if (endOf(first + c - 1) - lo > textTarget) {
+          // largest count whose last line still ends inside the target (if the
+          // starts ascend; if they do not, the device check will say so)
+          uint64_t good = 1, bad = c;
+          while (good + 1 < bad) {
+            const uint64_t mid = good + (bad - good) / 2;
+            if ((endOf(first + mid - 1) >= lo) && (endOf(first + mid - 1) - lo <= textTarget))
+              good = mid;
+            else
+              bad = mid;
+          }
+          c = good;
+        }
+        hi = endOf(first + c - 1);
+        count = c;
+        opt = (hi >= lo) && (hi <= text_len) && (hi - lo <= textTarget + (8u << 20));
       }
-      const uint64_t nlo = std::min(lo, blo), nhi = std::max(hi, bhi);
-      if (count && (((nhi - nlo) > textTarget) || (count + m > lineTarget)))
-        break;
-      lo = nlo;
-      hi = nhi;
-      count += m;
-    }
-    if (hi > text_len)
-      return fail(RED_B200_EAPI, "line extends past end of text");
-    // (re)size the staging buffers; growing waits for the work in flight
-    if (!prog->pipe || (prog->pipe->textCap < hi - lo) || (prog->pipe->lineCap < count)) {
-      if (prog->pipe)
-        for (int s = 0; s < HostPipe::kSlots; ++s)
-          CUDA_TRY(cudaStreamSynchronize(prog->pipe->stream[s]));
-      rc = ensure_pipe(prog, std::max<size_t>(hi - lo, textTarget + (8u << 20)),
-                       std::max<size_t>(count, lineTarget));
+      if (!opt) {
+        lo = ~0ull;
+        hi = 0;
+        count = 0;
+        while (first + count < stop) {
+          const uint64_t m = std::min<uint64_t>(kBlock, stop - first - count);
+          const uint64_t *sp = starts + first + count;
+          const uint32_t *lp = lens + first + count;
+          uint64_t blo = ~0ull, bhi = 0;
+          for (uint64_t k = 0; k < m; ++k) {
+            const uint64_t a0 = sp[k], a1 = sp[k] + lp[k];
+            blo = a0 < blo ? a0 : blo;
+            bhi = a1 > bhi ? a1 : bhi;
+          }
+          const uint64_t nlo = std::min(lo, blo), nhi = std::max(hi, bhi);
+          if (count && (((nhi - nlo) > textTarget) || (count + m > lineTarget)))
+            break;
+          lo = nlo;
+          hi = nhi;
+          count += m;
+        }
+        if (hi > text_len)
+          return fail(RED_B200_EAPI, "line extends past end of text");
+      }
+      // (re)size the staging buffers; growing waits for the work in flight
+      if (!prog->pipe || (prog->pipe->textCap < hi - lo) || (prog->pipe->lineCap < count)) {
+        if (prog->pipe) {
+          for (int s = 0; s < HostPipe::kSlots; ++s)
+            CUDA_TRY(cudaStreamSynchronize(prog->pipe->stream[s]));
+          for (int s = 0; s < HostPipe::kSlots; ++s)
+            if (prog->pipe->slotOptimistic[s] && (prog->pipe->hN[s] == 0)) {
+              redo.emplace_back(prog->pipe->slotFirst[s], prog->pipe->slotCount[s]);
+              prog->pipe->slotOptimistic[s] = false;
+            }
+        }
+        rc = ensure_pipe(prog, std::max<size_t>(hi - lo, textTarget + (8u << 20)),
+                         std::max<size_t>(count, lineTarget));
+        if (rc != RED_B200_OK)
+          return rc;
+      }
+      HostPipe *pp = prog->pipe;
+      const int s = static_cast<int>(ci % HostPipe::kSlots);
+      cudaStream_t st = pp->stream[s];
+      // slot free? (its previous copy-out finished)
+      CUDA_TRY(cudaEventSynchronize(pp->done[s]));
+      if (pp->slotOptimistic[s] && (pp->hN[s] == 0))
+        redo.emplace_back(pp->slotFirst[s], pp->slotCount[s]);
+      pp->slotOptimistic[s] = opt;
+      pp->slotFirst[s] = first;
+      pp->slotCount[s] = count;
+      pp->hN[s] = ~0ull;
+      // The device copy keeps the span's alignment modulo 16, and the kernels are
+      // handed a text base shifted by the span's (aligned) start, so the caller's
+      // absolute start offsets are used as they are - no per-line rewriting.
+      const uint64_t lo16 = lo & ~uint64_t(15);
+      CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], starts + first, count * 8,
+                               cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + first, count * 4,
+                               cudaMemcpyHostToDevice, st));
+      if (opt) {
+        CUDA_TRY(cudaMemsetAsync(pp->dN[s], 0xff, 8, st));
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((count + 255) / 256, 4 * 148));
+        span_check_kernel<<<grid, 256, 0, st>>>(pp->dStarts[s], pp->dLens[s], count, lo, hi,
+                                                reinterpret_cast<unsigned long long *>(pp->dN[s]));
+      }
+      CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (lo - lo16), text + lo, hi - lo,
+                               cudaMemcpyHostToDevice, st));
+      BatchArgs args;
+      args.text = pp->dText[s] - lo16;
+      args.starts = pp->dStarts[s];
+      args.lens = pp->dLens[s];
+      args.nLines = count;
+      args.nLinesDev = opt ? pp->dN[s] : nullptr;
+      args.results = pp->dRes[s];
+      args.matchStarts = match_starts ? pp->dMs[s] : nullptr;
+      args.matchEnds = match_ends ? pp->dMe[s] : nullptr;
+      rc = launch_batch(prog, args, verb, style, st);
       if (rc != RED_B200_OK)
         return rc;
+      CUDA_TRY(cudaMemcpyAsync(results + first, pp->dRes[s], count * 4,
+                               cudaMemcpyDeviceToHost, st));
+      if (match_starts)
+        CUDA_TRY(cudaMemcpyAsync(match_starts + first, pp->dMs[s], count * 4,
+                                 cudaMemcpyDeviceToHost, st));
+      if (match_ends)
+        CUDA_TRY(cudaMemcpyAsync(match_ends + first, pp->dMe[s], count * 4,
+                                 cudaMemcpyDeviceToHost, st));
+      if (opt)
+        CUDA_TRY(cudaMemcpyAsync(pp->hN + s, pp->dN[s], 8, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(pp->done[s], st));
+      first += count;
     }
+    // drain: everything copied out, failed optimistic chunks collected
     HostPipe *pp = prog->pipe;
-    const int s = static_cast<int>(ci % HostPipe::kSlots);
-    cudaStream_t st = pp->stream[s];
-    // slot free? (its previous copy-out finished)
-    CUDA_TRY(cudaEventSynchronize(pp->done[s]));
-    // The device copy keeps the span's alignment modulo 16, and the kernels are
-    // handed a text base shifted by the span's (aligned) start, so the caller's
-    // absolute start offsets are used as they are - no per-line rewriting.
-    const uint64_t lo16 = lo & ~uint64_t(15);
-    CUDA_TRY(cudaMemcpyAsync(pp->dText[s] + (lo - lo16), text + lo, hi - lo,
-                             cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pp->dStarts[s], starts + first, count * 8,
-                             cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(pp->dLens[s], lens + first, count * 4,
-                             cudaMemcpyHostToDevice, st));
-    BatchArgs args;
-    args.text = pp->dText[s] - lo16;
-    args.starts = pp->dStarts[s];
-    args.lens = pp->dLens[s];
-    args.nLines = count;
-    args.results = pp->dRes[s];
-    args.matchStarts = match_starts ? pp->dMs[s] : nullptr;
-    args.matchEnds = match_ends ? pp->dMe[s] : nullptr;
-    rc = launch_batch(prog, args, verb, style, st);
+    if (pp) {
+      for (int s = 0; s < HostPipe::kSlots; ++s)
+        CUDA_TRY(cudaStreamSynchronize(pp->stream[s]));
+      for (int s = 0; s < HostPipe::kSlots; ++s) {
+        if (pp->slotOptimistic[s] && (pp->hN[s] == 0))
+          redo.emplace_back(pp->slotFirst[s], pp->slotCount[s]);
+        pp->slotOptimistic[s] = false;
+      }
+    }
+    return RED_B200_OK;
+  };
+
+  int rc = run(0, n_lines, optimistic);
+  if (rc != RED_B200_OK)
+    return rc;
+  // chunks whose lines were not all inside the optimistic span: exact plan
+  std::vector<std::pair<uint64_t, uint64_t>> again;
+  again.swap(redo);
+  for (auto &fc : again) {
+    rc = run(fc.first, fc.second, false);
     if (rc != RED_B200_OK)
       return rc;
-    CUDA_TRY(cudaMemcpyAsync(results + first, pp->dRes[s], count * 4,
-                             cudaMemcpyDeviceToHost, st));
-    if (match_starts)
-      CUDA_TRY(cudaMemcpyAsync(match_starts + first, pp->dMs[s], count * 4,
-                               cudaMemcpyDeviceToHost, st));
-    if (match_ends)
-      CUDA_TRY(cudaMemcpyAsync(match_ends + first, pp->dMe[s], count * 4,
-                               cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(pp->done[s], st));
-    first += count;
   }
-  HostPipe *pp = prog->pipe;
-  if (!pp)
-    return RED_B200_OK;
-  for (int s = 0; s < HostPipe::kSlots; ++s)
-    CUDA_TRY(cudaStreamSynchronize(pp->stream[s]));
   return RED_B200_OK;
 }
 

@@ -118,10 +118,11 @@ batch_anchored_kernel(const ProgramDev pd, const BatchArgs args) {
   const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
 
   // persistent CTAs: tile t covers lines [t*blockDim, (t+1)*blockDim)
-  const uint64_t tiles = (args.nLines + blockDim.x - 1) / blockDim.x;
+  const uint64_t nLines = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint64_t tiles = (nLines + blockDim.x - 1) / blockDim.x;
   for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const uint64_t line = t * blockDim.x + threadIdx.x;
-    if (line >= args.nLines)
+    if (line >= nLines)
       continue;
     const uint8_t *p = args.text + args.starts[line];
     uint32_t len = args.lens[line];
@@ -290,10 +291,11 @@ batch_sliding_kernel(const ProgramDev pd, const BatchArgs args) {
     stage_table(pd, smem + kClsBytes);
   __syncthreads();
   const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
-  const uint64_t tiles = (args.nLines + blockDim.x - 1) / blockDim.x;
+  const uint64_t nLines = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint64_t tiles = (nLines + blockDim.x - 1) / blockDim.x;
   for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const uint64_t line = t * blockDim.x + threadIdx.x;
-    if (line >= args.nLines)
+    if (line >= nLines)
       continue;
     const uint8_t *p = args.text + args.starts[line];
     const uint32_t len = args.lens[line];
@@ -337,15 +339,16 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
   const Tab tab{SMEM ? smem + kClsBytes
                      : static_cast<const unsigned char *>(pd.table)};
   const uint32_t lane = threadIdx.x & 31;
+  const uint64_t nLines = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   constexpr uint32_t kBatch = 8;  // lines claimed at a time
   for (;;) {
     unsigned long long first = 0;
     if (lane == 0)
       first = atomicAdd(lineCounter, static_cast<unsigned long long>(kBatch));
     first = __shfl_sync(0xffffffffu, first, 0);
-    if (first >= args.nLines)
+    if (first >= nLines)
       break;
-    const uint64_t last = min(args.nLines, static_cast<uint64_t>(first) + kBatch);
+    const uint64_t last = min(nLines, static_cast<uint64_t>(first) + kBatch);
     for (uint64_t line = first; line < last; ++line) {
       const uint8_t *p = args.text + __ldg(args.starts + line);
       const uint32_t len = __ldg(args.lens + line);

@@ -244,6 +244,40 @@ def test_edge_cases_ragged_and_empty(gpu_red, vectors, oracle_cls):
     prog.close()
 
 
+def test_host_batch_chunk_planning(gpu_red, vectors, oracle_cls, monkeypatch):
+    """The host pipeline plans its chunks optimistically (lines in text order,
+    span = first start .. last end, count by bisection) and a kernel checks on
+    the device that every line is inside; chunks that fail are redone with the
+    exact plan.  Lines in text order, reversed, shuffled, with views that
+    overlap, many small chunks - and RED_B200_EXACT_PLAN=1 - all agree with the
+    oracle, for every verb."""
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    orc = oracle_cls(blob)
+    text, starts, lens = synth.make_corpus(60000, seed=77)
+    rng = np.random.RandomState(5)
+    orders = {"in order": np.arange(len(starts)), "reversed": np.arange(len(starts))[::-1].copy(),
+              "shuffled": rng.permutation(len(starts)),
+              "mostly ordered": np.arange(len(starts))}
+    orders["mostly ordered"][[100, 40000]] = orders["mostly ordered"][[40000, 100]]
+    monkeypatch.setenv("RED_B200_HOST_CHUNK_BYTES", str(256 << 10))
+    for exact in (False, True):
+        if exact:
+            monkeypatch.setenv("RED_B200_EXACT_PLAN", "1")
+        prog = gpu_red.Program(blob)
+        for name, perm in orders.items():
+            st, ln = starts[perm].copy(), lens[perm].copy()
+            if name == "shuffled":
+                ln[::7] = np.minimum(ln[::7] + 40, (len(text) - st[::7]).astype(np.uint32))  # overlapping views
+            for verb, sty in (("match", "last"), ("match", "instant"), ("check", "full"), ("search", "first")):
+                res, ms, me = prog.match_batch_host(text, st, ln, verb, sty)
+                eres, ems, eme = orc.batch(text, st, ln, verb, sty)
+                assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), \
+                    (exact, name, verb, sty)
+        prog.close()
+
+
 def test_device_resident_batch_and_compaction(gpu_red, vectors, oracle_cls):
     import torch
     from one_b200 import synth
