@@ -1,12 +1,12 @@
-/* kernels_lanes.cu - the production batch kernels for check/match.
-
-   Two schedules share one chunk engine (process_chunk):
-     batch_tile_kernel   (default)  a warp takes 32 consecutive lines, one per
-                                    lane, all lanes in step, outcomes stored
-                                    together; next tile prefetched
-     batch_lanes_kernel  (RED_B200_VARIANT=3)  persistent lanes, described next
-   They measure within a few percent of each other on B200 (profiles/); the
-   tile schedule is simpler and slightly ahead, so it is the default.
+/* kernels_lanes.cu - the entry point of the check/match batch kernels
+   (launch_batch_lanes, at the end of this file: it picks the schedule) and the
+   persistent-lane schedule, one of the three that share the chunk engine
+   (chunk_engine.cuh):
+     kernels_sorted.cu  (default)              tiles of equally long lines
+     kernels_tile.cu    (RED_B200_VARIANT=2)   tiles of 32 consecutive lines
+     this file          (RED_B200_VARIANT=3)   persistent lanes, described next
+   Measured against each other on B200 in profiles/; every schedule is
+   bit-exact (tests/test_gpu_parity.py::test_kernel_variants_agree).
 
    Persistent lanes.
 

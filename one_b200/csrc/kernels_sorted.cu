@@ -1,5 +1,16 @@
-/* kernels_sorted.cu - the tile schedule over length-sorted groups of lines
-   (default when start positions are tracked). */
+/* kernels_sorted.cu - the production schedule of the check/match batch
+   kernels: tiles of 32 lines that span the same number of 16-byte chunks.
+
+   block_sort_kernel    sorts the line numbers of every block of 4096 lines by
+                        chunk count (2 bytes per line written);
+   batch_sorted_kernel  takes tiles of 32 consecutive entries of that array,
+                        walks them in step with the chunk engine
+                        (chunk_engine.cuh), a tight mask-free loop between the
+                        head and the tail chunk, and - when start positions are
+                        asked for - finds them in a second phase, for matched
+                        lines only.
+   RED_B200_VARIANT=4 sorts per warp inside the batch kernel instead (the first
+   version, kept for A/B).  DESIGN.md has the measurements. */
 
 #include "lanes_dispatch.cuh"
 #include "stream.h"
@@ -10,9 +21,10 @@ namespace {
 
 using namespace dev;
 
-/* batch_sorted_kernel (default when positions are tracked; RED_B200_VARIANT=4
-   forces it): the tile schedule with tiles of SIMILAR
-   lines.  In a tile every lane waits for the longest line; with consecutive
+/* batch_sorted_kernel: the tile schedule with tiles of SIMILAR lines.  The
+   paragraph below describes the per-warp sort (RED_B200_VARIANT=4); with the
+   pre-sorted array (gOrder, the default) a group is one tile of that array.
+   In a tile every lane waits for the longest line; with consecutive
    lines of a log one instruction serves 20 of 32 lanes on average (ncu:
    profiles/), and the shared-memory pipe that bounds the kernel is busy with
    mostly-empty wavefronts.  Here a warp claims a GROUP of 32*T consecutive
