@@ -81,7 +81,8 @@ template <int STYLE, bool WANT_START, class Fast, class Tab, class ClsT>
 __device__ __forceinline__ bool
 process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT *cls,
               const uint4 &cur, const uint32_t mask, const uint32_t pos0,
-              Walk<STYLE, WANT_START> &wk, const bool cValid, const bool allFull = false) {
+              Walk<STYLE, WANT_START> &wk, const bool cValid, const bool allFull = false,
+              const uint32_t quarters = 0xfu) {
   bool stopped = false;
   // A lane with nothing in this chunk (its line is over, or it has no line)
   // stays out altogether: its lookups would be pure noise in the shared-memory
@@ -121,22 +122,27 @@ process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT
           }
         }
         else {
+          // `quarters` (warp-uniform): bit q clear = no lane of the warp has a
+          // byte in quarter q of this chunk (tiles sorted by the alignment of
+          // their lines' ends): the quarter's eight lookups are not issued
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t word = word_of(cur, q);
             uint32_t m = 0;
+            if (quarters & (1u << q)) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = 4 * q + jj;
-              const bool act = (mask & (1u << j)) != 0;
-              const uint32_t ne = fast.step(e, word, jj);
-              if (WANT_START) {
-                if (act && (e == eInit) && (ne != eInit))
-                  msFast = pos0 + j;
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * q + jj;
+                const bool act = (mask & (1u << j)) != 0;
+                const uint32_t ne = fast.step(e, word, jj);
+                if (WANT_START) {
+                  if (act && (e == eInit) && (ne != eInit))
+                    msFast = pos0 + j;
+                }
+                if (act)
+                  e = ne;
+                m = max(m, e);
               }
-              if (act)
-                e = ne;
-              m = max(m, e);
             }
             if (q == 0) { mq0 = m; cp0 = e; }
             if (q == 1) { mq1 = m; cp1 = e; }

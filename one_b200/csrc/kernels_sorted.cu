@@ -56,10 +56,14 @@ inline size_t sorted_smem_bytes(int warps, uint32_t T) {
    dozen adjacent blocks: neighbouring lines are walked at about the same time
    and the DRAM traffic stays at the algorithmic minimum. */
 constexpr uint32_t kSortBlock = 4096;
+// chunk count (32) x leading empty quarters of the first chunk (4) x trailing
+// empty quarters of the last chunk (4): the lanes of a tile then also agree on
+// which quarters of the head and tail chunks hold no byte of anybody's line
+constexpr uint32_t kSortBuckets = 512;
 
 __global__ void __launch_bounds__(256)
 block_sort_kernel(const BatchArgs args, uint16_t *order) {
-  __shared__ uint32_t hist[32];
+  __shared__ uint32_t hist[kSortBuckets];
   __shared__ uint16_t sorted[kSortBlock];
   constexpr int kPer = kSortBlock / 256;  // lines per thread, strided: coalesced loads
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
@@ -68,8 +72,8 @@ block_sort_kernel(const BatchArgs args, uint16_t *order) {
   for (uint64_t blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
     const uint64_t base = blk * kSortBlock;
     const uint32_t cnt = (base < n) ? static_cast<uint32_t>(min(n - base, static_cast<uint64_t>(kSortBlock))) : 0;
-    if (threadIdx.x < 32)
-      hist[threadIdx.x] = 0;
+    for (uint32_t b = threadIdx.x; b < kSortBuckets; b += 256)
+      hist[b] = 0;
     // all index loads of the thread are issued before the first is used
     uint32_t len[kPer];
     uint32_t low[kPer];
@@ -79,12 +83,14 @@ block_sort_kernel(const BatchArgs args, uint16_t *order) {
       len[k] = (i < cnt) ? __ldg(args.lens + base + i) : 0;
       low[k] = (i < cnt) ? static_cast<uint32_t>(__ldg(args.starts + base + i)) : 0;
     }
-    uint8_t bucket[kPer];
+    uint16_t bucket[kPer];
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       // chunks the line spans from its 16-byte aligned start: what a lane walks
       const uint32_t skip = static_cast<uint32_t>((textLow + low[k]) & 15);
-      bucket[k] = static_cast<uint8_t>(min(31u, (skip + len[k] + 15u) >> 4));
+      const uint32_t chunks = min(31u, (skip + len[k] + 15u) >> 4);
+      const uint32_t tailEmpty = (16u - ((skip + len[k]) & 15u)) & 15u;  // bytes past the line in its last chunk
+      bucket[k] = static_cast<uint16_t>((chunks * 4 + (skip >> 2)) * 4 + (tailEmpty >> 2));
     }
     __syncthreads();
 #pragma unroll
@@ -93,15 +99,26 @@ block_sort_kernel(const BatchArgs args, uint16_t *order) {
         atomicAdd(&hist[bucket[k]], 1u);
     __syncthreads();
     if (threadIdx.x < 32) {
-      const uint32_t c = hist[threadIdx.x];
-      uint32_t incl = c;
+      // exclusive scan of the counters: 16 consecutive ones per lane
+      constexpr int kEach = kSortBuckets / 32;
+      uint32_t sum = 0;
+#pragma unroll
+      for (int b = 0; b < kEach; ++b)
+        sum += hist[threadIdx.x * kEach + b];
+      uint32_t incl = sum;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t up = __shfl_up_sync(kFull, incl, d);
         if (threadIdx.x >= d)
           incl += up;
       }
-      hist[threadIdx.x] = incl - c;
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int b = 0; b < kEach; ++b) {
+        const uint32_t c = hist[threadIdx.x * kEach + b];
+        hist[threadIdx.x * kEach + b] = run;
+        run += c;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -391,8 +408,13 @@ batch_sorted_kernel(const ProgramDev pd, const BatchArgs args,
       const uint32_t mask = (0xffffu >> (16 - hi)) & (0xffffu << lo);
       const uint32_t pos0 = k * 16 - skip;
       const bool allFull = __all_sync(kFull, (mask == 0xffffu) || (mask == 0));
-      const bool stopped =
-          process_chunk<STYLE, false>(pd, fast, tab, cls, cur, mask, pos0, wk, active, allFull);
+      // quarters of the chunk in which some lane has a byte
+      uint32_t quarters = 0xfu;
+      if (!allFull)
+        quarters = (__any_sync(kFull, mask & 0x000fu) ? 1u : 0u) | (__any_sync(kFull, mask & 0x00f0u) ? 2u : 0u) |
+                   (__any_sync(kFull, mask & 0x0f00u) ? 4u : 0u) | (__any_sync(kFull, mask & 0xf000u) ? 8u : 0u);
+      const bool stopped = process_chunk<STYLE, false>(pd, fast, tab, cls, cur, mask, pos0, wk, active,
+                                                       allFull, quarters);
       if (stopped)
         ranOut = false;
       if (stopped || lastChunk)
