@@ -42,6 +42,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 namespace red_b200 {
 
@@ -127,7 +128,7 @@ __device__ __forceinline__ void walk_bytes(const ProgramDev &pd, const typename 
 }
 
 /* text/len: the window; v0: the (exact) state at its start */
-template <bool SMEM, int K, class ClsT>
+template <bool SMEM, int K, class ClsT, bool TRACK>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 stream_walk_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
                    uint32_t chunkBytes, uint64_t nChunks, ChunkRec *recs,
@@ -162,16 +163,18 @@ stream_walk_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
       walk_bytes<STY_FULL, false, Eng>(pd, fast, tab, cls, text + begin - lb, lb, sp);
       rec.startV = (c == 0) ? v0 : sp.v;
     }
-    Walk<STY_LAST, true> wk;
+    // TRACK: also the last exit from the initial state (three more
+    // instructions per step: only the lazy start search asks for it)
+    Walk<STY_LAST, TRACK> wk;
     wk.begin(pd);
     wk.v = rec.startV;
     wk.mstart = kNoPos;
-    walk_bytes<STY_LAST, true, Eng>(pd, fast, tab, cls, text + begin, n, wk);
+    walk_bytes<STY_LAST, TRACK, Eng>(pd, fast, tab, cls, text + begin, n, wk);
     if (mine) {
       rec.endV = wk.v;
       rec.accV = wk.accV;
       rec.accEnd = wk.absorbed ? n : wk.mend;
-      rec.lastLeaveOff = wk.mstart;
+      rec.lastLeaveOff = TRACK ? wk.mstart : kNoPos;
       rec.dirty = 0;
       recs[c] = rec;
     }
@@ -337,9 +340,11 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   } while (0)
 
   const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : pd.hotBytes);
-  auto walk = stream_walk_kernel<SMEM, K, ClsT>;
+  auto walkPlain = stream_walk_kernel<SMEM, K, ClsT, false>;
+  auto walkTrack = stream_walk_kernel<SMEM, K, ClsT, true>;
   auto tail = stream_tail_kernel<SMEM, K, ClsT>;
-  TRY(cudaFuncSetAttribute(walk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TRY(cudaFuncSetAttribute(walkPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TRY(cudaFuncSetAttribute(walkTrack, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 
   // chunk size of a window: one chunk per lane of the whole chip if that
@@ -363,20 +368,20 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
                           (style == RED_B200_STY_TANGENT);
   if (!earlyStyle && !pd.hasFinalStates && !getenv("RED_B200_STREAM_WINDOW"))
     firstWindow = (len + 15) & ~uint64_t(15);
-  uint64_t maxChunks = 0;
-  for (uint64_t pos = 0, w = firstWindow; pos < len; pos += w, w *= kWindowGrowth) {
-    const uint64_t bytes = std::min(w, len - pos);
-    maxChunks = std::max(maxChunks, (bytes + chunkFor(bytes) - 1) / chunkFor(bytes));
-  }
+  // the most chunks any window can have: 1 KB chunks up to one per lane, more
+  // only with 16 KB chunks
+  const uint64_t maxChunks = std::max<uint64_t>(lanes, (len + 16383) / 16384) + 1;
 
-  ChunkRec *recs = nullptr;
+  ChunkRec *recs = nullptr, *recs2 = nullptr;
   StreamSummary *dSum = nullptr;
   TailOut *dTail = nullptr;
   TRY(scratch_alloc(&recs, maxChunks * sizeof(ChunkRec), stream));
+  TRY(scratch_alloc(&recs2, maxChunks * sizeof(ChunkRec), stream));
   TRY(scratch_alloc(&dSum, sizeof(StreamSummary), stream));
   TRY(scratch_alloc(&dTail, sizeof(TailOut), stream));
   auto release = [&]() {
     scratch_free(recs, stream);
+    scratch_free(recs2, stream);
     scratch_free(dSum, stream);
     scratch_free(dTail, stream);
   };
@@ -393,26 +398,18 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   };
 
   const uint64_t none = ~0ull;
-  out->result = 0;
-  out->start = 0;
-  out->end = 0;
-  // carried across windows
-  uint32_t v0 = pd.initV;
-  uint64_t lastLeave = none;     // last position at which the initial state was left
-  uint64_t lastAccEnd = 0;       // one past the last accepting position so far
-  uint32_t lastAccV = kNone;
-
   StreamSummary init{};
   init.firstBad = none;
   init.firstAccChunk = none;
-  int rc = RED_B200_OK;
-  bool decided = false;
-  uint64_t window = firstWindow;
-  for (uint64_t base = 0; (base < len) && !decided; base += window, window *= kWindowGrowth) {
-    const uint64_t bytes = std::min(window, len - base);
-    const uint64_t chunk = chunkFor(bytes);
+
+  /* One window [base, base + bytes) from the exact state v0: walk, confirm,
+     re-walk until nothing changes (or, with stopEarly, until the confirmed
+     prefix decides the walk).  track: also record the exits from the initial
+     state.  The records stay in `into`. */
+  auto runWindow = [&](uint64_t base, uint64_t bytes, uint32_t v0, uint64_t chunk, bool track,
+                       bool stopEarly, ChunkRec *into, StreamSummary &sum, bool &decided) -> int {
     const uint64_t nChunks = (bytes + chunk - 1) / chunk;
-    const uint8_t *wText = dText + base;  // windows are multiples of 16 bytes
+    const uint8_t *wText = dText + base;  // a multiple of 16 bytes
     // a small window is spread over all SMs with few warps each (a lane
     // walks several times faster when its SM is not full)
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, (nChunks + 31) / 32));
@@ -420,20 +417,20 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
         kMaxThreads, ((nChunks + grid - 1) / grid + 31) / 32 * 32));
     const unsigned vgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount * 4, (nChunks + 255) / 256));
     const unsigned rgrid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(geo.smCount, (nChunks + 1023) / 1024)));
-    walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, recs, 1, v0);
+    auto walk = track ? walkTrack : walkPlain;
+    walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, into, 1, v0);
     ++*launches;
-    StreamSummary sum;
+    decided = false;
     for (uint64_t round = 0;; ++round) {
       TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
-      stream_verify_kernel<<<vgrid, 256, 0, stream>>>(recs, nChunks, v0, dSum);
-      stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(recs, nChunks, none, dSum);
+      stream_verify_kernel<<<vgrid, 256, 0, stream>>>(into, nChunks, v0, dSum);
+      stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(into, nChunks, none, dSum);
       *launches += 2;
       TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
       TRY(cudaStreamSynchronize(stream));
       // is the walk decided inside the confirmed prefix?
-      const bool early = (style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_FIRST) ||
-                         (style == RED_B200_STY_TANGENT);
-      if ((early && (sum.firstAccChunk != none)) || (sum.reduced && (sum.finalV >= pd.absV))) {
+      if (stopEarly && ((earlyStyle && (sum.firstAccChunk != none)) ||
+                        (sum.reduced && (sum.finalV >= pd.absV)))) {
         decided = true;
         break;
       }
@@ -443,13 +440,86 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
         why = "stream stitching did not converge";
         return RED_B200_EINTERNAL;
       }
-      walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, recs, 0, v0);
+      walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, into, 0, v0);
       ++*launches;
     }
+    return RED_B200_OK;
+  };
 
-    const bool early = (style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_FIRST) ||
-                       (style == RED_B200_STY_TANGENT);
-    if (early && (sum.firstAccChunk != none)) {
+  struct Win {
+    uint64_t base, bytes, chunk;
+    uint32_t v0;
+  };
+  std::vector<Win> wins;  // the windows walked, in text order; recs holds the last one's records
+
+  /* Outcome::start_: the last position in front of `end` at which the initial
+     state was left (Matcher.h:436-439).  Nobody tracked it - that costs three
+     instructions in every step - so it is searched for now, backwards: the
+     tail of the last window in growing pieces (256 KB, x8, each from the exact
+     state phase 1 recorded at a chunk boundary) with tracking on, then the
+     windows in front of it.  With DFAs of the ".*pattern" kind the first
+     piece has it. */
+  auto lastLeaveBefore = [&](uint64_t end, uint64_t &found) -> int {
+    found = none;
+    int rc = RED_B200_OK;
+    const Win &L = wins.back();
+    uint64_t hiChunk = (end - L.base + L.chunk - 1) / L.chunk;  // chunks [0, hiChunk) of L reach `end`
+    uint64_t piece = 256u << 10;
+    while ((hiChunk > 0) && (found == none)) {
+      const uint64_t nCh = std::max<uint64_t>(1, piece / L.chunk);
+      const uint64_t loChunk = (hiChunk > nCh) ? hiChunk - nCh : 0;
+      uint32_t vStart = L.v0;
+      if (loChunk > 0) {
+        ChunkRec r;
+        TRY(cudaMemcpyAsync(&r, recs + loChunk, sizeof(r), cudaMemcpyDeviceToHost, stream));
+        TRY(cudaStreamSynchronize(stream));
+        vStart = r.startV;
+      }
+      const uint64_t rBase = L.base + loChunk * L.chunk;
+      const uint64_t rBytes = std::min(end, L.base + hiChunk * L.chunk) - rBase;
+      StreamSummary s2;
+      bool dummy = false;
+      const uint64_t ch = chunkFor(rBytes);
+      if ((rc = runWindow(rBase, rBytes, vStart, ch, true, false, recs2, s2, dummy)) != RED_B200_OK)
+        return rc;
+      if (s2.lastLeaveP1 != 0)
+        found = rBase + (s2.lastLeaveP1 - 1) * ch + s2.lastLeaveOff;
+      hiChunk = loChunk;
+      piece *= 8;
+    }
+    for (size_t w = wins.size() - 1; (w-- > 0) && (found == none);) {
+      StreamSummary s2;
+      bool dummy = false;
+      if ((rc = runWindow(wins[w].base, wins[w].bytes, wins[w].v0, wins[w].chunk, true, false, recs2, s2,
+                          dummy)) != RED_B200_OK)
+        return rc;
+      if (s2.lastLeaveP1 != 0)
+        found = wins[w].base + (s2.lastLeaveP1 - 1) * wins[w].chunk + s2.lastLeaveOff;
+    }
+    return RED_B200_OK;
+  };
+
+  out->result = 0;
+  out->start = 0;
+  out->end = 0;
+  // carried across windows
+  uint32_t v0 = pd.initV;
+  uint64_t lastAccEnd = 0;       // one past the last accepting position so far
+  uint32_t lastAccV = kNone;
+  uint64_t walkedEnd = 0;        // end of the confirmed text
+
+  int rc = RED_B200_OK;
+  bool decided = false;
+  uint64_t window = firstWindow;
+  for (uint64_t base = 0; (base < len) && !decided; base += window, window *= kWindowGrowth) {
+    const uint64_t bytes = std::min(window, len - base);
+    const uint64_t chunk = chunkFor(bytes);
+    wins.push_back(Win{base, bytes, chunk, v0});
+    StreamSummary sum;
+    if ((rc = runWindow(base, bytes, v0, chunk, false, true, recs, sum, decided)) != RED_B200_OK)
+      return rc;
+
+    if (earlyStyle && (sum.firstAccChunk != none)) {
       // careful walk from the chunk with the first accepting position
       const uint64_t c = sum.firstAccChunk;
       const uint64_t from = base + c * chunk;
@@ -461,21 +531,12 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
       if (t.accepted) {
         out->result = t.result;
         out->end = t.end;
-        // the initial state was last left either inside the tail walk, or in
-        // an earlier chunk of this window, or in an earlier window
+        // the initial state was last left either inside the tail walk or
+        // somewhere in front of it
         uint64_t leave = t.lastLeave;
-        if ((leave == none) && (c > 0)) {
-          TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
-          stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(recs, nChunks, c, dSum);
-          ++*launches;
-          StreamSummary before;
-          TRY(cudaMemcpyAsync(&before, dSum, sizeof(before), cudaMemcpyDeviceToHost, stream));
-          TRY(cudaStreamSynchronize(stream));
-          if (before.lastLeaveP1 != 0)
-            leave = base + (before.lastLeaveP1 - 1) * chunk + before.lastLeaveOff;
-        }
-        if (leave == none)
-          leave = lastLeave;
+        if ((leave == none) && (from > 0))
+          if ((rc = lastLeaveBefore(from, leave)) != RED_B200_OK)
+            return rc;
         out->start = (leave == none) ? 0 : leave;
       }
       return RED_B200_OK;
@@ -483,12 +544,11 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
 
     // fold the window (its confirmed prefix, which is all of it unless the
     // walk was decided) into the running outcome
-    if (sum.lastLeaveP1 != 0)
-      lastLeave = base + (sum.lastLeaveP1 - 1) * chunk + sum.lastLeaveOff;
     if (sum.lastAccP1 != 0) {
       lastAccEnd = base + (sum.lastAccP1 - 1) * chunk + sum.lastAccEnd;
       lastAccV = sum.lastAccV;
     }
+    walkedEnd = std::min(len, base + sum.reduced * chunk);
     v0 = sum.finalV;
     if (v0 >= pd.absV)
       decided = true;
@@ -497,26 +557,25 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   // Instant/First/Tangent come here only without a match.  v0 is the final
   // state, or a state that can never be left.
   const bool absorbing = (v0 >= pd.absV) && (v0 < pd.pureV);
+  int32_t r = 0;
+  uint32_t resultV = kNone;
   if (style == RED_B200_STY_FULL) {
     // the final state decides (a pure dead end carries result 0)
-    if ((v0 >= pd.acceptV) && (v0 < pd.pureV)) {
-      int32_t r = 0;
-      if ((rc = resultOf(v0, r)) != RED_B200_OK)
-        return rc;
-      out->result = r;
-      out->start = (lastLeave == none) ? 0 : lastLeave;
-      out->end = len;
-    }
+    if ((v0 >= pd.acceptV) && (v0 < pd.pureV))
+      resultV = v0;
   }
-  else if (style == RED_B200_STY_LAST) {
-    if (lastAccV != kNone) {
-      int32_t r = 0;
-      if ((rc = resultOf(lastAccV, r)) != RED_B200_OK)
+  else if (style == RED_B200_STY_LAST)
+    resultV = lastAccV;
+  if (resultV != kNone) {
+    if ((rc = resultOf(resultV, r)) != RED_B200_OK)
+      return rc;
+    uint64_t leave = none;
+    if ((r > 0) && (walkedEnd > 0))
+      if ((rc = lastLeaveBefore(walkedEnd, leave)) != RED_B200_OK)
         return rc;
-      out->result = r;
-      out->start = (lastLeave == none) ? 0 : lastLeave;
-      out->end = absorbing ? len : lastAccEnd;
-    }
+    out->result = r;
+    out->start = (leave == none) ? 0 : leave;
+    out->end = ((style == RED_B200_STY_FULL) || absorbing) ? len : lastAccEnd;
   }
 #undef TRY
   return RED_B200_OK;
