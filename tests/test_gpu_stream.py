@@ -111,6 +111,26 @@ def test_stream_windows(gpu_red, redlib, vectors, oracle_cls, monkeypatch):
     check_stream(gpu_red, oracle_cls, redlib.compileToSerialized(parity), b"ab" * 30000 + b"a", "w-parity")
 
 
+def test_stream_start_far_behind_the_match(gpu_red, redlib, oracle_cls, monkeypatch):
+    """The start position is searched for backwards from the match, lazily.
+    Worst case: the initial state is left at byte 0 and never again, the match
+    is at the very end - the search has to go back through every piece and
+    every window.  Also with exits scattered thinly, and with none at all."""
+    p = redlib.Parser()
+    p.add(b"a.*z", 1, 0)
+    p.add(b"[b-y ]*q.*z", 2, 0)
+    blob = redlib.compileToSerialized(p)
+    rng = np.random.RandomState(17)
+    body = bytes(rng.choice(list(b"bcdefgh ijklmnop"), size=900000).astype(np.uint8))
+    cases = [b"a" + body + b"z", b"a" + body + b"z" + body[:5000],
+             body[:300000] + b"q" + body[300000:] + b"z", body + b"z", b"a" + body]
+    for small in (False, True):
+        if small:
+            monkeypatch.setenv("RED_B200_STREAM_WINDOW", "16384")
+        for i, raw in enumerate(cases):
+            check_stream(gpu_red, oracle_cls, blob, raw, ("far", small, i))
+
+
 def test_large_dfa_uses_global_table(gpu_red, redlib, oracle_cls):
     """BASELINE configs[2]: a union too large for shared memory (L2-resident
     global table, 4-byte entries), first/last styles."""
