@@ -349,9 +349,20 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
     if (first >= nLines)
       break;
     const uint64_t last = min(nLines, static_cast<uint64_t>(first) + kBatch);
+    // the batch's index entries are loaded together (lane j holds line j's) and
+    // the head of every line is pulled towards the SM before the first is walked
+    uint64_t myStart = 0;
+    uint32_t myLen = 0;
+    if (first + lane < last) {
+      myStart = __ldg(args.starts + first + lane);
+      myLen = __ldg(args.lens + first + lane);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(args.text + myStart));
+      if (myLen > 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(args.text + myStart + 128));
+    }
     for (uint64_t line = first; line < last; ++line) {
-      const uint8_t *p = args.text + __ldg(args.starts + line);
-      const uint32_t len = __ldg(args.lens + line);
+      const uint8_t *p = args.text + __shfl_sync(0xffffffffu, myStart, static_cast<int>(line - first));
+      const uint32_t len = __shfl_sync(0xffffffffu, myLen, static_cast<int>(line - first));
       int32_t result = 0;
       uint32_t start = 0, end = 0;
       if (len == 0) {
