@@ -302,10 +302,18 @@ int red_b200_grep_host(const red_b200_program *prog, const uint8_t *text,
 
 /* ---- one long byte stream ---------------------------------------------- */
 
-/* match()/check() of one long device-resident text: the text is cut into
-   chunks, every chunk is run from every DFA state that can be live at its
-   start (all states, pruned as they converge), and the chunk state maps are
-   stitched with a parallel prefix composition.  Synchronous on `stream`. */
+/* match()/check() of one long device-resident text (reference:
+   match(exec, ptr, len, style), include/Matcher.h:79, over a single text).
+   The text is taken in windows of growing size and cut into chunks, one lane
+   each; a chunk's start state is speculated from a lookback window, every
+   chunk is walked in parallel, chunk i is confirmed against the end state of
+   chunk i-1 and the unconfirmed ones are walked again from the right state
+   until nothing changes: exact for every DFA, one or two rounds for DFAs that
+   forget their past.  A walk that is decided (first match for Instant/First/
+   Tangent, a state that can never be left) ends with its window; the start
+   position is searched for backwards only when an outcome needs it.
+   d_text must be 16-byte aligned.  Verbs check and match.  Synchronous on
+   `stream`. */
 int red_b200_match_stream_device(const red_b200_program *prog,
                                  const uint8_t *d_text, uint64_t len,
                                  int verb, int style, red_b200_outcome *out,
