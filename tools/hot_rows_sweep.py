@@ -1,3 +1,4 @@
+"""Hot-row mirror size sweep for a global-table program (2000 keywords): GB/s per size (GPU box)."""
 import os, sys, time
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch

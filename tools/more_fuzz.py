@@ -1,3 +1,4 @@
+"""More seeds for tests/test_gpu_fuzz.py (GPU box): python tools/more_fuzz.py"""
 import sys
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from one_b200 import build, red
