@@ -200,7 +200,7 @@ process_chunk(const ProgramDev &pd, const Fast &fast, const Tab &tab, const ClsT
                         }
                       }
                       // without start tracking mstart is free: it reports how
-                      // many bytes the walk consumed (kernels_tile2.cu)
+                      // many bytes the walk consumed (kernels_sorted.cu, phase 2)
                       if (!WANT_START && stopped)
                         wk.mstart = pos0 + 4 * q + jj + 1;
                     }
