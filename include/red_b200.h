@@ -123,6 +123,15 @@ void red_b200_program_free(red_b200_program *prog);
 int red_b200_program_get_info(const red_b200_program *prog,
                               red_b200_program_info *info);
 
+/* Kernels launched through this program so far, and how many of them were
+   launches of the staged batch kernel (diagnostics; bench.py's gpu_launches). */
+long red_b200_program_launch_count(const red_b200_program *prog);
+long red_b200_program_hot_launch_count(const red_b200_program *prog);
+/* With RED_B200_HOT_DEBUG=1 in the environment at upload: cycle counters of
+   the staged batch kernel since the last call (tools/hot_sweep.py prints
+   them); all zero otherwise.  Synchronises the device. */
+int red_b200_program_debug_counters(red_b200_program *prog, uint64_t out[16]);
+
 /* Host-only validation; returns NULL when good, else the reference's wording
    of the complaint (checkHeader, lib/Serializer.cpp:270). */
 const char *red_b200_check_header(const void *serialized, size_t len);

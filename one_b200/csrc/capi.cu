@@ -129,6 +129,108 @@ __global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, 
     atomicMin(dN, 0ull);
 }
 
+/* (Re)builds a hot image of the staged batch kernel from entry counts (or
+   breadth-first order when there are none) and puts it on the device.  Buffers
+   of an earlier image stay allocated until the program is freed: kernels
+   launched with them may still be running on other streams. */
+static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, HotDev &out) {
+  HotImage hot;
+  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, hot);
+  void *dTab = nullptr, *dC2v = nullptr, *dCodeOf = nullptr;
+  cudaError_t err;
+  if ((err = cudaMalloc(&dTab, hot.table.size())) != cudaSuccess)
+    return err;
+  prog->hotBuffers.push_back(dTab);
+  if ((err = cudaMalloc(&dC2v, 1024)) != cudaSuccess)
+    return err;
+  prog->hotBuffers.push_back(dC2v);
+  if ((err = cudaMalloc(&dCodeOf, hot.codeOf.size())) != cudaSuccess)
+    return err;
+  prog->hotBuffers.push_back(dCodeOf);
+  if ((err = cudaMemcpy(dTab, hot.table.data(), hot.table.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return err;
+  if ((err = cudaMemcpy(dC2v, hot.codeToV.data(), 1024, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return err;
+  if ((err = cudaMemcpy(dCodeOf, hot.codeOf.data(), hot.codeOf.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return err;
+  if ((err = cudaDeviceSynchronize()) != cudaSuccess)
+    return err;
+  HotDev hd;
+  hd.table = static_cast<const uint8_t *>(dTab);
+  hd.codeToV = static_cast<const uint32_t *>(dC2v);
+  hd.codeOf = static_cast<const uint8_t *>(dCodeOf);
+  hd.tableBytes = static_cast<uint32_t>(hot.table.size());
+  hd.nHot = hot.nHot;
+  hd.cAccept = hot.cAccept;
+  hd.cAbs = hot.cAbs;
+  hd.cPure = hot.cPure;
+  hd.initCode = hot.initCode;
+  hd.coverage = hot.coverage;
+  hd.wideTable = prog->smemTable ? 0 : 1;
+  out = hd;
+  return cudaSuccess;
+}
+
+/* First sizeable batch of a program: walk a sample of its lines on the full
+   table, count how often every state is entered, and choose the hot sets from
+   that (the states a walk over THIS kind of text spends its time in): one for
+   style Instant, whose walks end at the first accepting state, one for the
+   styles that go on.  Synchronises the stream once.  Skipped while the stream
+   is being captured. */
+static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(prog->hotMu);
+  if (prog->hotProfiled.load())
+    return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if ((cudaStreamIsCapturing(stream, &cap) != cudaSuccess) || (cap != cudaStreamCaptureStatusNone)) {
+    cudaGetLastError();
+    return;
+  }
+  prog->hotProfiled.store(1);  // one attempt, whatever comes of it
+  const uint32_t nStates = prog->img.stateCount;
+  const size_t words = 2 * static_cast<size_t>(nStates) + 1;
+  unsigned long long *dHist = nullptr;
+  if (cudaMalloc(&dHist, words * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  std::vector<uint64_t> visits(words, 0);
+  const uint64_t stride = std::max<uint64_t>(1, args.nLines / 32768);
+  bool ok = cudaMemsetAsync(dHist, 0, words * 8, stream) == cudaSuccess;
+  ok = ok && (launch_profile(prog->dev, prog->smemTable ? 0 : 1, args, stride, nStates, dHist,
+                             dHist + 2 * static_cast<size_t>(nStates), stream) == cudaSuccess);
+  ok = ok && (cudaMemcpyAsync(visits.data(), dHist, words * 8, cudaMemcpyDeviceToHost, stream) == cudaSuccess);
+  ok = ok && (cudaStreamSynchronize(stream) == cudaSuccess);
+  cudaFree(dHist);
+  if (!ok) {
+    cudaGetLastError();
+    return;
+  }
+  prog->launches += 1;
+  uint64_t seen = 0;
+  for (uint32_t st = 0; st < nStates; ++st) {
+    seen += visits[st];
+    visits[nStates + st] += visits[st];  // the second half becomes the whole line's count
+  }
+  if (seen == 0) {
+    prog->hotProfiled.store(0);  // nothing was walked (a chunk whose span check failed): try again
+    return;
+  }
+  const uint64_t samples = (args.nLines + stride - 1) / stride;
+  if (samples)
+    prog->avgLineBytes.store(static_cast<uint32_t>(std::min<uint64_t>(visits[2 * static_cast<size_t>(nStates)] / samples, 1u << 20)));
+  if (nStates > prog->hotMaxStates) {
+    HotDev instant, whole;
+    if ((upload_hot(prog, visits.data(), instant) == cudaSuccess) &&
+        (upload_hot(prog, visits.data() + nStates, whole) == cudaSuccess)) {
+      prog->hotDev[0] = instant;
+      prog->hotDev[1] = whole;
+    }
+    else
+      cudaGetLastError();
+  }
+}
+
 extern "C" {
 
 const char *red_b200_last_error(void) { return g_err.c_str(); }
@@ -304,7 +406,6 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   // the host copies of the big tables are no longer needed
   std::vector<uint16_t>().swap(img.table16);
   std::vector<uint32_t>().swap(img.table32);
-  std::vector<uint32_t>().swap(prog->parsed.next);
 
   if (const char *env = getenv("RED_B200_THREADS"))
     prog->tune.threads = atoi(env);
@@ -316,6 +417,44 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     prog->tune.linesPerLane = atoi(env);
   if (const char *env = getenv("RED_B200_SIMPLE_WALK"))
     prog->tune.simpleWalk = atoi(env) != 0;
+
+  // the staged batch kernel's image: breadth-first hot set until a batch has
+  // been profiled
+  if (const char *env = getenv("RED_B200_HOT"))
+    prog->hotEnabled = atoi(env) != 0;
+  if (const char *env = getenv("RED_B200_HOT_STATES"))
+    prog->hotMaxStates = std::max(1, std::min(atoi(env), static_cast<int>(kHotMax)));
+  if (const char *env = getenv("RED_B200_HOT_PROFILE"))
+    prog->hotProfileWanted = atoi(env) != 0;
+  if (const char *env = getenv("RED_B200_HOT_WARPS"))
+    prog->hotTune.consumerWarps = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_DEBUG"))
+    if (atoi(env) != 0) {
+      void *dbg = nullptr;
+      if (cudaMalloc(&dbg, 16 * 8) == cudaSuccess) {
+        cudaMemset(dbg, 0, 16 * 8);
+        prog->hotBuffers.push_back(dbg);
+        prog->hotTune.debug = static_cast<unsigned long long *>(dbg);
+      }
+    }
+  if (const char *env = getenv("RED_B200_HOT_DEFER"))
+    prog->hotTune.defer = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_PRODUCERS"))
+    prog->hotTune.producers = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_SLOTS"))
+    prog->hotTune.slots = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_BATCH"))
+    prog->hotTune.batchLines = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_SLOT_BYTES"))
+    prog->hotTune.slotBytes = atoi(env);
+  if (prog->hotEnabled) {
+    if ((err = upload_hot(prog, nullptr, prog->hotDev[0])) != cudaSuccess) {
+      for (void *p : prog->hotBuffers)
+        cudaFree(p);
+      return cleanup(err, "upload of the hot image");
+    }
+    prog->hotDev[1] = prog->hotDev[0];
+  }
 
   *out = prog;
   return RED_B200_OK;
@@ -330,6 +469,8 @@ void red_b200_program_free(red_b200_program *prog) {
     delete prog->pipe;
   }
   release_grep_pipe(prog);
+  for (void *p : prog->hotBuffers)
+    cudaFree(p);
   cudaFree(prog->dTable);
   cudaFree(prog->dCls);
   cudaFree(prog->dResults);
@@ -365,6 +506,28 @@ long red_b200_program_launch_count(const red_b200_program *prog) {
   return prog ? prog->launches.load() : 0;
 }
 
+/* RED_B200_HOT_DEBUG=1 at upload: cycle counters of the staged batch kernel,
+   summed over all launches so far (synchronises the device; zeroes them).
+   [0..3] producers: total, waiting for index entries, waiting for a slot, batches;
+   [4..8] consumers: total, waiting for a batch, walking, writing back, tiles. */
+int red_b200_program_debug_counters(red_b200_program *prog, uint64_t out[16]) {
+  if (!prog || !out)
+    return fail(RED_B200_EAPI, "null argument");
+  memset(out, 0, 16 * 8);
+  if (!prog->hotTune.debug)
+    return RED_B200_OK;
+  DeviceGuard guard(prog->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, prog->hotTune.debug, 16 * 8, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(prog->hotTune.debug, 0, 16 * 8));
+  return RED_B200_OK;
+}
+
+/* of those, launches of the staged batch kernel (kernels_hot.cu) */
+long red_b200_program_hot_launch_count(const red_b200_program *prog) {
+  return prog ? prog->hotLaunches.load() : 0;
+}
+
 static int launch_batch(red_b200_program *prog, const BatchArgs &args,
                         int verb, int style, cudaStream_t stream) {
   int launches = 0;
@@ -372,7 +535,26 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
   if ((verb == RED_B200_VERB_CHECK) || (verb == RED_B200_VERB_MATCH)) {
     BatchArgs a = args;
     a.checkLeader = (verb == RED_B200_VERB_CHECK) && (prog->dev.leaderLen > 0);
-    if (prog->tune.variant == 1)  // v1 tile kernel, kept as the A/B baseline
+    // the staged kernel (kernels_hot.cu) where it applies
+    err = cudaErrorNotSupported;
+    if (prog->hotEnabled && (prog->tune.variant == 0) && !a.checkLeader && !a.matchStarts &&
+        ((style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_LAST) || (style == RED_B200_STY_FULL))) {
+      if (prog->hotProfileWanted && !prog->hotProfiled.load() && (a.nLines >= 8192))
+        profile_hot(prog, a, stream);
+      unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
+      HotDev hd;
+      {
+        std::lock_guard<std::mutex> lock(prog->hotMu);
+        hd = prog->hotDev[(style == RED_B200_STY_INSTANT) ? 0 : 1];
+      }
+      err = launch_batch_hot(prog->dev, hd, a, style, prog->geo, prog->hotTune,
+                             prog->avgLineBytes.load(), ctr, stream, &launches);
+      if (err == cudaSuccess)
+        prog->hotLaunches += 1;
+    }
+    if (err != cudaErrorNotSupported)
+      ;
+    else if (prog->tune.variant == 1)  // v1 tile kernel, kept as the A/B baseline
       err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
                                   prog->geo, prog->tune, stream, &launches);
     else {

@@ -1,0 +1,1064 @@
+/* kernels_hot.cu - the staged check/match batch kernel (the production path for
+   styles Instant, Last and Full) and the visit-count profile kernel.
+
+   What bounded the first production kernel (kernels_sorted.cu; ncu in
+   profiles/r1_final_ncu_summary.json) was the LSU data pipe, one 128-byte
+   wavefront per cycle per SM: every lane's 16-byte text load from global
+   memory was a wavefront of its own (each lane sits in a different line), and
+   every byte cost two dependent shared-memory lookups (class, then
+   transition).  Here
+
+     * the TEXT goes through shared memory: a producer warp brings the
+       contiguous span of a batch of 256 consecutive lines into a ring of
+       slots with one bulk-async copy (cp.async.bulk ... mbarrier::
+       complete_tx), the consumer lanes read their line with LDS.128;
+     * a step is ONE lookup in the hot image (program.h: HotImage): up to 255
+       states with one-byte codes and byte-indexed rows; lanes that leave the
+       hot set continue on the full table in global memory (L2) until they are
+       back;
+     * the length sort (tiles of 32 lines that span the same number of
+       16-byte chunks) happens inside the CTA, per batch, by the producer
+       warp, from index entries it prefetches with cp.async; outcomes are
+       collected per batch in shared memory and written back coalesced.
+
+   Roles in a CTA: warps 0 .. NC-1 are consumers (a tile of 32 lines at a
+   time, claimed in order from a shared-memory ticket), warp NC is the
+   producer.  Synchronisation is by mbarriers only: full[slot] (producer's
+   arrival + the copy's bytes), empty[slot] (one arrival per tile).
+
+   Lines that are not laid out back to back (shuffled or overlapping views,
+   a batch whose span exceeds a slot) are gathered: one bulk copy per line,
+   as many lines per batch as fit a slot.  A line longer than a slot is walked
+   from global memory on the full table. */
+
+#include "hot.h"
+#include "program.h"
+#include "walk.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace red_b200 {
+
+namespace {
+
+using namespace dev;
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr uint32_t kMaxBatch = 256;       // lines per batch (and per claimed sub-block)
+constexpr uint32_t kSortBuckets = 256;    // chunks a lane walks (32) x 16-byte bank group of the line's start (8)
+constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
+constexpr uint32_t kMaxSlots = 12;
+constexpr uint32_t kMaxProducers = 4;
+
+struct HotParams {
+  // byte offsets into dynamic shared memory (behind its 256-byte alignment)
+  uint32_t oC2v, oBars, oCtl, oProd, oMeta, oSlots;
+  uint32_t nSlots, slotBytes, batchLines, tilesPerBatch, metaBytes, nProducers, prodBytes;
+  unsigned long long *dbg;  // null, or 16 cycle counters (HotTuning::debug)
+};
+
+// per-slot metadata (offsets within the slot's block)
+constexpr uint32_t kMetaIdx = 0;                          // u16[256] line (relative to the batch) at sorted position
+constexpr uint32_t kMetaOff = kMetaIdx + 2 * kMaxBatch;   // u16[256] text offset in the slot
+constexpr uint32_t kMetaLen = kMetaOff + 2 * kMaxBatch;   // u16[256]
+constexpr uint32_t kMetaRes = kMetaLen + 2 * kMaxBatch;   // i32[256] by line
+constexpr uint32_t kMetaEnd = kMetaRes + 4 * kMaxBatch;   // u32[256] by line
+constexpr uint32_t kMetaFirst = kMetaEnd + 4 * kMaxBatch; // u64 first line of the batch
+constexpr uint32_t kMetaCnt = kMetaFirst + 8;             // u32 lines in the batch
+constexpr uint32_t kMetaDone = kMetaCnt + 4;              // u32 tiles finished
+constexpr uint32_t kMetaSeq = kMetaDone + 4;              // u32 number of the batch the slot holds
+constexpr uint32_t kMetaBytes = kMetaSeq + 4;
+
+// per-producer scratch
+constexpr uint32_t kProdMeta = 0;                             // sorted idx/off/len of the batch being prepared
+constexpr uint32_t kProdOff = kProdMeta + 6 * kMaxBatch;      // u16[256] text offsets by line (gather path)
+constexpr uint32_t kProdHist = kProdOff + 2 * kMaxBatch;      // u32[kSortBuckets]
+constexpr uint32_t kProdBytes = kProdHist + 4 * kSortBuckets;
+
+// ---- PTX helpers ----------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// as mbar_try_wait, but the hardware may keep the thread suspended for up to `ns`
+__device__ __forceinline__ bool mbar_try_wait_for(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk-async copy global -> shared; completion counted on `bar` in bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// ---- the full table, wherever it lives (the cold path) ---------------------
+
+struct AnyTable {
+  const unsigned char *base;
+  uint32_t shift;  // byte offset of a row = v << shift
+  uint32_t wide;   // 1: u32 entries, 0: u16
+  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
+    const unsigned char *p = base + ((static_cast<size_t>(v) << shift) + co);
+    return wide ? __ldg(reinterpret_cast<const uint32_t *>(p))
+                : static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p)));
+  }
+};
+
+__device__ __forceinline__ AnyTable any_table(const ProgramDev &pd, uint32_t wide) {
+  AnyTable t;
+  t.base = static_cast<const unsigned char *>(pd.table);
+  t.shift = wide ? 2 : pd.unitShift + 1;
+  t.wide = wide;
+  return t;
+}
+
+/* Walks n bytes at p (generic pointer: a slot or global memory) on the full
+   table with the reference's per-byte decisions (walk.cuh).  True = the walk is
+   over; wk.mstart then holds the number of bytes consumed.  Rare: lanes that
+   left the hot set, lines longer than a slot. */
+template <int STYLE>
+__device__ __noinline__ bool cold_bytes(const ProgramDev &pd, uint32_t wide, Walk<STYLE, false> &wk,
+                                        const uint8_t *p, uint32_t n, uint32_t pos) {
+  const AnyTable tab = any_table(pd, wide);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t co = __ldg(pd.clsOffset + p[i]);
+    if (wk.step(pd, tab, co, pos + i)) {
+      wk.mstart = pos + i + 1;
+      return true;
+    }
+  }
+  return false;
+}
+
+/* One byte on the full table (a lane that left the hot set); true = the walk is
+   over. */
+template <int STYLE>
+__device__ __noinline__ bool cold_step(const ProgramDev &pd, uint32_t wide, Walk<STYLE, false> &wk,
+                                       uint32_t byte, uint32_t pos) {
+  const AnyTable tab = any_table(pd, wide);
+  return wk.step(pd, tab, __ldg(pd.clsOffset + byte), pos);
+}
+
+struct HotCtx {
+  uint32_t tab;     // shared address of the hot table
+  uint32_t c2v;     // shared address of codeToV; codeToResult sits 1024 bytes behind it
+  uint32_t sink;    // = nHot
+  uint32_t cLimit;  // codes >= cLimit need a decision
+  uint32_t cAbs, cPure;
+  uint32_t wide;
+  const uint8_t *codeOf;
+};
+
+// hx.tab has a zero low byte, so PRMT puts a text byte and the table base
+// together in one instruction: a step is PRMT, IMAD, LDS.U8
+__device__ __forceinline__ uint32_t hot_next(const HotCtx &hx, uint32_t c, uint32_t word, int jj) {
+  return lds8(c * kHotStride + __byte_perm(word, hx.tab, 0x7650 | jj));
+}
+__device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, uint32_t byte) {
+  return lds8(c * kHotStride + hx.tab + byte);
+}
+
+/* The fast pass over one aligned 16-byte chunk of one line per lane: no
+   decisions, only the largest code per quarter and the code at each quarter's
+   end.  [lo, hi): the bytes of the chunk that belong to the line; FULL16: they
+   all do.  Returns false when no code reached hx.cLimit (code is then the
+   state behind the chunk); true when one did: (j, cj) is where the careful
+   pass has to start, code is unchanged. */
+template <bool FULL16>
+__device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const uint32_t lo, const uint32_t hi,
+                                         uint32_t &code, uint32_t &j, uint32_t &cj) {
+  uint32_t c = code;
+  uint32_t mq0 = 0, mq1 = 0, mq2 = 0, mq3 = 0;
+  uint32_t cp0 = 0, cp1 = 0, cp2 = 0;
+  const uint32_t mask = FULL16 ? 0xffffu : ((0xffffu >> (16 - hi)) & (0xffffu << lo));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+    uint32_t m = 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      // a byte outside the line: no lookup at all (a predicated load), the
+      // lane's lookups would only collide with the others' in the banks
+      if (FULL16 || (mask & (1u << (4 * q + jj))))
+        c = hot_next(hx, c, word, jj);
+      m = max(m, c);
+    }
+    if (q == 0) { mq0 = m; cp0 = c; }
+    if (q == 1) { mq1 = m; cp1 = c; }
+    if (q == 2) { mq2 = m; cp2 = c; }
+    if (q == 3) { mq3 = m; }
+  }
+  if (max(max(mq0, mq1), max(mq2, mq3)) < hx.cLimit) {
+    code = c;
+    return false;
+  }
+  // the careful pass starts at the first flagged quarter
+  j = 0;
+  cj = code;
+  if (mq0 < hx.cLimit) {
+    j = 4; cj = cp0;
+    if (mq1 < hx.cLimit) {
+      j = 8; cj = cp1;
+      if (mq2 < hx.cLimit) { j = 12; cj = cp2; }
+    }
+  }
+  j = max(j, lo);
+  return true;
+}
+
+/* The careful pass: bytes [j, hi) of the chunk at chunkAddr one by one with
+   the style's decisions; on the hot table while the state is hot, on the full
+   table while it is not (First/Tangent are not walked here: the limit never
+   changes).  c: the state in front of byte j in, behind the last byte taken
+   out (hx.sink: it is in wk.v).  Returns true when the walk is over. */
+template <int STYLE>
+__device__ __forceinline__ bool hot_careful(const ProgramDev &pd, const HotCtx &hx, const uint32_t chunkAddr,
+                                            uint32_t j, const uint32_t hi, const uint32_t pos0,
+                                            uint32_t &c, Walk<STYLE, false> &wk) {
+#pragma unroll 1
+  for (; j < hi; ++j) {
+    const uint32_t byte = lds8(chunkAddr + j);
+    bool stopped = false;
+    if (c == hx.sink) {
+      // (a copy goes through the call, so that wk itself can stay in registers)
+      Walk<STYLE, false> tmp = wk;
+      stopped = cold_step<STYLE>(pd, hx.wide, tmp, byte, pos0 + j);
+      wk = tmp;
+      if (!stopped)
+        c = hx.codeOf[state_index(pd, wk.v)];
+    }
+    else {
+      const uint32_t nc = hot_next_byte(hx, c, byte);
+      if (nc >= hx.cLimit) {
+        if (nc == hx.sink) {
+          // leaves the hot set: this byte again, on the full table
+          wk.v = lds32(hx.c2v + 4 * c);
+          c = hx.sink;
+          --j;
+          continue;
+        }
+        if (nc >= hx.cPure)
+          stopped = true;  // pure dead end (Matcher.h:478)
+        else if (STYLE == STY_FULL)
+          stopped = true;  // absorbing accept: the outcome is known
+        else {
+          wk.accV = 0x80000000u | lds32(hx.c2v + 1024 + 4 * nc);  // tagged: the result id itself
+          wk.mend = pos0 + j + 1;
+          if (STYLE == STY_INSTANT)
+            stopped = true;
+          else if (nc >= hx.cAbs) {
+            wk.absorbed = true;
+            stopped = true;
+          }
+        }
+      }
+      c = nc;
+    }
+    if (stopped) {
+      wk.mstart = pos0 + j + 1;  // bytes consumed
+      return true;
+    }
+  }
+  return false;
+}
+
+// fast pass, and the careful pass right behind it where it is needed
+template <int STYLE, bool FULL16>
+__device__ __forceinline__ bool hot_chunk(const ProgramDev &pd, const HotCtx &hx, const uint4 &w,
+                                          const uint32_t chunkAddr, const uint32_t lo, const uint32_t hi,
+                                          const uint32_t pos0, uint32_t &code, Walk<STYLE, false> &wk) {
+  uint32_t j = lo, cj = code;
+  if ((code != hx.sink) && !hot_fast<FULL16>(hx, w, lo, hi, code, j, cj))
+    return false;
+  const bool stopped = hot_careful<STYLE>(pd, hx, chunkAddr, j, hi, pos0, cj, wk);
+  code = cj;
+  return stopped;
+}
+
+/* DEFER (styles whose walk ends at the first state that needs a decision:
+   Instant, Full): a lane whose chunk was flagged steps aside, and the careful
+   passes of a tile's flagged lanes run together once the tile is through,
+   instead of one after the other with the rest of the warp waiting. */
+template <int STYLE, bool DEFER>
+__global__ void __launch_bounds__(1024, 1)
+batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, const HotParams hp,
+                 unsigned long long *blockCounter) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  // everything sits behind a 256-byte boundary (hot_next wants the table there)
+  unsigned char *smem = smemRaw + ((256u - (smem_addr(smemRaw) & 255u)) & 255u);
+  const uint32_t sBase = smem_addr(smem);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t P = hp.nProducers;
+  const uint32_t nConsumers = (blockDim.x >> 5) - P;
+  const uint32_t R = hp.nSlots;
+  const uint32_t TPB = hp.tilesPerBatch;
+  const uint32_t barsAddr = sBase + hp.oBars;      // full[0..R), empty[0..R)
+  const uint32_t ctlAddr = sBase + hp.oCtl;        // +0 ticket, +4 next batch number, +8 producers done, +12 endQ, +16 batches that have their slot
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+
+  // stage the hot image, set up the barriers
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(hd.table);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < (hd.tableBytes >> 4); i += blockDim.x)
+      dst[i] = __ldg(src + i);
+    uint32_t *c2v = reinterpret_cast<uint32_t *>(smem + hp.oC2v);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+      const uint32_t v = __ldg(hd.codeToV + i);
+      c2v[i] = v;
+      // result id of the state behind a code (0 unless accepting)
+      c2v[256 + i] = ((i < hd.nHot) && (v >= pd.acceptV) && (v < pd.pureV))
+          ? static_cast<uint32_t>(__ldg(pd.results + state_index(pd, v))) : 0u;
+    }
+    if (threadIdx.x == 0) {
+      for (uint32_t s = 0; s < R; ++s) {
+        mbar_init(barsAddr + 8 * s, 1);
+        mbar_init(barsAddr + 8 * (R + s), TPB);
+        sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaDone, 0);
+        sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq, 0xffffffffu);
+      }
+      sts32(ctlAddr, 0);
+      sts32(ctlAddr + 4, 0);
+      sts32(ctlAddr + 8, 0);
+      sts32(ctlAddr + 12, 0xffffffffu);
+      sts32(ctlAddr + 16, 0);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  if (warp >= nConsumers) {
+    // ======================= producers =======================================
+    /* A producer's per-batch work is a chain of dependent shared-memory
+       operations behind the consumers' lookups in the same pipe; several
+       producers overlap their chains.  A batch gets its number q (it lives in
+       slot q % R, consumers take the batches in order of q) when its producer
+       has everything ready and only needs a slot to fill. */
+    const uint32_t SUB = hp.batchLines;
+    const uint64_t textA = reinterpret_cast<uint64_t>(args.text);
+    const uint32_t prodA = sBase + hp.oProd + (warp - nConsumers) * hp.prodBytes;
+    const uint32_t scrA = prodA + kProdMeta;
+    const uint32_t offA = prodA + kProdOff;
+    const uint32_t histA = prodA + kProdHist;
+    uint32_t *sHist = reinterpret_cast<uint32_t *>(smem + hp.oProd + (warp - nConsumers) * hp.prodBytes + kProdHist);
+    uint32_t q = 0;  // the batch being produced
+    constexpr uint32_t kPer = kMaxBatch / 32;
+
+    /* Slots are handed out in the order of q: a parity wait can only tell two
+       consecutive phases of a barrier apart, so the producer of batch q may
+       look at empty[q % R] only after the producer of batch q - R has seen
+       ITS phase complete. */
+    unsigned long long tAcq = 0, tIdx = 0, nBatches = 0;
+    auto acquire = [&]() -> uint32_t {
+      const long long t0 = hp.dbg ? clock64() : 0;
+      if (lane == 0) {
+        q = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl + 4), 1u);
+        while (lds32_volatile(ctlAddr + 16) != q)
+          __nanosleep(32);
+      }
+      q = __shfl_sync(kFullMask, q, 0);
+      const uint32_t s = q % R;
+      if (q >= R)
+        mbar_wait(barsAddr + 8 * (R + s), ((q / R) - 1) & 1);
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctlAddr + 16), "r"(q + 1) : "memory");
+      if (hp.dbg) {
+        tAcq += clock64() - t0;
+        ++nBatches;
+      }
+      return s;
+    };
+    /* The sort key of a line at slot offset off: the number of 16-byte chunks
+       a lane walks (lanes of a tile are in step), then the 16-byte bank group
+       its text starts in - the consumers deal a tile's entries out so that the
+       eight lanes that share a phase of an LDS.128 come from eight different
+       groups where the batch has them (see the consumers' `pos`). */
+    auto bucketOf = [](uint32_t off, uint32_t len) -> uint32_t {
+      const uint32_t chunks = ((off != kUnstaged) && (len != 0)) ? min(31u, ((off & 15) + len + 15u) >> 4) : 0;
+      // longest first: the tile that takes longest is then the first to be
+      // claimed, and the slot is not held up by a late starter
+      return (31 - chunks) * 8 + ((off >> 4) & 7);
+    };
+    // counting sort: bucket[] in, position in the sorted order out
+    auto sortPositions = [&](const uint32_t (&bucket)[kPer], const bool (&valid)[kPer], uint32_t (&pos)[kPer]) {
+      const uint32_t mineA = histA + 32 * lane;  // this lane's eight counters
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(mineA), "r"(0) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(mineA + 16), "r"(0) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; ++k)
+        pos[k] = valid[k] ? atomicAdd(sHist + bucket[k], 1u) : 0;
+      __syncwarp();
+      const uint4 c0 = lds128(mineA), c1 = lds128(mineA + 16);
+      const uint32_t sum = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= static_cast<uint32_t>(d))
+          incl += up;
+      }
+      uint4 e0, e1;
+      e0.x = incl - sum;
+      e0.y = e0.x + c0.x;
+      e0.z = e0.y + c0.y;
+      e0.w = e0.z + c0.z;
+      e1.x = e0.w + c0.w;
+      e1.y = e1.x + c1.x;
+      e1.z = e1.y + c1.y;
+      e1.w = e1.z + c1.z;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mineA), "r"(e0.x), "r"(e0.y), "r"(e0.z), "r"(e0.w) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mineA + 16), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; ++k)
+        if (valid[k])
+          pos[k] += lds32(histA + 4 * bucket[k]);
+      __syncwarp();
+    };
+    auto finishBatch = [&](uint32_t s, uint64_t first, uint32_t count) {
+      if (lane == 0) {
+        *reinterpret_cast<uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) = first;
+        sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaCnt, count);
+        sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq, q);
+      }
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(barsAddr + 8 * s);
+    };
+
+    /* The rare shapes: lines [i0, cnt) of the sub-block at `base`, read from
+       global memory.  Ranges that lie back to back and fit a slot go in with
+       one bulk copy (a range that does not fit is halved); below a tile's
+       worth the lines are gathered one by one (views that are not in text
+       order, lines of many kilobytes), one bulk copy per line; a line longer
+       than a slot is left to the consumers' global-memory walk. */
+    auto slowPath = [&](uint64_t base, uint32_t cnt) {
+      auto startOf = [&](uint32_t i) { return textA + __ldg(args.starts + base + i); };
+      auto lenOf = [&](uint32_t i) { return __ldg(args.lens + base + i); };
+      // lines [i0, i1) with offsets in offA: sorted straight into the slot's arrays
+      auto publishRange = [&](uint32_t s, uint32_t i0, uint32_t i1) {
+        const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
+        uint32_t bucket[kPer], pos[kPer];
+        bool valid[kPer];
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; ++k) {
+          const uint32_t i = i0 + lane + 32 * k;
+          valid[k] = i < i1;
+          bucket[k] = valid[k] ? bucketOf(lds16(offA + 2 * i), lenOf(i)) : 0;
+        }
+        sortPositions(bucket, valid, pos);
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; ++k) {
+          const uint32_t i = i0 + lane + 32 * k;
+          if (valid[k]) {
+            sts16(mA + kMetaIdx + 2 * pos[k], i - i0);
+            sts16(mA + kMetaOff + 2 * pos[k], lds16(offA + 2 * i));
+            sts16(mA + kMetaLen + 2 * pos[k], min(lenOf(i), 0xffffu));
+          }
+        }
+        finishBatch(s, base + i0, i1 - i0);
+      };
+      uint32_t i0 = 0, tryLines = cnt;
+      while (i0 < cnt) {
+        const uint32_t i1 = min(i0 + tryLines, cnt);
+        const uint64_t a0 = startOf(i0);
+        const uint64_t aEnd = startOf(i1 - 1) + lenOf(i1 - 1);
+        const uint64_t loA = a0 & ~15ull;
+        const uint64_t hiA = (aEnd + 15) & ~15ull;
+        bool inside = (aEnd >= a0) && (hiA - loA <= hp.slotBytes);
+        if (inside) {
+          bool mine = true;
+          for (uint32_t i = i0 + lane; i < i1; i += 32) {
+            const uint64_t a = startOf(i);
+            mine &= (a >= a0) && (a + lenOf(i) <= aEnd);
+            sts16(offA + 2 * i, static_cast<uint32_t>(a - loA));
+          }
+          inside = __all_sync(kFullMask, mine);
+        }
+        if (inside) {
+          const uint32_t s = acquire();
+          const uint32_t bytes = static_cast<uint32_t>(hiA - loA);
+          if ((lane == 0) && bytes) {
+            mbar_expect_tx(barsAddr + 8 * s, bytes);
+            bulk_g2s(sBase + hp.oSlots + s * hp.slotBytes, reinterpret_cast<const void *>(loA), bytes,
+                     barsAddr + 8 * s);
+          }
+          __syncwarp();
+          publishRange(s, i0, i1);
+          i0 = i1;
+          continue;
+        }
+        if (tryLines > 32) {
+          tryLines = (tryLines + 1) >> 1;
+          continue;
+        }
+        uint32_t running = 0, g1 = i0;
+        bool cut = false;
+        for (uint32_t g = i0; (g < cnt) && !cut; g += 32) {
+          const uint32_t i = g + lane;
+          const bool valid = i < cnt;
+          uint32_t ext = 0, low = 0;
+          bool big = false;
+          if (valid) {
+            const uint64_t a = startOf(i);
+            const uint64_t len = lenOf(i);
+            low = static_cast<uint32_t>(a & 15);
+            const uint64_t e = len ? ((a + len + 15) & ~15ull) - (a & ~15ull) : 0;
+            big = e > hp.slotBytes;
+            ext = big ? 0 : static_cast<uint32_t>(e);
+          }
+          uint32_t incl = ext;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= static_cast<uint32_t>(d))
+              incl += up;
+          }
+          const bool fits = !valid || (running + incl <= hp.slotBytes);
+          const unsigned bad = ~__ballot_sync(kFullMask, fits);
+          const uint32_t nfit = bad ? static_cast<uint32_t>(__ffs(bad) - 1) : 32u;
+          if (valid && (lane < nfit))
+            sts16(offA + 2 * i, big ? kUnstaged : running + incl - ext + low);
+          g1 = min(g + nfit, cnt);
+          if (g1 < min(g + 32, cnt))
+            cut = true;
+          else
+            running += __shfl_sync(kFullMask, incl, 31);
+        }
+        __syncwarp();
+        const uint32_t s = acquire();
+        const uint32_t slotA = sBase + hp.oSlots + s * hp.slotBytes;
+        uint32_t mineBytes = 0;
+        for (uint32_t i = i0 + lane; i < g1; i += 32) {
+          const uint32_t off = lds16(offA + 2 * i);
+          const uint64_t len = lenOf(i);
+          if ((off != kUnstaged) && len) {
+            const uint64_t a = startOf(i);
+            const uint32_t ext = static_cast<uint32_t>(((a + len + 15) & ~15ull) - (a & ~15ull));
+            bulk_g2s(slotA + (off & ~15u), reinterpret_cast<const void *>(a & ~15ull), ext, barsAddr + 8 * s);
+            mineBytes += ext;
+          }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1)
+          mineBytes += __shfl_xor_sync(kFullMask, mineBytes, d);
+        if ((lane == 0) && mineBytes)
+          mbar_expect_tx(barsAddr + 8 * s, mineBytes);
+        publishRange(s, i0, g1);
+        i0 = g1;
+      }
+    };
+
+    unsigned long long claimed = 0;
+    if (lane == 0)
+      claimed = atomicAdd(blockCounter, 1ull);
+    uint64_t block = __shfl_sync(kFullMask, claimed, 0);
+    const long long tStart = hp.dbg ? clock64() : 0;
+    while (block * SUB < n) {
+      const long long tI0 = hp.dbg ? clock64() : 0;
+      const uint64_t base = block * SUB;
+      const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base));
+      // the sub-block's index entries, lane + 32 k: coalesced, all in flight at once
+      uint64_t st[kPer];
+      uint32_t ln[kPer];
+      bool valid[kPer];
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t i = lane + 32 * k;
+        valid[k] = i < cnt;
+        st[k] = valid[k] ? __ldg(args.starts + base + i) : 0;
+        ln[k] = valid[k] ? __ldg(args.lens + base + i) : 0;
+      }
+      if (lane == 0)
+        claimed = atomicAdd(blockCounter, 1ull);  // the next sub-block; looked at below
+      // the span of the sub-block's text
+      uint64_t lo = ~0ull, hi = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < kPer; ++k)
+        if (valid[k]) {
+          st[k] += textA;
+          lo = min(lo, st[k]);
+          hi = max(hi, st[k] + ln[k]);
+        }
+      if (hp.dbg)
+        tIdx += clock64() - tI0;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(kFullMask, lo, d));
+        hi = max(hi, __shfl_xor_sync(kFullMask, hi, d));
+      }
+      const uint64_t loA = lo & ~15ull;
+      const uint64_t hiA = (hi + 15) & ~15ull;
+      if ((hi >= lo) && (hiA - loA <= hp.slotBytes)) {
+        // the usual shape: the whole sub-block's text fits a slot (whatever the
+        // order of its lines).  Sort in the scratch, then take a slot, start
+        // the copy and hand the sorted arrays over.
+        uint32_t bucket[kPer], pos[kPer];
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; ++k)
+          bucket[k] = valid[k] ? bucketOf(static_cast<uint32_t>(st[k] - loA), ln[k]) : 0;
+        sortPositions(bucket, valid, pos);
+#pragma unroll
+        for (uint32_t k = 0; k < kPer; ++k)
+          if (valid[k]) {
+            sts16(scrA + 2 * pos[k], lane + 32 * k);
+            sts16(scrA + 2 * kMaxBatch + 2 * pos[k], static_cast<uint32_t>(st[k] - loA));
+            sts16(scrA + 4 * kMaxBatch + 2 * pos[k], min(ln[k], 0xffffu));
+          }
+        __syncwarp();
+        const uint32_t s = acquire();
+        const uint32_t bytes = static_cast<uint32_t>(hiA - loA);
+        if ((lane == 0) && bytes) {
+          mbar_expect_tx(barsAddr + 8 * s, bytes);
+          bulk_g2s(sBase + hp.oSlots + s * hp.slotBytes, reinterpret_cast<const void *>(loA), bytes,
+                   barsAddr + 8 * s);
+        }
+        const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
+        static_assert((kMetaOff == 2 * kMaxBatch) && (kMetaLen == 4 * kMaxBatch), "scratch mirrors the slot's arrays");
+#pragma unroll
+        for (uint32_t k = 0; k < 6 * kMaxBatch / (32 * 16); ++k) {
+          const uint32_t o = 16 * (lane + 32 * k);
+          const uint4 v = lds128(scrA + o);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mA + o), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        finishBatch(s, base, cnt);
+      }
+      else
+        slowPath(base, cnt);
+      block = __shfl_sync(kFullMask, claimed, 0);
+    }
+    if (hp.dbg && (lane == 0)) {
+      atomicAdd(hp.dbg + 0, static_cast<unsigned long long>(clock64() - tStart));
+      atomicAdd(hp.dbg + 1, tIdx);
+      atomicAdd(hp.dbg + 2, tAcq);
+      atomicAdd(hp.dbg + 3, nBatches);
+    }
+    // the last producer to run out of lines tells the consumers how many
+    // batches there were: a ticket for a later one means the work is done
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl + 8), 1u) == P - 1) {
+        __threadfence_block();
+        const uint32_t total = lds32_volatile(ctlAddr + 4);
+        asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctlAddr + 12), "r"(total) : "memory");
+      }
+    }
+    return;
+  }
+
+  // ========================= consumers =======================================
+  HotCtx hx;
+  hx.tab = sBase;
+  hx.c2v = sBase + hp.oC2v;
+  hx.sink = hd.nHot;
+  hx.cLimit = (STYLE == STY_FULL) ? hd.cAbs : hd.cAccept;
+  hx.cAbs = hd.cAbs;
+  hx.cPure = hd.cPure;
+  hx.wide = hd.wideTable;
+  hx.codeOf = hd.codeOf;
+  unsigned long long tWait = 0, tWalk = 0, tTail = 0, nTiles = 0;
+  const long long tStartC = hp.dbg ? clock64() : 0;
+
+  for (;;) {
+    const long long tc0 = hp.dbg ? clock64() : 0;
+    uint32_t tk = 0;
+    if (lane == 0)
+      tk = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl), 1u);
+    tk = __shfl_sync(kFullMask, tk, 0);
+    const uint32_t qq = tk / TPB;
+    const uint32_t t = tk - qq * TPB;
+    const uint32_t s = qq % R;
+    /* Wait for batch qq.  A parity wait tells two consecutive phases of
+       full[s] apart and no more: with several producers batches are published
+       out of order, and this warp may be here before batch qq - R - same slot -
+       is even published.  The slot's sequence number says whose phase it was. */
+    bool ended = false;
+    const uint32_t seqAddr = sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq;
+    for (uint32_t spins = 0;; ++spins) {
+      if (mbar_try_wait(barsAddr + 8 * s, (qq / R) & 1)) {
+        if (lds32_volatile(seqAddr) == qq)
+          break;
+        __nanosleep(64);  // an earlier phase: batch qq - R is still to come
+      }
+      // not there yet: is there such a batch at all?  (looked at every so
+      // often only: a poll is a shared-memory wavefront the walkers want)
+      if ((spins & 15) == 15) {
+        if (qq >= lds32_volatile(ctlAddr + 12)) {
+          ended = true;
+          break;
+        }
+      }
+    }
+    if (ended)
+      break;
+    const long long tc1 = hp.dbg ? clock64() : 0;
+    const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
+    const uint32_t cnt = lds32(mA + kMetaCnt);
+    // entries of a tile are sorted by bank group: lane l takes entry
+    // (l % 8) * 4 + l / 8, so that lanes 8j .. 8j+7 get one of each group
+    const uint32_t pos = t * 32 + ((lane & 7) << 2) + (lane >> 3);
+    const bool has = pos < cnt;
+    uint32_t idx = 0, off = kUnstaged, len = 0;
+    if (has) {
+      idx = lds16(mA + kMetaIdx + 2 * pos);
+      off = lds16(mA + kMetaOff + 2 * pos);
+      len = lds16(mA + kMetaLen + 2 * pos);
+    }
+    bool active = has && (off != kUnstaged) && (len != 0);
+    const uint32_t tb = sBase + hp.oSlots + s * hp.slotBytes + off;
+    const uint32_t skip = active ? (tb & 15) : 0;
+    const uint32_t blk = tb - skip;
+    const uint32_t total = skip + len;
+
+    Walk<STYLE, false> wk;
+    wk.begin(pd);
+    uint32_t code = hd.initCode;
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+    if (active)
+      cur = lds128(blk);
+    uint32_t k = 0;
+
+    // a lane whose careful pass is still to come (DEFER): chunk, first byte, state there
+    bool pending = false;
+    uint32_t pk = 0, pj = 0, pc = 0;
+    // one chunk of this lane; full16: no byte of it outside the line
+    auto step = [&](auto full16) {
+      const uint32_t rem = total - k * 16;
+      const uint32_t lo = (!full16.value && (k == 0)) ? skip : 0;
+      const uint32_t hi = full16.value ? 16u : min(16u, rem);
+      const bool lastChunk = !full16.value && (rem <= 16);
+      if (!lastChunk)
+        nxt = lds128(blk + 16 * (k + 1));
+      bool stopped;
+      if (DEFER) {
+        uint32_t j = lo, cj = code;
+        stopped = (code == hx.sink) || hot_fast<full16.value>(hx, cur, lo, hi, code, j, cj);
+        if (stopped) {
+          pending = true;
+          pk = k;
+          pj = j;
+          pc = cj;
+        }
+      }
+      else
+        stopped = hot_chunk<STYLE, full16.value>(pd, hx, cur, blk + 16 * k, lo, hi, k * 16 - skip, code, wk);
+      if (stopped || lastChunk)
+        active = false;
+    };
+    const uint32_t kMin = __reduce_min_sync(kFullMask, active ? ((total + 15u) >> 4) : 0xffffffffu);
+    if (kMin != 0xffffffffu) {
+      if (active)
+        step(std::false_type());  // the head chunk
+      ++k;
+      cur = nxt;
+      // chunks 1 .. kMin-2 are whole for every lane still walking: a loop
+      // without masks or per-lane bookkeeping
+      for (; k + 1 < kMin; ++k) {
+        if (active)
+          step(std::true_type());
+        cur = nxt;
+      }
+      while (__any_sync(kFullMask, active)) {
+        if (active)
+          step(std::false_type());
+        ++k;
+        cur = nxt;
+      }
+    }
+    if (DEFER && pending) {
+      // the flagged chunk byte by byte; a walk that goes on behind it (it left
+      // the hot set and came back) takes the rest of its line on its own
+      uint32_t kk = pk;
+      uint32_t c = pc;
+      bool stopped = hot_careful<STYLE>(pd, hx, blk + 16 * kk, pj, min(16u, total - kk * 16), kk * 16 - skip, c, wk);
+      code = c;
+      while (!stopped && (total - kk * 16 > 16)) {
+        ++kk;
+        const uint4 w = lds128(blk + 16 * kk);
+        stopped = hot_chunk<STYLE, false>(pd, hx, w, blk + 16 * kk, 0, min(16u, total - kk * 16), kk * 16 - skip, code, wk);
+      }
+    }
+
+    if (has) {
+      uint32_t lineLen = len;
+      if (off == kUnstaged) {
+        // longer than a slot: from global memory, on the full table
+        const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
+        lineLen = __ldg(args.lens + line);
+        cold_bytes<STYLE>(pd, hx.wide, wk, args.text + __ldg(args.starts + line), lineLen, 0);
+        code = hx.sink;  // the state is in wk.v
+      }
+      // Walk::finish (Matcher.h:481-493), with the result ids of hot states
+      // taken from shared memory
+      int32_t now, before = 0;
+      if (code != hx.sink)
+        now = static_cast<int32_t>(lds32(hx.c2v + 1024 + 4 * code));
+      else
+        now = ((wk.v >= pd.acceptV) && (wk.v < pd.pureV)) ? __ldg(pd.results + state_index(pd, wk.v)) : 0;
+      if ((STYLE == STY_LAST) && (wk.accV != kNone))
+        before = (wk.accV & 0x80000000u) ? static_cast<int32_t>(wk.accV & 0x7fffffffu)
+                                          : __ldg(pd.results + state_index(pd, wk.accV));
+      const int32_t result = (before > 0) ? before : now;
+      const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || wk.absorbed) ? lineLen : wk.mend) : 0;
+      sts32(mA + kMetaRes + 4 * idx, static_cast<uint32_t>(result));
+      sts32(mA + kMetaEnd + 4 * idx, end);
+    }
+    // the tile that finishes a batch writes the batch's outcomes back, coalesced
+    __syncwarp();
+    const long long tc2 = hp.dbg ? clock64() : 0;
+    uint32_t last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      last = (atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaDone), 1u) == TPB - 1) ? 1 : 0;
+      __threadfence_block();
+    }
+    last = __shfl_sync(kFullMask, last, 0);
+    if (last) {
+      const uint64_t first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
+      for (uint32_t i = lane; i < cnt; i += 32) {
+        args.results[first + i] = static_cast<int32_t>(lds32(mA + kMetaRes + 4 * i));
+        if (args.matchEnds)
+          args.matchEnds[first + i] = lds32(mA + kMetaEnd + 4 * i);
+      }
+      if (lane == 0)
+        sts32(mA + kMetaDone, 0);
+      __syncwarp();
+    }
+    if (lane == 0)
+      mbar_arrive(barsAddr + 8 * (R + s));
+    if (hp.dbg) {
+      const long long tc3 = clock64();
+      tWait += tc1 - tc0;
+      tWalk += tc2 - tc1;
+      tTail += tc3 - tc2;
+      ++nTiles;
+    }
+  }
+  if (hp.dbg && (lane == 0)) {
+    atomicAdd(hp.dbg + 4, static_cast<unsigned long long>(clock64() - tStartC));
+    atomicAdd(hp.dbg + 5, tWait);
+    atomicAdd(hp.dbg + 6, tWalk);
+    atomicAdd(hp.dbg + 7, tTail);
+    atomicAdd(hp.dbg + 8, nTiles);
+  }
+}
+
+// ---- profile ----------------------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+profile_kernel(const ProgramDev pd, const uint32_t wide, const BatchArgs args, const uint64_t stride,
+               const uint32_t nStates, unsigned long long *hist, unsigned long long *lenSum) {
+  const AnyTable tab = any_table(pd, wide);
+  const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
+  const uint64_t samples = (n + stride - 1) / stride;
+  unsigned long long bytes = 0;
+  for (uint64_t sIdx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; sIdx < samples;
+       sIdx += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t line = sIdx * stride;
+    const uint8_t *p = args.text + __ldg(args.starts + line);
+    const uint32_t len = __ldg(args.lens + line);
+    bytes += len;
+    uint32_t v = pd.initV;
+    unsigned long long *h = hist;  // until the first accepting state: what an Instant walk enters
+    uint32_t initRuns = 1;         // entries into the initial state, added once per line
+    for (uint32_t i = 0; i < len; ++i) {
+      const uint32_t nv = tab.next(v, __ldg(pd.clsOffset + __ldg(p + i)));
+      if (nv != v) {
+        if ((nv == pd.initV) && (h == hist))
+          ++initRuns;
+        else
+          atomicAdd(h + state_index(pd, nv), 1ull);
+        v = nv;
+        if (v >= pd.acceptV)
+          h = hist + nStates;
+        if (v >= pd.pureV)
+          break;
+      }
+    }
+    atomicAdd(hist + state_index(pd, pd.initV), static_cast<unsigned long long>(initRuns));
+  }
+  if (bytes)
+    atomicAdd(lenSum, bytes);
+}
+
+} // anonymous
+
+cudaError_t launch_profile(const ProgramDev &pd, uint32_t wideTable, const BatchArgs &args,
+                           uint64_t stride, uint32_t nStates, unsigned long long *hist,
+                           unsigned long long *lenSum, cudaStream_t stream) {
+  if ((args.nLines == 0) || (stride == 0))
+    return cudaSuccess;
+  const uint64_t samples = (args.nLines + stride - 1) / stride;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((samples + 255) / 256, 148 * 8));
+  profile_kernel<<<grid, 256, 0, stream>>>(pd, wideTable, args, stride, nStates, hist, lenSum);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const BatchArgs &args,
+                             int style, const LaunchGeometry &geo, const HotTuning &tune,
+                             uint32_t avgLineBytes, unsigned long long *counter,
+                             cudaStream_t stream, int *launches) {
+  if ((style != STY_INSTANT) && (style != STY_LAST) && (style != STY_FULL))
+    return cudaErrorNotSupported;
+  if (args.checkLeader || args.matchStarts || !hd.table)
+    return cudaErrorNotSupported;
+  if (args.nLines == 0)
+    return cudaSuccess;
+
+  HotParams hp{};
+  uint32_t at = (hd.tableBytes + 15u) & ~15u;
+  auto take = [&](uint32_t bytes, uint32_t align) {
+    at = (at + align - 1) & ~(align - 1);
+    const uint32_t o = at;
+    at += bytes;
+    return o;
+  };
+  const uint32_t producers = std::max(1, std::min(tune.producers ? tune.producers : 3, static_cast<int>(kMaxProducers)));
+  hp.nProducers = producers;
+  hp.prodBytes = (kProdBytes + 15u) & ~15u;
+  hp.oC2v = take(2048, 16);
+  hp.oBars = take(2 * kMaxSlots * 8, 16);
+  hp.oCtl = take(32, 16);
+  hp.oProd = take(producers * hp.prodBytes, 16);
+  hp.metaBytes = (kMetaBytes + 15u) & ~15u;
+
+  // Geometry.  A batch's text has to fit a slot; the ring has to hold a tile
+  // for every consumer warp plus one batch that is being fetched
+  // (consumers <= (slots - 1) * tiles per batch: that also keeps a ticket from
+  // ever being two phases away from its slot's barrier).
+  const int maxConsumers = 32 - static_cast<int>(producers);
+  uint32_t batchLines = tune.batchLines ? static_cast<uint32_t>(tune.batchLines) : kMaxBatch;
+  batchLines = std::max(32u, std::min(batchLines, kMaxBatch)) & ~31u;
+  const uint32_t fixed = at + 256 + 256;  // alignment pad in front, slack for the slots' own alignment
+  const uint32_t room = (static_cast<uint32_t>(geo.maxSmemOptin) > fixed) ? geo.maxSmemOptin - fixed : 0;
+  uint32_t slots = 0, slotBytes = 0;
+  int warps = 0;
+  for (;;) {
+    const uint32_t tiles = batchLines / 32;
+    // a batch's text: its mean plus 1.5 sigma if line lengths scatter by a
+    // quarter of their mean (a batch that does not fit is split, see the producer)
+    const uint32_t sqrtB = (batchLines >= 256) ? 16 : (batchLines >= 128) ? 12 : (batchLines >= 64) ? 8 : 6;
+    const uint32_t need = avgLineBytes ? (avgLineBytes + 2) * batchLines + avgLineBytes * sqrtB * 3 / 8 + 64
+                                       : 108u * batchLines;
+    slotBytes = std::max(256u, std::min((need + 15u) & ~15u, 65520u));
+    if (tune.slotBytes)
+      slotBytes = std::max(256u, std::min((static_cast<uint32_t>(tune.slotBytes) + 15u) & ~15u, 65520u));
+    slots = std::min<uint32_t>(kMaxSlots, room / (slotBytes + hp.metaBytes));
+    if (tune.slots)
+      slots = std::min<uint32_t>(slots, static_cast<uint32_t>(tune.slots));
+    if (slots >= 2) {
+      if (!tune.slotBytes)  // the room that is left makes the slots longer
+        slotBytes = std::min((room / slots - hp.metaBytes) & ~15u, 65520u);
+      warps = tune.consumerWarps ? tune.consumerWarps : maxConsumers;
+      warps = std::max(1, std::min(warps, std::min(maxConsumers, static_cast<int>((slots - 1) * tiles))));
+      if ((warps >= 16) || (batchLines == 32) || tune.batchLines)
+        break;
+    }
+    if (batchLines == 32)
+      return cudaErrorNotSupported;
+    batchLines -= 32;
+  }
+  hp.dbg = tune.debug;
+  hp.nSlots = slots;
+  hp.slotBytes = slotBytes;
+  hp.batchLines = batchLines;
+  hp.tilesPerBatch = batchLines / 32;
+  hp.oMeta = take(slots * hp.metaBytes, 16);
+  hp.oSlots = take(slots * slotBytes, 128);
+  const size_t smemBytes = at + 256;  // alignment pad
+  if (smemBytes > static_cast<size_t>(geo.maxSmemOptin))
+    return cudaErrorNotSupported;
+
+  cudaError_t err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+  if (err != cudaSuccess)
+    return err;
+  // careful passes together at the end of a tile - unless the hot set leaves
+  // so much out that lanes would often go on alone behind theirs
+  const bool defer = tune.defer ? (tune.defer > 0) : (hd.coverage >= 999);
+  auto kern = (style == STY_LAST) ? batch_hot_kernel<STY_LAST, false>
+            : (style == STY_INSTANT) ? (defer ? batch_hot_kernel<STY_INSTANT, true> : batch_hot_kernel<STY_INSTANT, false>)
+                                     : (defer ? batch_hot_kernel<STY_FULL, true> : batch_hot_kernel<STY_FULL, false>);
+  err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
+  if (err != cudaSuccess)
+    return err;
+  const uint64_t blocks = (args.nLines + batchLines - 1) / batchLines;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, blocks));
+  kern<<<grid, (warps + static_cast<int>(producers)) * 32, smemBytes, stream>>>(pd, hd, args, hp, counter);
+  err = cudaGetLastError();
+  if ((err == cudaSuccess) && launches)
+    *launches += 1;
+  return err;
+}
+
+} // namespace red_b200

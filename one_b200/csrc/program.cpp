@@ -189,6 +189,7 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   for (uint32_t ii = 0; ii < n; ++ii)
     oldToNew[order[ii]] = ii;
   img.newToOld = order;
+  img.oldToNew = oldToNew;
 
   img.stateCount = n;
   img.classCount = C;
@@ -309,6 +310,94 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   img.pureV = firstPure * img.vPerState;
   img.acceptV = firstAccept * img.vPerState;
   img.absV = firstAbsorb * img.vPerState;
+}
+
+void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
+                     const uint64_t *visits, uint32_t maxHot, HotImage &hot) {
+  const uint32_t n = pp.stateCount;
+  const uint32_t C = pp.classCount;
+  maxHot = std::max(1u, std::min(maxHot, kHotMax));
+  const uint32_t firstPure = img.pureV / img.vPerState;
+  // successor in renumbered indices; pure dead ends loop to themselves, as in
+  // the full image
+  auto nextOf = [&](uint32_t idx, uint32_t byte) -> uint32_t {
+    if (idx >= firstPure)
+      return idx;
+    return img.oldToNew[pp.next[static_cast<size_t>(img.newToOld[idx]) * C + pp.equiv[byte]]];
+  };
+  // breadth-first order from the initial state
+  const uint32_t init = img.initV / img.vPerState;
+  std::vector<uint32_t> bfs;
+  std::vector<uint32_t> rank(n, 0xffffffffu);
+  bfs.reserve(n);
+  bfs.push_back(init);
+  rank[init] = 0;
+  for (size_t head = 0; head < bfs.size(); ++head) {
+    const uint32_t st = bfs[head];
+    if (st >= firstPure)
+      continue;
+    const uint32_t *row = &pp.next[static_cast<size_t>(img.newToOld[st]) * C];
+    for (uint32_t c = 0; c < C; ++c) {
+      const uint32_t nx = img.oldToNew[row[c]];
+      if (rank[nx] == 0xffffffffu) {
+        rank[nx] = static_cast<uint32_t>(bfs.size());
+        bfs.push_back(nx);
+      }
+    }
+  }
+  // the hottest states: by visits (ties and the unvisited by depth)
+  std::vector<uint32_t> cand = bfs;
+  if (visits)
+    std::stable_sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b) {
+      if ((a == init) != (b == init))
+        return a == init;
+      return visits[a] > visits[b];
+    });
+  if (visits) {
+    // what the sample never entered stays on the full table
+    size_t seen = 1;
+    while ((seen < cand.size()) && (visits[cand[seen]] > 0))
+      ++seen;
+    cand.resize(seen);
+  }
+  if (cand.size() > maxHot)
+    cand.resize(maxHot);
+  std::sort(cand.begin(), cand.end());  // codes follow the state order
+
+  if (visits) {
+    uint64_t all = 0, kept = 0;
+    for (uint32_t st = 0; st < n; ++st)
+      all += visits[st];
+    for (uint32_t st : cand)
+      kept += visits[st];
+    hot.coverage = all ? static_cast<uint32_t>(kept * 1000 / all) : 1000;
+  }
+  else
+    hot.coverage = (cand.size() == bfs.size()) ? 1000 : 0;  // no profile: unknown unless every state is hot
+  hot.nHot = static_cast<uint32_t>(cand.size());
+  hot.codeOf.assign(n, static_cast<uint8_t>(hot.nHot));
+  hot.codeToV.assign(256, 0);
+  for (uint32_t c = 0; c < hot.nHot; ++c) {
+    hot.codeOf[cand[c]] = static_cast<uint8_t>(c);
+    hot.codeToV[c] = cand[c] * img.vPerState;
+  }
+  auto below = [&](uint32_t v) {
+    const uint32_t idx = v / img.vPerState;
+    return static_cast<uint32_t>(std::lower_bound(cand.begin(), cand.end(), idx) - cand.begin());
+  };
+  hot.cAccept = below(img.acceptV);
+  hot.cAbs = below(img.absV);
+  hot.cPure = below(img.pureV);
+  hot.initCode = hot.codeOf[init];
+  const size_t bytes = (static_cast<size_t>(hot.nHot + 1) * kHotStride + 15) & ~size_t(15);
+  hot.table.assign(bytes, static_cast<uint8_t>(hot.nHot));
+  for (uint32_t c = 0; c < hot.nHot; ++c) {
+    uint8_t *row = &hot.table[static_cast<size_t>(c) * kHotStride];
+    for (uint32_t b = 0; b < 256; ++b)
+      row[b] = hot.codeOf[nextOf(cand[c], b)];
+    for (uint32_t b = 256; b < kHotStride; ++b)
+      row[b] = static_cast<uint8_t>(c);
+  }
 }
 
 } // namespace red_b200

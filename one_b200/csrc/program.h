@@ -91,6 +91,7 @@ struct DeviceImage {
   std::vector<uint32_t> table32;     // mode global
   std::vector<int32_t> results;      // by new index
   std::vector<uint32_t> newToOld;    // new index -> serialized row
+  std::vector<uint32_t> oldToNew;    // serialized row -> new index
   std::vector<uint8_t> leader;       // class space
   size_t tableBytes() const {
     return mode == kTableSmemU16 ? table16.size() * 2 : table32.size() * 4;
@@ -100,5 +101,38 @@ struct DeviceImage {
 // smemBudget: bytes of shared memory the table may take
 void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img,
                  bool allowByteRows = true);
+
+/* The hot image: what kernels_hot.cu keeps in shared memory.  Up to 255 states
+   - the ones a walk over real text spends its time in, by measured visit
+   counts where a profile exists, breadth-first from the initial state
+   otherwise - get a one-byte CODE and a row indexed by the raw byte, so that a
+   step is ONE shared-memory load:   code = T[code * kHotStride + byte].
+   Codes follow the order of the renumbered states, so the thresholds of the
+   full image carry over (code >= cAccept: accepting, ...); every transition
+   that leaves the hot set leads to the code nHot ("sink", a row of its own
+   that loops to itself), and the lane then continues on the full table.
+   kHotStride = 260 bytes: consecutive rows start one bank apart, which spreads
+   the lanes of a warp that sit in different rows over the banks (simulated on
+   the bench corpus: 1.51 wavefronts per lookup, 1.95 with stride 256).
+   Column 256 of every row holds the row's own code (a step that changes
+   nothing).  */
+constexpr uint32_t kHotStride = 260;
+constexpr uint32_t kHotMax = 255;
+
+struct HotImage {
+  uint32_t nHot = 0;              // codes 0 .. nHot-1; nHot = sink
+  uint32_t cAccept = 0;           // codes >= cAccept (and < cPure): accepting
+  uint32_t cAbs = 0;              // codes >= cAbs (and < cPure): accepting, never left
+  uint32_t cPure = 0;             // codes >= cPure (and < nHot): pure dead ends
+  uint32_t initCode = 0;
+  uint32_t coverage = 1000;       // per mille of the counted state entries that the hot set holds
+  std::vector<uint8_t> table;     // (nHot + 1) * kHotStride, padded to 16 bytes
+  std::vector<uint32_t> codeToV;  // 256 entries: v of the full image
+  std::vector<uint8_t> codeOf;    // by renumbered state index; nHot = not hot
+};
+
+// visits: per renumbered state index, or nullptr (breadth-first order then)
+void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
+                     const uint64_t *visits, uint32_t maxHot, HotImage &hot);
 
 } // namespace red_b200

@@ -5,9 +5,11 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/red_b200.h"
 #include "device_program.h"
+#include "hot.h"
 #include "program.h"
 
 struct HostPipe;
@@ -43,6 +45,18 @@ struct red_b200_program {
   HostPipe *pipe = nullptr;
   GrepPipe *grep = nullptr;   // lazily created by red_b200_grep_host
   std::atomic<long> launches{0};  // kernels launched through this program (for bench)
+  std::atomic<long> hotLaunches{0};  // of those: launches of the staged batch kernel
+
+  // the hot image of the staged batch kernel (kernels_hot.cu)
+  red_b200::HotDev hotDev[2]{};        // [0] style Instant, [1] styles Last and Full
+  red_b200::HotTuning hotTune;
+  bool hotEnabled = true;
+  uint32_t hotMaxStates = red_b200::kHotMax;
+  std::atomic<int> hotProfiled{0};    // 1: the hot set was chosen from measured visit counts
+  bool hotProfileWanted = true;
+  std::atomic<uint32_t> avgLineBytes{0};  // from the profile sample (0: unknown)
+  std::mutex hotMu;                   // guards re-profiling
+  std::vector<void *> hotBuffers;     // every device buffer a hot image ever used (freed with the program)
 };
 
 

@@ -121,6 +121,8 @@ def lib():
         L.red_b200_program_get_info.argtypes = [vp, C.POINTER(ProgramInfo)]
         L.red_b200_program_launch_count.restype = C.c_long
         L.red_b200_program_launch_count.argtypes = [vp]
+        L.red_b200_program_hot_launch_count.restype = C.c_long
+        L.red_b200_program_hot_launch_count.argtypes = [vp]
         L.red_b200_match_batch_device.argtypes = [vp, vp, vp, vp, u64, i32, i32, vp, vp, vp, vp]
         L.red_b200_match_batch_host.argtypes = [vp, vp, u64, vp, vp, u64, i32, i32, vp, vp, vp]
         L.red_b200_match.argtypes = [vp, vp, C.c_size_t, i32, i32, C.POINTER(_Outcome)]
@@ -255,6 +257,11 @@ class Program:
     @property
     def launch_count(self):
         return lib().red_b200_program_launch_count(self._h)
+
+    @property
+    def hot_launch_count(self):
+        """launches of the staged batch kernel (kernels_hot.cu) among them"""
+        return lib().red_b200_program_hot_launch_count(self._h)
 
     # -- one text -------------------------------------------------------------
 
