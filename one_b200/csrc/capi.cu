@@ -133,9 +133,9 @@ __global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, 
    breadth-first order when there are none) and puts it on the device.  Buffers
    of an earlier image stay allocated until the program is freed: kernels
    launched with them may still be running on other streams. */
-static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, HotDev &out) {
+static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bool asciiRows, HotDev &out) {
   HotImage hot;
-  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, hot);
+  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, asciiRows, hot);
   void *dTab = nullptr, *dC2v = nullptr, *dCodeOf = nullptr;
   cudaError_t err;
   if ((err = cudaMalloc(&dTab, hot.table.size())) != cudaSuccess)
@@ -160,6 +160,7 @@ static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, Ho
   hd.codeToV = static_cast<const uint32_t *>(dC2v);
   hd.codeOf = static_cast<const uint8_t *>(dCodeOf);
   hd.tableBytes = static_cast<uint32_t>(hot.table.size());
+  hd.stride = hot.stride;
   hd.nHot = hot.nHot;
   hd.cAccept = hot.cAccept;
   hd.cAbs = hot.cAbs;
@@ -188,7 +189,7 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
   }
   prog->hotProfiled.store(1);  // one attempt, whatever comes of it
   const uint32_t nStates = prog->img.stateCount;
-  const size_t words = 2 * static_cast<size_t>(nStates) + 1;
+  const size_t words = 2 * static_cast<size_t>(nStates) + 2;
   unsigned long long *dHist = nullptr;
   if (cudaMalloc(&dHist, words * 8) != cudaSuccess) {
     cudaGetLastError();
@@ -219,10 +220,15 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
   const uint64_t samples = (args.nLines + stride - 1) / stride;
   if (samples)
     prog->avgLineBytes.store(static_cast<uint32_t>(std::min<uint64_t>(visits[2 * static_cast<size_t>(nStates)] / samples, 1u << 20)));
-  if (nStates > prog->hotMaxStates) {
+  {
+    // rows of 128 columns when (nearly) all of the text is ASCII: half the
+    // shared memory for the table, more of it for text
+    const uint64_t allBytes = visits[2 * static_cast<size_t>(nStates)];
+    const uint64_t highBytes = visits[2 * static_cast<size_t>(nStates) + 1];
+    const bool ascii = prog->hotAsciiRows ? (prog->hotAsciiRows > 0) : (highBytes * 2000 <= allBytes);
     HotDev instant, whole;
-    if ((upload_hot(prog, visits.data(), instant) == cudaSuccess) &&
-        (upload_hot(prog, visits.data() + nStates, whole) == cudaSuccess)) {
+    if ((upload_hot(prog, visits.data(), ascii, instant) == cudaSuccess) &&
+        (upload_hot(prog, visits.data() + nStates, ascii, whole) == cudaSuccess)) {
       prog->hotDev[0] = instant;
       prog->hotDev[1] = whole;
     }
@@ -437,6 +443,10 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
         prog->hotTune.debug = static_cast<unsigned long long *>(dbg);
       }
     }
+  if (const char *env = getenv("RED_B200_HOT_ASCII"))
+    prog->hotAsciiRows = atoi(env);
+  if (const char *env = getenv("RED_B200_HOT_FORCE"))
+    prog->hotTune.force = atoi(env) != 0;
   if (const char *env = getenv("RED_B200_HOT_DEFER"))
     prog->hotTune.defer = atoi(env);
   if (const char *env = getenv("RED_B200_HOT_PRODUCERS"))
@@ -448,7 +458,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   if (const char *env = getenv("RED_B200_HOT_SLOT_BYTES"))
     prog->hotTune.slotBytes = atoi(env);
   if (prog->hotEnabled) {
-    if ((err = upload_hot(prog, nullptr, prog->hotDev[0])) != cudaSuccess) {
+    if ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, prog->hotDev[0])) != cudaSuccess) {
       for (void *p : prog->hotBuffers)
         cudaFree(p);
       return cleanup(err, "upload of the hot image");

@@ -12,7 +12,8 @@ namespace red_b200 {
 
 // device copy of a HotImage (program.h); all pointers are device pointers
 struct HotDev {
-  const uint8_t *table = nullptr;     // (nHot + 1) rows of kHotStride bytes
+  const uint8_t *table = nullptr;     // (nHot + 1) rows of `stride` bytes
+  uint32_t stride = 0;                // kHotStrideWide or kHotStrideAscii (program.h)
   const uint32_t *codeToV = nullptr;  // [256]
   const uint8_t *codeOf = nullptr;    // [stateCount] by renumbered state index
   uint32_t tableBytes = 0;            // multiple of 16
@@ -27,6 +28,7 @@ struct HotTuning {
   int consumerWarps = 0;   // 0 = pick (all the warps the ring can feed)
   int producers = 0;       // 0 = pick (3)
   int defer = 0;           // careful passes at the end of a tile: 0 = pick, 1 = yes, -1 = no
+  bool force = false;      // take this kernel even when the hot set leaves out states the profile saw
   int slots = 0;           // 0 = pick (as many as fit)
   int batchLines = 0;      // 0 = pick (256); a multiple of 32, <= 256
   int slotBytes = 0;       // 0 = pick
@@ -47,7 +49,8 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
    the hot set pays per excursion, not per byte): hist[index] up to and
    including the first accepting state of a line - what an Instant walk sees -
    and hist[nStates + index] behind it.  hist: zeroed device array of
-   2 * nStates u64; lenSum (device u64, zeroed): the sampled lines' total length. */
+   2 * nStates u64; lenSum (two device u64, zeroed): the sampled lines' total
+   length and how many of their bytes are >= 128. */
 cudaError_t launch_profile(const ProgramDev &pd, uint32_t wideTable, const BatchArgs &args,
                            uint64_t stride, uint32_t nStates, unsigned long long *hist,
                            unsigned long long *lenSum, cudaStream_t stream);

@@ -46,14 +46,14 @@ using namespace dev;
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr uint32_t kMaxBatch = 256;       // lines per batch (and per claimed sub-block)
-constexpr uint32_t kSortBuckets = 256;    // chunks a lane walks (32) x 16-byte bank group of the line's start (8)
+constexpr uint32_t kSortBuckets = 32;     // by the number of 16-byte chunks a lane walks
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
 constexpr uint32_t kMaxSlots = 12;
 constexpr uint32_t kMaxProducers = 4;
 
 struct HotParams {
   // byte offsets into dynamic shared memory (behind its 256-byte alignment)
-  uint32_t oC2v, oBars, oCtl, oProd, oMeta, oSlots;
+  uint32_t oC2v, oBars, oCtl, oProd, oDeal, oMeta, oSlots;
   uint32_t nSlots, slotBytes, batchLines, tilesPerBatch, metaBytes, nProducers, prodBytes;
   unsigned long long *dbg;  // null, or 16 cycle counters (HotTuning::debug)
 };
@@ -218,11 +218,13 @@ struct HotCtx {
 
 // hx.tab has a zero low byte, so PRMT puts a text byte and the table base
 // together in one instruction: a step is PRMT, IMAD, LDS.U8
+template <int STRIDE>
 __device__ __forceinline__ uint32_t hot_next(const HotCtx &hx, uint32_t c, uint32_t word, int jj) {
-  return lds8(c * kHotStride + __byte_perm(word, hx.tab, 0x7650 | jj));
+  return lds8(c * STRIDE + __byte_perm(word, hx.tab, 0x7650 | jj));
 }
+template <int STRIDE>
 __device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, uint32_t byte) {
-  return lds8(c * kHotStride + hx.tab + byte);
+  return lds8(c * STRIDE + hx.tab + byte);
 }
 
 /* The fast pass over one aligned 16-byte chunk of one line per lane: no
@@ -231,7 +233,7 @@ __device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, 
    all do.  Returns false when no code reached hx.cLimit (code is then the
    state behind the chunk); true when one did: (j, cj) is where the careful
    pass has to start, code is unchanged. */
-template <bool FULL16>
+template <bool FULL16, int STRIDE>
 __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const uint32_t lo, const uint32_t hi,
                                          uint32_t &code, uint32_t &j, uint32_t &cj) {
   uint32_t c = code;
@@ -247,7 +249,7 @@ __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const
       // a byte outside the line: no lookup at all (a predicated load), the
       // lane's lookups would only collide with the others' in the banks
       if (FULL16 || (mask & (1u << (4 * q + jj))))
-        c = hot_next(hx, c, word, jj);
+        c = hot_next<STRIDE>(hx, c, word, jj);
       m = max(m, c);
     }
     if (q == 0) { mq0 = m; cp0 = c; }
@@ -255,13 +257,20 @@ __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const
     if (q == 2) { mq2 = m; cp2 = c; }
     if (q == 3) { mq3 = m; }
   }
-  if (max(max(mq0, mq1), max(mq2, mq3)) < hx.cLimit) {
+  // rows of 128 columns: a byte >= 128 anywhere in the chunk and the lookups
+  // above mean nothing (they stayed inside shared memory: codes are bytes)
+  const bool high = (STRIDE == static_cast<int>(kHotStrideAscii)) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0);
+  if (!high && (max(max(mq0, mq1), max(mq2, mq3)) < hx.cLimit)) {
     code = c;
     return false;
   }
   // the careful pass starts at the first flagged quarter
   j = 0;
   cj = code;
+  if (high) {
+    j = lo;
+    return true;
+  }
   if (mq0 < hx.cLimit) {
     j = 4; cj = cp0;
     if (mq1 < hx.cLimit) {
@@ -278,7 +287,7 @@ __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const
    table while it is not (First/Tangent are not walked here: the limit never
    changes).  c: the state in front of byte j in, behind the last byte taken
    out (hx.sink: it is in wk.v).  Returns true when the walk is over. */
-template <int STYLE>
+template <int STYLE, int STRIDE>
 __device__ __forceinline__ bool hot_careful(const ProgramDev &pd, const HotCtx &hx, const uint32_t chunkAddr,
                                             uint32_t j, const uint32_t hi, const uint32_t pos0,
                                             uint32_t &c, Walk<STYLE, false> &wk) {
@@ -295,7 +304,8 @@ __device__ __forceinline__ bool hot_careful(const ProgramDev &pd, const HotCtx &
         c = hx.codeOf[state_index(pd, wk.v)];
     }
     else {
-      const uint32_t nc = hot_next_byte(hx, c, byte);
+      const uint32_t nc = ((STRIDE == static_cast<int>(kHotStrideAscii)) && (byte >= 128))
+          ? hx.sink : hot_next_byte<STRIDE>(hx, c, byte);
       if (nc >= hx.cLimit) {
         if (nc == hx.sink) {
           // leaves the hot set: this byte again, on the full table
@@ -330,14 +340,14 @@ __device__ __forceinline__ bool hot_careful(const ProgramDev &pd, const HotCtx &
 }
 
 // fast pass, and the careful pass right behind it where it is needed
-template <int STYLE, bool FULL16>
+template <int STYLE, bool FULL16, int STRIDE>
 __device__ __forceinline__ bool hot_chunk(const ProgramDev &pd, const HotCtx &hx, const uint4 &w,
                                           const uint32_t chunkAddr, const uint32_t lo, const uint32_t hi,
                                           const uint32_t pos0, uint32_t &code, Walk<STYLE, false> &wk) {
   uint32_t j = lo, cj = code;
-  if ((code != hx.sink) && !hot_fast<FULL16>(hx, w, lo, hi, code, j, cj))
+  if ((code != hx.sink) && !hot_fast<FULL16, STRIDE>(hx, w, lo, hi, code, j, cj))
     return false;
-  const bool stopped = hot_careful<STYLE>(pd, hx, chunkAddr, j, hi, pos0, cj, wk);
+  const bool stopped = hot_careful<STYLE, STRIDE>(pd, hx, chunkAddr, j, hi, pos0, cj, wk);
   code = cj;
   return stopped;
 }
@@ -346,7 +356,7 @@ __device__ __forceinline__ bool hot_chunk(const ProgramDev &pd, const HotCtx &hx
    Instant, Full): a lane whose chunk was flagged steps aside, and the careful
    passes of a tile's flagged lanes run together once the tile is through,
    instead of one after the other with the rest of the warp waiting. */
-template <int STYLE, bool DEFER>
+template <int STYLE, bool DEFER, int STRIDE>
 __global__ void __launch_bounds__(1024, 1)
 batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, const HotParams hp,
                  unsigned long long *blockCounter) {
@@ -439,52 +449,33 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       return s;
     };
     /* The sort key of a line at slot offset off: the number of 16-byte chunks
-       a lane walks (lanes of a tile are in step), then the 16-byte bank group
-       its text starts in - the consumers deal a tile's entries out so that the
-       eight lanes that share a phase of an LDS.128 come from eight different
-       groups where the batch has them (see the consumers' `pos`). */
+       a lane walks (the lanes of a tile are in step), longest first: the tile
+       that takes longest is then the first to be claimed, and the slot is not
+       held up by a late starter. */
     auto bucketOf = [](uint32_t off, uint32_t len) -> uint32_t {
       const uint32_t chunks = ((off != kUnstaged) && (len != 0)) ? min(31u, ((off & 15) + len + 15u) >> 4) : 0;
-      // longest first: the tile that takes longest is then the first to be
-      // claimed, and the slot is not held up by a late starter
-      return (31 - chunks) * 8 + ((off >> 4) & 7);
+      return 31 - chunks;
     };
     // counting sort: bucket[] in, position in the sorted order out
     auto sortPositions = [&](const uint32_t (&bucket)[kPer], const bool (&valid)[kPer], uint32_t (&pos)[kPer]) {
-      const uint32_t mineA = histA + 32 * lane;  // this lane's eight counters
-      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(mineA), "r"(0) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(mineA + 16), "r"(0) : "memory");
+      sts32(histA + 4 * lane, 0);
       __syncwarp();
 #pragma unroll
       for (uint32_t k = 0; k < kPer; ++k)
         pos[k] = valid[k] ? atomicAdd(sHist + bucket[k], 1u) : 0;
       __syncwarp();
-      const uint4 c0 = lds128(mineA), c1 = lds128(mineA + 16);
-      const uint32_t sum = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
-      uint32_t incl = sum;
+      const uint32_t mine = lds32(histA + 4 * lane);
+      uint32_t incl = mine;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t up = __shfl_up_sync(kFullMask, incl, d);
         if (lane >= static_cast<uint32_t>(d))
           incl += up;
       }
-      uint4 e0, e1;
-      e0.x = incl - sum;
-      e0.y = e0.x + c0.x;
-      e0.z = e0.y + c0.y;
-      e0.w = e0.z + c0.z;
-      e1.x = e0.w + c0.w;
-      e1.y = e1.x + c1.x;
-      e1.z = e1.y + c1.y;
-      e1.w = e1.z + c1.z;
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mineA), "r"(e0.x), "r"(e0.y), "r"(e0.z), "r"(e0.w) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mineA + 16), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w) : "memory");
-      __syncwarp();
+      const uint32_t excl = incl - mine;
 #pragma unroll
       for (uint32_t k = 0; k < kPer; ++k)
-        if (valid[k])
-          pos[k] += lds32(histA + 4 * bucket[k]);
-      __syncwarp();
+        pos[k] += __shfl_sync(kFullMask, excl, bucket[k]);
     };
     auto finishBatch = [&](uint32_t s, uint64_t first, uint32_t count) {
       if (lane == 0) {
@@ -759,94 +750,179 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           break;
         }
       }
+      __nanosleep(20);  // (a spinning warp takes issue slots from the walkers)
     }
     if (ended)
       break;
     const long long tc1 = hp.dbg ? clock64() : 0;
     const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
     const uint32_t cnt = lds32(mA + kMetaCnt);
-    // entries of a tile are sorted by bank group: lane l takes entry
-    // (l % 8) * 4 + l / 8, so that lanes 8j .. 8j+7 get one of each group
-    const uint32_t pos = t * 32 + ((lane & 7) << 2) + (lane >> 3);
-    const bool has = pos < cnt;
+    const uint32_t pos = t * 32 + lane;
+    bool has = pos < cnt;
     uint32_t idx = 0, off = kUnstaged, len = 0;
     if (has) {
       idx = lds16(mA + kMetaIdx + 2 * pos);
       off = lds16(mA + kMetaOff + 2 * pos);
       len = lds16(mA + kMetaLen + 2 * pos);
     }
-    bool active = has && (off != kUnstaged) && (len != 0);
-    const uint32_t tb = sBase + hp.oSlots + s * hp.slotBytes + off;
-    const uint32_t skip = active ? (tb & 15) : 0;
-    const uint32_t blk = tb - skip;
-    const uint32_t total = skip + len;
-
+    /* Deal the tile's lines out to the lanes by the 16-byte bank group their
+       text starts in (every chunk of a line is then in step with its first):
+       an LDS.128 is served eight lanes at a time, and eight lanes that read
+       from eight different groups cost one wavefront (measured with the lines
+       as they come: 10 wavefronts per instruction; 4 is the floor).  The
+       lines are ranked by group; rank r goes to lane (r % 4) * 8 + r / 4, so
+       every run of eight lanes gets every fourth line of that order. */
+    {
+      const uint32_t g = (off >> 4) & 7;  // (no line: 7, sorts last)
+      uint32_t r = 0;
+#pragma unroll
+      for (uint32_t v = 0; v < 8; ++v) {
+        const unsigned m = __ballot_sync(kFullMask, g == v);
+        if (v < g)
+          r += __popc(m);
+        if (v == g)
+          r += __popc(m & ((1u << lane) - 1));
+      }
+      const uint32_t to = ((r & 3) << 3) | (r >> 2);
+      const uint32_t dealA = sBase + hp.oDeal + 32 * warp;
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(dealA + to), "r"(lane) : "memory");
+      __syncwarp();
+      const uint32_t src = lds8(dealA + lane);
+      __syncwarp();
+      idx = __shfl_sync(kFullMask, idx, src);
+      off = __shfl_sync(kFullMask, off, src);
+      len = __shfl_sync(kFullMask, len, src);
+      has = __shfl_sync(kFullMask, has ? 1u : 0u, src) != 0;
+    }
+    // what the lane keeps of its line while it walks: where it was dealt from
+    // (idx, off and len are fetched again when the walk is over)
+    const uint32_t slotA = sBase + hp.oSlots + s * hp.slotBytes;
     Walk<STYLE, false> wk;
-    wk.begin(pd);
     uint32_t code = hd.initCode;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-    if (active)
-      cur = lds128(blk);
-    uint32_t k = 0;
+    bool done = false;  // the outcome is in wk (the walk stopped, or it went on the full table)
 
-    // a lane whose careful pass is still to come (DEFER): chunk, first byte, state there
-    bool pending = false;
-    uint32_t pk = 0, pj = 0, pc = 0;
-    // one chunk of this lane; full16: no byte of it outside the line
-    auto step = [&](auto full16) {
-      const uint32_t rem = total - k * 16;
-      const uint32_t lo = (!full16.value && (k == 0)) ? skip : 0;
-      const uint32_t hi = full16.value ? 16u : min(16u, rem);
-      const bool lastChunk = !full16.value && (rem <= 16);
-      if (!lastChunk)
-        nxt = lds128(blk + 16 * (k + 1));
-      bool stopped;
-      if (DEFER) {
-        uint32_t j = lo, cj = code;
-        stopped = (code == hx.sink) || hot_fast<full16.value>(hx, cur, lo, hi, code, j, cj);
-        if (stopped) {
-          pending = true;
-          pk = k;
+    if (DEFER) {
+      /* Lean walk for the styles that end at the first state that needs a
+         decision.  Live per lane: the address of the current chunk, the bytes
+         left from there to the end of the line, the state; a flagged lane
+         freezes them (plus the byte its careful pass starts at) and steps
+         aside.  A chunk is loaded right before it is walked: the other warps
+         cover that latency, and there is no second chunk to keep. */
+      bool active = has && (off != kUnstaged) && (len != 0);
+      uint32_t addr = (slotA + off) & ~15u;
+      uint32_t rem = active ? ((slotA + off) & 15u) + len : 0;   // bytes from addr to the line's end
+      uint32_t pj = 0xffu;                                        // flagged: first byte of the careful pass
+      const uint32_t nCh = (rem + 15u) >> 4;
+      const uint32_t kMin = __reduce_min_sync(kFullMask, active ? nCh : 0xffffffffu);
+      if (active) {
+        // the head chunk
+        const uint4 w = lds128(addr);
+        uint32_t j = 0, cj = 0;
+        if (hot_fast<false, STRIDE>(hx, w, (slotA + off) & 15u, min(16u, rem), code, j, cj)) {
           pj = j;
-          pc = cj;
+          code = cj;
+          active = false;
+        }
+        else if (rem <= 16)
+          active = false;
+        else {
+          addr += 16;
+          rem -= 16;
         }
       }
-      else
-        stopped = hot_chunk<STYLE, full16.value>(pd, hx, cur, blk + 16 * k, lo, hi, k * 16 - skip, code, wk);
-      if (stopped || lastChunk)
-        active = false;
-    };
-    const uint32_t kMin = __reduce_min_sync(kFullMask, active ? ((total + 15u) >> 4) : 0xffffffffu);
-    if (kMin != 0xffffffffu) {
-      if (active)
-        step(std::false_type());  // the head chunk
-      ++k;
-      cur = nxt;
-      // chunks 1 .. kMin-2 are whole for every lane still walking: a loop
-      // without masks or per-lane bookkeeping
-      for (; k + 1 < kMin; ++k) {
-        if (active)
-          step(std::true_type());
-        cur = nxt;
+      if (kMin != 0xffffffffu) {
+        // chunks 1 .. kMin-2 are whole for every lane still walking
+        for (uint32_t k = 1; k + 1 < kMin; ++k) {
+          if (active) {
+            const uint4 w = lds128(addr);
+            uint32_t j = 0, cj = 0;
+            if (hot_fast<true, STRIDE>(hx, w, 0, 16, code, j, cj)) {
+              pj = j;
+              code = cj;
+              active = false;
+            }
+            else {
+              addr += 16;
+              rem -= 16;
+            }
+          }
+        }
       }
       while (__any_sync(kFullMask, active)) {
-        if (active)
-          step(std::false_type());
-        ++k;
-        cur = nxt;
+        if (active) {
+          const uint4 w = lds128(addr);
+          uint32_t j = 0, cj = 0;
+          if (hot_fast<false, STRIDE>(hx, w, 0, min(16u, rem), code, j, cj)) {
+            pj = j;
+            code = cj;
+            active = false;
+          }
+          else if (rem <= 16)
+            active = false;
+          else {
+            addr += 16;
+            rem -= 16;
+          }
+        }
+      }
+      if (pj != 0xffu) {
+        // the flagged chunk byte by byte; a walk that goes on behind it (it left
+        // the hot set and came back) takes the rest of its line on its own
+        wk.begin(pd);
+        const uint32_t tb = slotA + off;
+        bool stopped = hot_careful<STYLE, STRIDE>(pd, hx, addr, pj, min(16u, rem), addr - tb, code, wk);
+        while (!stopped && (rem > 16)) {
+          addr += 16;
+          rem -= 16;
+          const uint4 w = lds128(addr);
+          stopped = hot_chunk<STYLE, false, STRIDE>(pd, hx, w, addr, 0, min(16u, rem), addr - tb, code, wk);
+        }
+        done = true;
       }
     }
-    if (DEFER && pending) {
-      // the flagged chunk byte by byte; a walk that goes on behind it (it left
-      // the hot set and came back) takes the rest of its line on its own
-      uint32_t kk = pk;
-      uint32_t c = pc;
-      bool stopped = hot_careful<STYLE>(pd, hx, blk + 16 * kk, pj, min(16u, total - kk * 16), kk * 16 - skip, c, wk);
-      code = c;
-      while (!stopped && (total - kk * 16 > 16)) {
-        ++kk;
-        const uint4 w = lds128(blk + 16 * kk);
-        stopped = hot_chunk<STYLE, false>(pd, hx, w, blk + 16 * kk, 0, min(16u, total - kk * 16), kk * 16 - skip, code, wk);
+    else {
+      bool active = has && (off != kUnstaged) && (len != 0);
+      const uint32_t tb = slotA + off;
+      const uint32_t skip = active ? (tb & 15) : 0;
+      const uint32_t blk = tb - skip;
+      const uint32_t total = skip + len;
+      wk.begin(pd);
+      done = true;
+      uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+      if (active)
+        cur = lds128(blk);
+      uint32_t k = 0;
+      // one chunk of this lane; full16: no byte of it outside the line
+      auto step = [&](auto full16) {
+        const uint32_t rem = total - k * 16;
+        const uint32_t lo = (!full16.value && (k == 0)) ? skip : 0;
+        const uint32_t hi = full16.value ? 16u : min(16u, rem);
+        const bool lastChunk = !full16.value && (rem <= 16);
+        if (!lastChunk)
+          nxt = lds128(blk + 16 * (k + 1));
+        const bool stopped = hot_chunk<STYLE, full16.value, STRIDE>(pd, hx, cur, blk + 16 * k, lo, hi, k * 16 - skip, code, wk);
+        if (stopped || lastChunk)
+          active = false;
+      };
+      const uint32_t kMin = __reduce_min_sync(kFullMask, active ? ((total + 15u) >> 4) : 0xffffffffu);
+      if (kMin != 0xffffffffu) {
+        if (active)
+          step(std::false_type());  // the head chunk
+        ++k;
+        cur = nxt;
+        // chunks 1 .. kMin-2 are whole for every lane still walking: a loop
+        // without masks or per-lane bookkeeping
+        for (; k + 1 < kMin; ++k) {
+          if (active)
+            step(std::true_type());
+          cur = nxt;
+        }
+        while (__any_sync(kFullMask, active)) {
+          if (active)
+            step(std::false_type());
+          ++k;
+          cur = nxt;
+        }
       }
     }
 
@@ -856,6 +932,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         // longer than a slot: from global memory, on the full table
         const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
         lineLen = __ldg(args.lens + line);
+        wk.begin(pd);
+        done = true;
         cold_bytes<STYLE>(pd, hx.wide, wk, args.text + __ldg(args.starts + line), lineLen, 0);
         code = hx.sink;  // the state is in wk.v
       }
@@ -870,7 +948,10 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         before = (wk.accV & 0x80000000u) ? static_cast<int32_t>(wk.accV & 0x7fffffffu)
                                           : __ldg(pd.results + state_index(pd, wk.accV));
       const int32_t result = (before > 0) ? before : now;
-      const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || wk.absorbed) ? lineLen : wk.mend) : 0;
+      // (a walk that ran out without a decision has no accepting position to report)
+      const bool absorbed = done && wk.absorbed;
+      const uint32_t mend = done ? wk.mend : 0;
+      const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || absorbed) ? lineLen : mend) : 0;
       sts32(mA + kMetaRes + 4 * idx, static_cast<uint32_t>(result));
       sts32(mA + kMetaEnd + 4 * idx, end);
     }
@@ -922,7 +1003,7 @@ profile_kernel(const ProgramDev pd, const uint32_t wide, const BatchArgs args, c
   const AnyTable tab = any_table(pd, wide);
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   const uint64_t samples = (n + stride - 1) / stride;
-  unsigned long long bytes = 0;
+  unsigned long long bytes = 0, highBytes = 0;
   for (uint64_t sIdx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; sIdx < samples;
        sIdx += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t line = sIdx * stride;
@@ -933,7 +1014,9 @@ profile_kernel(const ProgramDev pd, const uint32_t wide, const BatchArgs args, c
     unsigned long long *h = hist;  // until the first accepting state: what an Instant walk enters
     uint32_t initRuns = 1;         // entries into the initial state, added once per line
     for (uint32_t i = 0; i < len; ++i) {
-      const uint32_t nv = tab.next(v, __ldg(pd.clsOffset + __ldg(p + i)));
+      const uint32_t byte = __ldg(p + i);
+      highBytes += byte >> 7;
+      const uint32_t nv = tab.next(v, __ldg(pd.clsOffset + byte));
       if (nv != v) {
         if ((nv == pd.initV) && (h == hist))
           ++initRuns;
@@ -950,6 +1033,8 @@ profile_kernel(const ProgramDev pd, const uint32_t wide, const BatchArgs args, c
   }
   if (bytes)
     atomicAdd(lenSum, bytes);
+  if (highBytes)
+    atomicAdd(lenSum + 1, highBytes);
 }
 
 } // anonymous
@@ -973,6 +1058,13 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
     return cudaErrorNotSupported;
   if (args.checkLeader || args.matchStarts || !hd.table)
     return cudaErrorNotSupported;
+  // A lane that leaves the hot set walks on the full table in global memory,
+  // a byte per L2 round trip, with its warp waiting: with more than the odd
+  // excursion the other kernels are faster (measured on union64, styles Last
+  // and Full, where a line's walk goes on behind its match and enters more
+  // states than the hot set holds: 560-700 GB/s against 1500-1650).
+  if ((hd.coverage < 999) && !tune.force)
+    return cudaErrorNotSupported;
   if (args.nLines == 0)
     return cudaSuccess;
 
@@ -991,6 +1083,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   hp.oBars = take(2 * kMaxSlots * 8, 16);
   hp.oCtl = take(32, 16);
   hp.oProd = take(producers * hp.prodBytes, 16);
+  hp.oDeal = take(32 * 32, 16);
   hp.metaBytes = (kMetaBytes + 15u) & ~15u;
 
   // Geometry.  A batch's text has to fit a slot; the ring has to hold a tile
@@ -1046,9 +1139,15 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   // careful passes together at the end of a tile - unless the hot set leaves
   // so much out that lanes would often go on alone behind theirs
   const bool defer = tune.defer ? (tune.defer > 0) : (hd.coverage >= 999);
-  auto kern = (style == STY_LAST) ? batch_hot_kernel<STY_LAST, false>
-            : (style == STY_INSTANT) ? (defer ? batch_hot_kernel<STY_INSTANT, true> : batch_hot_kernel<STY_INSTANT, false>)
-                                     : (defer ? batch_hot_kernel<STY_FULL, true> : batch_hot_kernel<STY_FULL, false>);
+  constexpr int W = kHotStrideWide, A = kHotStrideAscii;
+  const bool ascii = hd.stride == kHotStrideAscii;
+  auto kern = (style == STY_LAST)
+      ? (ascii ? batch_hot_kernel<STY_LAST, false, A> : batch_hot_kernel<STY_LAST, false, W>)
+      : (style == STY_INSTANT)
+          ? (defer ? (ascii ? batch_hot_kernel<STY_INSTANT, true, A> : batch_hot_kernel<STY_INSTANT, true, W>)
+                   : (ascii ? batch_hot_kernel<STY_INSTANT, false, A> : batch_hot_kernel<STY_INSTANT, false, W>))
+          : (defer ? (ascii ? batch_hot_kernel<STY_FULL, true, A> : batch_hot_kernel<STY_FULL, true, W>)
+                   : (ascii ? batch_hot_kernel<STY_FULL, false, A> : batch_hot_kernel<STY_FULL, false, W>));
   err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
   if (err != cudaSuccess)
     return err;

@@ -313,7 +313,7 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
 }
 
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
-                     const uint64_t *visits, uint32_t maxHot, HotImage &hot) {
+                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, HotImage &hot) {
   const uint32_t n = pp.stateCount;
   const uint32_t C = pp.classCount;
   maxHot = std::max(1u, std::min(maxHot, kHotMax));
@@ -389,14 +389,14 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
   hot.cAbs = below(img.absV);
   hot.cPure = below(img.pureV);
   hot.initCode = hot.codeOf[init];
-  const size_t bytes = (static_cast<size_t>(hot.nHot + 1) * kHotStride + 15) & ~size_t(15);
+  hot.stride = asciiRows ? kHotStrideAscii : kHotStrideWide;
+  const uint32_t columns = hot.stride - 4;
+  const size_t bytes = (static_cast<size_t>(hot.nHot + 1) * hot.stride + 15) & ~size_t(15);
   hot.table.assign(bytes, static_cast<uint8_t>(hot.nHot));
   for (uint32_t c = 0; c < hot.nHot; ++c) {
-    uint8_t *row = &hot.table[static_cast<size_t>(c) * kHotStride];
-    for (uint32_t b = 0; b < 256; ++b)
+    uint8_t *row = &hot.table[static_cast<size_t>(c) * hot.stride];
+    for (uint32_t b = 0; b < columns; ++b)
       row[b] = hot.codeOf[nextOf(cand[c], b)];
-    for (uint32_t b = 256; b < kHotStride; ++b)
-      row[b] = static_cast<uint8_t>(c);
   }
 }
 

@@ -111,12 +111,14 @@ void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img,
    full image carry over (code >= cAccept: accepting, ...); every transition
    that leaves the hot set leads to the code nHot ("sink", a row of its own
    that loops to itself), and the lane then continues on the full table.
-   kHotStride = 260 bytes: consecutive rows start one bank apart, which spreads
-   the lanes of a warp that sit in different rows over the banks (simulated on
-   the bench corpus: 1.51 wavefronts per lookup, 1.95 with stride 256).
-   Column 256 of every row holds the row's own code (a step that changes
-   nothing).  */
-constexpr uint32_t kHotStride = 260;
+   A row is 256 entries + 4 bytes (kHotStrideWide), or - for text that is
+   ASCII, which the profile tells - 128 entries + 4 bytes (kHotStrideAscii: a
+   byte >= 128 then counts as leaving the hot set, and half the shared memory
+   is free for text).  The 4 bytes make consecutive rows start one bank apart,
+   which spreads the lanes of a warp that sit in different rows over the banks
+   (simulated on the bench corpus: 1.5 wavefronts per lookup, 2.0 without). */
+constexpr uint32_t kHotStrideWide = 260;
+constexpr uint32_t kHotStrideAscii = 132;
 constexpr uint32_t kHotMax = 255;
 
 struct HotImage {
@@ -125,14 +127,15 @@ struct HotImage {
   uint32_t cAbs = 0;              // codes >= cAbs (and < cPure): accepting, never left
   uint32_t cPure = 0;             // codes >= cPure (and < nHot): pure dead ends
   uint32_t initCode = 0;
+  uint32_t stride = kHotStrideWide; // bytes per row
   uint32_t coverage = 1000;       // per mille of the counted state entries that the hot set holds
-  std::vector<uint8_t> table;     // (nHot + 1) * kHotStride, padded to 16 bytes
+  std::vector<uint8_t> table;     // (nHot + 1) * stride, padded to 16 bytes
   std::vector<uint32_t> codeToV;  // 256 entries: v of the full image
   std::vector<uint8_t> codeOf;    // by renumbered state index; nHot = not hot
 };
 
 // visits: per renumbered state index, or nullptr (breadth-first order then)
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
-                     const uint64_t *visits, uint32_t maxHot, HotImage &hot);
+                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, HotImage &hot);
 
 } // namespace red_b200

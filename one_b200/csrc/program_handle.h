@@ -54,6 +54,7 @@ struct red_b200_program {
   uint32_t hotMaxStates = red_b200::kHotMax;
   std::atomic<int> hotProfiled{0};    // 1: the hot set was chosen from measured visit counts
   bool hotProfileWanted = true;
+  int hotAsciiRows = 0;               // rows of 128 columns: 0 = by the profile, 1 = always, -1 = never
   std::atomic<uint32_t> avgLineBytes{0};  // from the profile sample (0: unknown)
   std::mutex hotMu;                   // guards re-profiling
   std::vector<void *> hotBuffers;     // every device buffer a hot image ever used (freed with the program)

@@ -13,12 +13,13 @@ pytestmark = pytest.mark.gpu
 
 STYLES = ["instant", "last", "full"]
 KNOBS = ["RED_B200_HOT", "RED_B200_HOT_STATES", "RED_B200_HOT_PROFILE", "RED_B200_HOT_WARPS",
-         "RED_B200_HOT_SLOTS", "RED_B200_HOT_BATCH", "RED_B200_HOT_SLOT_BYTES", "RED_B200_HOT_PRODUCERS", "RED_B200_HOT_DEFER"]
+         "RED_B200_HOT_SLOTS", "RED_B200_HOT_BATCH", "RED_B200_HOT_SLOT_BYTES", "RED_B200_HOT_PRODUCERS", "RED_B200_HOT_DEFER", "RED_B200_HOT_ASCII", "RED_B200_HOT_FORCE"]
 
 
 def program(gpu_red, monkeypatch, blob, **knobs):
     for k in KNOBS:
         monkeypatch.delenv(k, raising=False)
+    knobs.setdefault("force", 1)  # this kernel, also where the launcher would rather take another
     for k, v in knobs.items():
         monkeypatch.setenv("RED_B200_HOT_" + k.upper() if k != "hot" else "RED_B200_HOT", str(v))
     prog = gpu_red.Program(blob)
@@ -88,7 +89,7 @@ def test_small_hot_set_takes_the_full_table(gpu_red, vectors, oracle_cls, monkey
                                    dict(warps=16, batch=64, producers=4), dict(slots=8, batch=32, warps=4),
                                    dict(slot_bytes=4096, producers=2), dict(slot_bytes=1024, warps=12),
                                    dict(slots=2, producers=4), dict(batch=224, producers=1),
-                                   dict(defer=-1), dict(defer=1, batch=96)])
+                                   dict(defer=-1), dict(defer=1, batch=96), dict(ascii=-1), dict(ascii=1, profile=0)])
 def test_launch_shapes(gpu_red, vectors, oracle_cls, monkeypatch, knobs):
     """Other ring geometries; slots smaller than a batch's text make the producer
     split batches and gather line by line."""
@@ -193,3 +194,25 @@ def test_device_resident_batch(gpu_red, vectors, oracle_cls, monkeypatch):
             assert np.array_equal(res.cpu().numpy(), eres), (shift, sty)
             assert np.array_equal(me.cpu().numpy().view(np.uint32), eme), (shift, sty)
     prog.close()
+
+
+def test_bytes_above_127(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Text that is not ASCII: with rows of 128 columns (forced here, and chosen
+    or not by the profile) a byte >= 128 takes the lane to the full table."""
+    from one_b200 import synth
+    rng = np.random.RandomState(4)
+    lines = synth.make_lines(20000, seed=8)
+    for i in range(0, len(lines), 3):
+        ln = bytearray(lines[i])
+        for _ in range(rng.randint(1, 6)):
+            ln[rng.randint(0, len(ln))] = rng.randint(128, 256)
+        lines[i] = bytes(ln)
+    lines[7] = bytes(rng.randint(128, 256, 300).astype(np.uint8))
+    text, starts, lens = synth.pack_lines(lines)
+    for name in ("union64", "single_auto"):
+        blob = blob_of(vectors, name)
+        orc = oracle_cls(blob)
+        for knobs in (dict(ascii=1), dict(ascii=1, defer=1), dict(), dict(ascii=1, profile=0, states=20)):
+            prog = program(gpu_red, monkeypatch, blob, **knobs)
+            agree(prog, orc, text, starts, lens, what=(name, knobs))
+            prog.close()
