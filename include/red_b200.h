@@ -157,8 +157,14 @@ int red_b200_match_batch_device(const red_b200_program *prog,
                                 uint32_t *d_match_ends,
                                 void *stream);
 
-/* Same with host buffers: text and index go to the GPU, results come back;
-   copies are chunked and overlapped with the kernels.  Synchronous. */
+/* Same with host buffers: text and index go to the GPU, results come back, in
+   chunks through three slots so that the copies of one chunk overlap the
+   kernels of another.  That overlap needs PINNED host buffers (cudaHostAlloc /
+   cudaHostRegister, torch pin_memory): from pageable memory the CUDA runtime
+   stages every copy itself and a device-to-host copy returns only when it is
+   done, so the chunks then run one after the other - correct, but at about the
+   speed of the slowest copy.  Synchronous; on an error nothing is left in
+   flight. */
 int red_b200_match_batch_host(const red_b200_program *prog,
                               const uint8_t *text, uint64_t text_len,
                               const uint64_t *starts, const uint32_t *lens,
@@ -244,7 +250,8 @@ int red_b200_replace(const red_b200_program *prog, const void *text, size_t len,
 /* The reference's StatefulMatcher (include/Matcher.h:770-794) keeps one DFA
    state and is fed byte by byte.  Here the caller keeps the state - an opaque
    u32 per stream, valid only with the program that produced it - and feeds a
-   SEGMENT per stream per call; RED_B200_STATE_FRESH starts a new matcher.
+   SEGMENT per stream per call; RED_B200_STATE_FRESH (like any value that is
+   not a state of this program) starts a new matcher.
    d_results[i] is result() after the segment (for an empty segment: of the
    state as it is).  Optional: d_hit_results[i] / d_hit_ends[i], the result at
    and the offset one past the last accepting position inside the segment
@@ -303,7 +310,9 @@ typedef struct {
    goes in and only these records come out.  *n_lines gets the number of lines
    seen.  RED_B200_ELIMIT if there are more matching lines than `capacity`
    (the first `capacity` are stored) or if a line is longer than the staging
-   piece.  Synchronous. */
+   piece (32 MiB).  Any line density is fine: a piece with more lines than its
+   index holds (one per 8 bytes) is taken again in smaller pieces.
+   Synchronous. */
 int red_b200_grep_host(const red_b200_program *prog, const uint8_t *text,
                        uint64_t text_len, uint8_t delim, int style,
                        red_b200_line_match *matches, uint64_t capacity,

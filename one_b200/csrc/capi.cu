@@ -115,6 +115,22 @@ struct HostPipe {
   }
 };
 
+/* red_b200_match() on one short text: a staging buffer of its own */
+constexpr size_t kSingleTextMax = 256u << 10;
+struct SingleMeta {
+  uint64_t start;
+  uint32_t len;
+  int32_t result;
+  uint32_t mstart, mend;
+  uint32_t pad[2];  // the text behind it starts on a 16-byte boundary
+};
+static_assert(sizeof(SingleMeta) % 16 == 0, "text alignment");
+struct SinglePipe {
+  cudaStream_t stream = nullptr;
+  uint8_t *hBuf = nullptr;  // pinned
+  uint8_t *dBuf = nullptr;
+};
+
 /* Every line of the chunk inside [lo, hi)?  If not, *dN becomes 0 and the
    kernels that follow on the stream walk nothing. */
 __global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, uint64_t count,
@@ -359,6 +375,23 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
 
   if ((err = cudaMalloc(&prog->dCounters, kCounters * sizeof(unsigned long long))) != cudaSuccess)
     return cleanup(err, "cudaMalloc(counters)");
+  {
+    // [256 * 8 reset states | 256 reset counts]
+    const size_t statesBytes = img.resetStates.size() * 4;
+    void *dReset = nullptr;
+    if ((err = cudaMalloc(&dReset, statesBytes + 256)) != cudaSuccess)
+      return cleanup(err, "cudaMalloc(reset states)");
+    prog->hotBuffers.push_back(dReset);
+    if ((err = cudaMemcpy(dReset, img.resetStates.data(), statesBytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (err = cudaMemcpy(static_cast<char *>(dReset) + statesBytes, img.resetCount.data(), 256,
+                          cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(dReset);
+      prog->hotBuffers.clear();
+      return cleanup(err, "cudaMemcpy(reset states)");
+    }
+    prog->dev.resetStates = static_cast<const uint32_t *>(dReset);
+    prog->dev.resetCount = reinterpret_cast<const uint8_t *>(dReset) + statesBytes;
+  }
 
   ProgramDev &pd = prog->dev;
   pd.equiv = static_cast<const uint8_t *>(prog->dLeader);
@@ -375,6 +408,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   pd.absV = img.absV;
   pd.pureV = img.pureV;
   pd.vPerState = img.vPerState;
+  pd.stateCount = img.stateCount;
   {
     // reciprocal for v / vPerState, kept only if exact over the whole v range
     const uint64_t d = img.vPerState;
@@ -479,6 +513,12 @@ void red_b200_program_free(red_b200_program *prog) {
     delete prog->pipe;
   }
   release_grep_pipe(prog);
+  if (prog->single) {
+    if (prog->single->stream) cudaStreamDestroy(prog->single->stream);
+    if (prog->single->hBuf) cudaFreeHost(prog->single->hBuf);
+    cudaFree(prog->single->dBuf);
+    delete prog->single;
+  }
   for (void *p : prog->hotBuffers)
     cudaFree(p);
   cudaFree(prog->dTable);
@@ -542,6 +582,18 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
                         int verb, int style, cudaStream_t stream) {
   int launches = 0;
   cudaError_t err;
+  /* Every launch gets a work counter of its own, from the stream-ordered pool:
+     it is handed back behind the kernel on the same stream, so it cannot be
+     zeroed for another launch while this one still counts on it (launches of
+     one program overlap on different streams). */
+  unsigned long long *ctr = nullptr;
+  if ((err = scratch_alloc(&ctr, sizeof(unsigned long long), stream)) != cudaSuccess)
+    return cuda_fail(err, "work counter");
+  struct CounterRelease {
+    unsigned long long *p;
+    cudaStream_t st;
+    ~CounterRelease() { scratch_free(p, st); }
+  } counterRelease{ctr, stream};
   if ((verb == RED_B200_VERB_CHECK) || (verb == RED_B200_VERB_MATCH)) {
     BatchArgs a = args;
     a.checkLeader = (verb == RED_B200_VERB_CHECK) && (prog->dev.leaderLen > 0);
@@ -551,7 +603,6 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
         ((style == RED_B200_STY_INSTANT) || (style == RED_B200_STY_LAST) || (style == RED_B200_STY_FULL))) {
       if (prog->hotProfileWanted && !prog->hotProfiled.load() && (a.nLines >= 8192))
         profile_hot(prog, a, stream);
-      unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
       HotDev hd;
       {
         std::lock_guard<std::mutex> lock(prog->hotMu);
@@ -568,15 +619,11 @@ static int launch_batch(red_b200_program *prog, const BatchArgs &args,
       err = launch_batch_anchored(prog->dev, prog->smemTable, a, style,
                                   prog->geo, prog->tune, stream, &launches);
     else {
-      // every launch gets its own block counter: launches of one program may
-      // overlap on different streams (the host pipeline does that)
-      unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
       err = launch_batch_lanes(prog->dev, prog->smemTable, a, style, prog->geo,
                                prog->tune, ctr, stream, &launches);
     }
   }
   else {
-    unsigned long long *ctr = prog->dCounters + (prog->nextCounter++ % kCounters);
     err = launch_batch_sliding(prog->dev, prog->smemTable, args, style,
                                verb == RED_B200_VERB_SEARCH, prog->geo, stream,
                                &launches, ctr, prog->tune.simpleWalk);
@@ -846,16 +893,31 @@ int red_b200_match_batch_host(const red_b200_program *cprog,
     return RED_B200_OK;
   };
 
+  // an error leaves nothing in flight: copies into the caller's buffers may
+  // still be queued on the slots' streams when run() gives up
+  auto settle = [&](int code) {
+    if (prog->pipe) {
+      const std::string keep = g_err;
+      for (int s = 0; s < HostPipe::kSlots; ++s) {
+        if (prog->pipe->stream[s])
+          cudaStreamSynchronize(prog->pipe->stream[s]);
+        prog->pipe->slotOptimistic[s] = false;
+      }
+      cudaGetLastError();
+      g_err = keep;
+    }
+    return code;
+  };
   int rc = run(0, n_lines, optimistic);
   if (rc != RED_B200_OK)
-    return rc;
+    return settle(rc);
   // chunks whose lines were not all inside the optimistic span: exact plan
   std::vector<std::pair<uint64_t, uint64_t>> again;
   again.swap(redo);
   for (auto &fc : again) {
     rc = run(fc.first, fc.second, false);
     if (rc != RED_B200_OK)
-      return rc;
+      return settle(rc);
   }
   return RED_B200_OK;
 }
@@ -888,6 +950,50 @@ int red_b200_match(const red_b200_program *prog, const void *text, size_t len,
   }
   if (len >= (1ull << 31))
     return fail(RED_B200_ELIMIT, "text too long for this verb; use match on the stream entry point");
+  if (len <= kSingleTextMax) {
+    // a short text: one pinned staging buffer, one stream, three small copies
+    // and the batch kernel for a single line - not the three-slot pipeline of
+    // the batch entry point (tens of megabytes of device buffers)
+    red_b200_program *p = const_cast<red_b200_program *>(prog);
+    std::lock_guard<std::mutex> lock(p->mu);
+    DeviceGuard guard(p->device);
+    if (!p->single) {
+      SinglePipe *sp = new SinglePipe;
+      p->single = sp;
+      CUDA_TRY(cudaStreamCreateWithFlags(&sp->stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaHostAlloc(&sp->hBuf, kSingleTextMax + 64 + sizeof(SingleMeta), cudaHostAllocDefault));
+      CUDA_TRY(cudaMalloc(&sp->dBuf, kSingleTextMax + 64 + sizeof(SingleMeta)));
+    }
+    SinglePipe *sp = p->single;
+    // [meta | text]: one copy in, the meta block back
+    SingleMeta *hm = reinterpret_cast<SingleMeta *>(sp->hBuf);
+    SingleMeta *dm = reinterpret_cast<SingleMeta *>(sp->dBuf);
+    hm->start = 0;
+    hm->len = static_cast<uint32_t>(len);
+    hm->result = 0;
+    hm->mstart = hm->mend = 0;
+    if (len)
+      memcpy(sp->hBuf + sizeof(SingleMeta), text, len);
+    CUDA_TRY(cudaMemcpyAsync(sp->dBuf, sp->hBuf, sizeof(SingleMeta) + len, cudaMemcpyHostToDevice, sp->stream));
+    BatchArgs args;
+    args.text = sp->dBuf + sizeof(SingleMeta);
+    args.starts = &dm->start;
+    args.lens = &dm->len;
+    args.nLines = 1;
+    args.results = &dm->result;
+    const bool positions = (verb == RED_B200_VERB_MATCH) || (verb == RED_B200_VERB_SEARCH);
+    args.matchStarts = positions ? &dm->mstart : nullptr;
+    args.matchEnds = positions ? &dm->mend : nullptr;
+    int rc = launch_batch(p, args, verb, style, sp->stream);
+    if (rc != RED_B200_OK)
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(hm, dm, sizeof(SingleMeta), cudaMemcpyDeviceToHost, sp->stream));
+    CUDA_TRY(cudaStreamSynchronize(sp->stream));
+    out->result = hm->result;
+    out->start = hm->mstart;
+    out->end = hm->mend;
+    return RED_B200_OK;
+  }
   uint64_t start0 = 0;
   uint32_t len32 = static_cast<uint32_t>(len);
   int32_t res = 0;

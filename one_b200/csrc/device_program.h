@@ -29,6 +29,9 @@ struct ProgramDev {
   int32_t initResult;
   uint32_t byteRows;    // 1: 256-column rows indexed by the raw byte (unitShift 8)
   uint32_t hasFinalStates;  // 1: a state >= absV is reachable from the initial state
+  uint32_t stateCount;  // v < stateCount * vPerState for every state of the program
+  const uint8_t *resetCount;    // [256], see DeviceImage::resetCount (program.h)
+  const uint32_t *resetStates;  // [256 * 8]
   uint32_t hotBytes;    // global-table mode: leading bytes of the table mirrored in shared
                         // memory by the production kernels (0: none)
 };

@@ -14,6 +14,7 @@
    flight. */
 
 #include <algorithm>
+#include <functional>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -170,29 +171,98 @@ extern "C" int red_b200_grep_host(const red_b200_program *cprog, const uint8_t *
   size_t piece = 32u << 20;
   if (const char *env = getenv("RED_B200_HOST_CHUNK_BYTES"))
     piece = std::max<size_t>(1 << 12, strtoull(env, nullptr, 0));
-  // Worst case a piece is all delimiters; index capacity is sized for lines of
-  // >= 8 bytes on average and the piece is shortened when a text is denser.
+  // The index of a piece holds one line per 8 bytes of text.  A piece that has
+  // more (word lists, runs of blank lines) is taken again in smaller pieces,
+  // sized by the line count the split reported - down to pieces of lineCap
+  // bytes, which cannot overflow whatever they hold.
   const size_t lineCap = piece / 8 + 16;
   int rc = ensure_grep(prog, piece, lineCap);
   if (rc != RED_B200_OK)
     return fail(rc, g_why);
   GrepPipe *gp = prog->grep;
 
-  struct InFlight { bool busy = false; uint64_t base = 0; } slot[kSlots];
+  struct InFlight { bool busy = false; uint64_t base = 0, bytes = 0; } slot[kSlots];
   uint64_t written = 0, lines = 0;
   bool truncated = false;
   std::string why;
 
-  // copy out what a finished slot produced
-  auto drain = [&](int s) -> int {
+  // text [pos, end) through slot s: copy in, index, match, compact, gather
+  auto submit = [&](int s, uint64_t pos, uint64_t end) -> int {
+    cudaStream_t st = gp->stream[s];
+    const uint64_t n = end - pos;
+    CUDA_TRY(cudaMemcpyAsync(gp->dText[s], text + pos, n, cudaMemcpyHostToDevice, st));
+    int r = split_lines_async(gp->dText[s], n, delim, gp->lineCap, gp->dStarts[s], gp->dLens[s],
+                              gp->dInfo[s], gp->scratch[s], st, why);
+    if (r != RED_B200_OK) {
+      g_why = why;
+      return r;
+    }
+    BatchArgs args;
+    args.text = gp->dText[s];
+    args.starts = gp->dStarts[s];
+    args.lens = gp->dLens[s];
+    args.nLines = gp->lineCap;
+    args.nLinesDev = &gp->dInfo[s]->nLines;
+    args.results = gp->dRes[s];
+    args.matchStarts = gp->dMs[s];
+    args.matchEnds = gp->dMe[s];
+    r = launch_batch_for(prog, args, RED_B200_VERB_MATCH, style, st, why);
+    if (r != RED_B200_OK) {
+      g_why = why;
+      return r;
+    }
+    r = compact_matches_n(gp->dRes[s], gp->lineCap, &gp->dInfo[s]->nLines, gp->dIdx[s],
+                          gp->dCount[s], gp->scratch[s], st, why);
+    if (r != RED_B200_OK) {
+      g_why = why;
+      return r;
+    }
+    gather_matches_kernel<<<148 * 2, 256, 0, st>>>(gp->dIdx[s], gp->dCount[s], gp->lineCap,
+                                                   gp->dStarts[s], gp->dLens[s], gp->dRes[s],
+                                                   gp->dMs[s], gp->dMe[s], pos, gp->dOut[s]);
+    prog->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(gp->hCount[s], gp->dCount[s], 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gp->hInfo[s], gp->dInfo[s], sizeof(LineCount), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(gp->done[s], st));
+    slot[s].busy = true;
+    slot[s].base = pos;
+    slot[s].bytes = n;
+    return RED_B200_OK;
+  };
+
+  // copy out what a finished slot produced; a piece whose index overflowed is
+  // taken again, in smaller pieces, before anything behind it is looked at
+  std::function<int(int)> drain = [&](int s) -> int {
     if (!slot[s].busy)
       return RED_B200_OK;
     CUDA_TRY(cudaEventSynchronize(gp->done[s]));
     slot[s].busy = false;
     const LineCount info = *gp->hInfo[s];
     if (info.overflow) {
-      g_why = "a piece of the text has more lines than the index holds (lines shorter than 8 bytes on average)";
-      return RED_B200_ELIMIT;
+      const uint64_t base = slot[s].base, end = base + slot[s].bytes;
+      // half of what the average density would allow, never more than half the
+      // piece that failed; lineCap bytes always fit
+      uint64_t sub = slot[s].bytes / std::max<uint64_t>(2, 2 * ((info.wanted + gp->lineCap - 1) / gp->lineCap));
+      sub = std::max<uint64_t>(sub, std::min<uint64_t>(gp->lineCap, slot[s].bytes / 2));
+      sub = std::max<uint64_t>(sub, 16);
+      for (uint64_t p = base; p < end;) {
+        uint64_t q = std::min(end, p + sub);
+        if (q < end) {
+          // cut just behind a delimiter; a line longer than `sub` is kept whole
+          const void *d = memrchr(text + p, delim, q - p);
+          if (!d)
+            d = memchr(text + q, delim, end - q);
+          q = d ? static_cast<uint64_t>(static_cast<const uint8_t *>(d) - text) + 1 : end;
+        }
+        int r = submit(s, p, q);
+        if (r != RED_B200_OK)
+          return r;
+        if ((r = drain(s)) != RED_B200_OK)
+          return r;
+        p = q;
+      }
+      return RED_B200_OK;
     }
     lines += info.nLines;
     uint64_t cnt = *gp->hCount[s];
@@ -206,7 +276,7 @@ extern "C" int red_b200_grep_host(const red_b200_program *cprog, const uint8_t *
                                cudaMemcpyDeviceToHost, gp->stream[s]));
       CUDA_TRY(cudaStreamSynchronize(gp->stream[s]));
     }
-    written += *gp->hCount[s] > room ? room : *gp->hCount[s];
+    written += cnt;
     return RED_B200_OK;
   };
 
@@ -225,43 +295,8 @@ extern "C" int red_b200_grep_host(const red_b200_program *cprog, const uint8_t *
     const int s = static_cast<int>(ci % kSlots);
     if ((rc = drain(s)) != RED_B200_OK)
       return fail(rc, g_why);
-    cudaStream_t st = gp->stream[s];
-    const uint64_t n = end - pos;
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(gp->dText[s], text + pos, n, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-      return fail(cuda_fail(e, "cudaMemcpyAsync(text)"), g_why);
-    rc = split_lines_async(gp->dText[s], n, delim, gp->lineCap, gp->dStarts[s], gp->dLens[s],
-                           gp->dInfo[s], gp->scratch[s], st, why);
-    if (rc != RED_B200_OK)
-      return fail(rc, why);
-    BatchArgs args;
-    args.text = gp->dText[s];
-    args.starts = gp->dStarts[s];
-    args.lens = gp->dLens[s];
-    args.nLines = gp->lineCap;
-    args.nLinesDev = &gp->dInfo[s]->nLines;
-    args.results = gp->dRes[s];
-    args.matchStarts = gp->dMs[s];
-    args.matchEnds = gp->dMe[s];
-    rc = launch_batch_for(prog, args, RED_B200_VERB_MATCH, style, st, why);
-    if (rc != RED_B200_OK)
-      return fail(rc, why);
-    rc = compact_matches_n(gp->dRes[s], gp->lineCap, &gp->dInfo[s]->nLines, gp->dIdx[s],
-                           gp->dCount[s], gp->scratch[s], st, why);
-    if (rc != RED_B200_OK)
-      return fail(rc, why);
-    gather_matches_kernel<<<148 * 2, 256, 0, st>>>(gp->dIdx[s], gp->dCount[s], gp->lineCap,
-                                                   gp->dStarts[s], gp->dLens[s], gp->dRes[s],
-                                                   gp->dMs[s], gp->dMe[s], pos, gp->dOut[s]);
-    prog->launches += 1;
-    if ((e = cudaGetLastError()) != cudaSuccess)
-      return fail(cuda_fail(e, "gather_matches_kernel"), g_why);
-    if ((e = cudaMemcpyAsync(gp->hCount[s], gp->dCount[s], 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(gp->hInfo[s], gp->dInfo[s], sizeof(LineCount), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
-        (e = cudaEventRecord(gp->done[s], st)) != cudaSuccess)
-      return fail(cuda_fail(e, "grep copy-out"), g_why);
-    slot[s].busy = true;
-    slot[s].base = pos;
+    if ((rc = submit(s, pos, end)) != RED_B200_OK)
+      return fail(rc, g_why);
     pos = end;
     // keep text order: the oldest slot is always drained first (round robin)
   }

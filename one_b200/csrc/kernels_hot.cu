@@ -158,26 +158,7 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// ---- the full table, wherever it lives (the cold path) ---------------------
-
-struct AnyTable {
-  const unsigned char *base;
-  uint32_t shift;  // byte offset of a row = v << shift
-  uint32_t wide;   // 1: u32 entries, 0: u16
-  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
-    const unsigned char *p = base + ((static_cast<size_t>(v) << shift) + co);
-    return wide ? __ldg(reinterpret_cast<const uint32_t *>(p))
-                : static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p)));
-  }
-};
-
-__device__ __forceinline__ AnyTable any_table(const ProgramDev &pd, uint32_t wide) {
-  AnyTable t;
-  t.base = static_cast<const unsigned char *>(pd.table);
-  t.shift = wide ? 2 : pd.unitShift + 1;
-  t.wide = wide;
-  return t;
-}
+// (AnyTable - the full table wherever it lives, the cold path - is in walk.cuh)
 
 /* Walks n bytes at p (generic pointer: a slot or global memory) on the full
    table with the reference's per-byte decisions (walk.cuh).  True = the walk is

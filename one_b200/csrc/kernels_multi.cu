@@ -363,7 +363,10 @@ batch_advance_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *s
     const uint8_t *p = text + starts[line];
     const uint32_t len = lens[line];
     uint32_t v = states[line];
-    if (v == kStateFresh)
+    // a state of this program is a multiple of vPerState below stateCount *
+    // vPerState; anything else (RED_B200_STATE_FRESH, a stale or foreign
+    // value) starts a new matcher instead of indexing the table with it
+    if ((v >= pd.stateCount * pd.vPerState) || (state_index(pd, v) * pd.vPerState != v))
       v = pd.initV;
     uint32_t hitV = kNone, hitEnd = 0;
     for (uint32_t idx = 0; idx < len; ++idx) {

@@ -305,6 +305,37 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
     for (int b = 0; b < 256; ++b)
       img.clsOffset[b] = static_cast<uint16_t>(pp.equiv[b] * 4);
   }
+  // images of the whole state set under one byte (long-stream matcher)
+  {
+    img.resetCount.assign(256, 0);
+    img.resetStates.assign(256 * DeviceImage::kResetMax, 0);
+    std::vector<uint32_t> stamp(n, 0xffffffffu);
+    for (uint32_t c = 0; c < C; ++c) {
+      uint32_t found[DeviceImage::kResetMax];
+      uint32_t cnt = 0;
+      bool small = true;
+      for (uint32_t ii = 0; (ii < n) && small; ++ii) {
+        // (pure dead ends stay where they are, as in the table)
+        const uint32_t to = absorbing(ii) ? ii : oldToNew[pp.next[static_cast<size_t>(order[ii]) * C + c]];
+        if (stamp[to] != c) {
+          stamp[to] = c;
+          if (cnt == DeviceImage::kResetMax)
+            small = false;
+          else
+            found[cnt++] = to;
+        }
+      }
+      if (!small)
+        continue;
+      std::sort(found, found + cnt);
+      for (int b = 0; b < 256; ++b)
+        if (pp.equiv[b] == c) {
+          img.resetCount[b] = static_cast<uint8_t>(cnt);
+          for (uint32_t k = 0; k < cnt; ++k)
+            img.resetStates[b * DeviceImage::kResetMax + k] = found[k] * img.vPerState;
+        }
+    }
+  }
   img.initV = oldToNew[pp.initialState] * img.vPerState;
   img.leaderV = oldToNew[pp.leaderState] * img.vPerState;
   img.pureV = firstPure * img.vPerState;

@@ -93,6 +93,15 @@ struct DeviceImage {
   std::vector<uint32_t> newToOld;    // new index -> serialized row
   std::vector<uint32_t> oldToNew;    // serialized row -> new index
   std::vector<uint8_t> leader;       // class space
+  /* For the long-stream matcher: the states the DFA can be in right behind
+     byte b, whatever it was in before - the image of ALL states under b - for
+     the bytes where those are at most kResetMax (v values, resetCount[b] of
+     them; resetCount[b] = 0: more than that).  A chunk's walk can start from
+     every one of them behind such a byte and be sure to include the true
+     state. */
+  static constexpr uint32_t kResetMax = 8;
+  std::vector<uint8_t> resetCount;   // [256]
+  std::vector<uint32_t> resetStates; // [256 * kResetMax]
   size_t tableBytes() const {
     return mode == kTableSmemU16 ? table16.size() * 2 : table32.size() * 4;
   }

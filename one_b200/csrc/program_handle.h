@@ -14,6 +14,7 @@
 
 struct HostPipe;
 struct GrepPipe;
+struct SinglePipe;
 
 using red_b200::BatchArgs;
 using red_b200::BatchTuning;
@@ -44,6 +45,7 @@ struct red_b200_program {
   std::mutex mu;        // guards the lazily created host pipeline
   HostPipe *pipe = nullptr;
   GrepPipe *grep = nullptr;   // lazily created by red_b200_grep_host
+  SinglePipe *single = nullptr;  // lazily created by red_b200_match on a short text
   std::atomic<long> launches{0};  // kernels launched through this program (for bench)
   std::atomic<long> hotLaunches{0};  // of those: launches of the staged batch kernel
 

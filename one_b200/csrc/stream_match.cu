@@ -10,30 +10,37 @@
         front of it, and a walk that is decided early (Instant/First/Tangent
         on the first match, any style in a state that can never be left) ends
         after the window it was decided in, as the reference's does;
-     2. a window is cut into chunks, one lane per chunk (2-16 KB each);
-     3. SPECULATE the state at the start of chunk i: run the DFA from the
-        initial state over a lookback window in front of the chunk.  DFAs of
-        the ".*pattern" kind forget their past quickly, so the guess is almost
-        always the true state;
-     4. walk every chunk from its guess, in parallel, with the batch kernels'
-        chunk engine (chunk_engine.cuh) in style Last with start tracking: the
-        record of a chunk is its end state, its last accepting position with
-        the state there, and the last position at which the initial state was
-        left;
-     5. STITCH: chunk i is confirmed when its start state equals the end state
-        of chunk i-1.  The records in front of the first unconfirmed chunk are
-        reduced in text order; if they already decide the walk, it is over.
-        Otherwise the unconfirmed chunks get the correct start state and are
-        walked again - all of them in parallel - until a round changes
-        nothing.  A chunk whose guess was wrong usually still ENDS in the
-        right state (the DFA converges inside the chunk), so a wrong guess
-        does not cascade and the loop ends after one or two rounds; in the
-        worst case (a DFA that never forgets, e.g. a parity counter) it
-        degrades to one chunk per round and stays exact;
-     6. the styles that stop at the first match get one short careful walk
-        from the start of the chunk that holds it.
+     2. a window is cut into chunks, one lane per chunk (1-16 KB each);
+     3. every chunk is walked from a small SET OF CANDIDATE start states that
+        is sure to hold the true one:
+          - a DFA of at most 8 states: all of them (the state map of the
+            chunk);
+          - otherwise: the lane looks back from its chunk for the last byte b
+            behind which the DFA can only be in a handful of states whatever
+            came before (the image of ALL states under b, precomputed at
+            upload: in a ".*pattern" automaton any byte that occurs in no
+            pattern leads everything to the initial state), takes those, and
+            walks them up to the chunk's start;
+        with the batch kernels' chunk engine (chunk_engine.cuh) in style Last:
+        the record of a (chunk, candidate) is its end state, its last accepting
+        position with the state there and, when asked for, the last position
+        at which the initial state was left;
+     4. STITCH on the device: a chunk's candidates map to the next chunk's by
+        their end states; these maps (eight 4-bit entries) are composed within
+        a warp's 32 consecutive chunks, the warps' maps by ONE thread block in
+        a three-level scan, and the true candidate of every chunk comes back
+        down the same way.  No host round trip, three small launches.
+     5. a chunk without such a byte within its lookback (a large DFA that
+        forgets nothing) has no candidates; what lies behind the first of
+        those in a window is resolved by one warp, in order, walking where it
+        must - exact for every DFA, a bounded number of launches, slow only
+        where the DFA leaves no other way;
+     6. the styles that stop at the first match get one careful walk from the
+        start of the chunk that holds it; a run of accepting positions that
+        outlasts that chunk (Tangent, First) is ended in parallel: every chunk
+        behind it reports the first position at which the run would break.
 
-   Every answer is exact: nothing is derived from an unconfirmed chunk.
+   Every answer is exact.
  */
 
 #include "stream.h"
@@ -54,6 +61,14 @@ constexpr uint32_t kNoPos = 0xffffffffu;
 constexpr uint32_t kLookback = 256;
 constexpr uint64_t kFirstWindow = 32ull << 20;
 constexpr uint64_t kWindowGrowth = 8;
+
+constexpr uint32_t kCand = DeviceImage::kResetMax;  // candidate start states per chunk
+constexpr uint32_t kNoCand = 0xfu;
+
+// one walk of a chunk from one candidate start state
+struct CandRec {
+  uint32_t startV, endV, accV, accEnd, lastLeaveOff;
+};
 
 struct ChunkRec {
   uint32_t startV;        // state the walk started from
@@ -127,12 +142,14 @@ __device__ __forceinline__ void walk_bytes(const ProgramDev &pd, const typename 
   }
 }
 
-/* text/len: the window; v0: the (exact) state at its start */
+/* text/len: the window; v0: the (exact) state at its start.  Chunk c is walked
+   from each of its candidate start states: cands[c * kCand + k], nCand[c] of
+   them (0: no candidates, see the file comment). */
 template <bool SMEM, int K, class ClsT, bool TRACK>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-stream_walk_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
-                   uint32_t chunkBytes, uint64_t nChunks, ChunkRec *recs,
-                   int firstRound, uint32_t v0) {
+stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
+                   uint32_t chunkBytes, uint64_t nChunks, CandRec *cands, uint8_t *nCand,
+                   uint32_t v0, uint32_t lookback) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   using Eng = Engine<SMEM, K, ClsT>;
   unsigned char *smem = Eng::stage(pd, smemRaw);
@@ -144,70 +161,246 @@ stream_walk_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint64_t rounds = (nChunks + stride - 1) / stride;
+  const bool allStates = pd.stateCount <= kCand;
   for (uint64_t r = 0; r < rounds; ++r) {
     const uint64_t c = first + r * stride;
-    ChunkRec rec{};
-    bool mine = c < nChunks;
-    if (mine && !firstRound) {
-      rec = recs[c];
-      mine = rec.dirty != 0;
-    }
+    const bool mine = c < nChunks;
     const uint64_t begin = mine ? c * chunkBytes : 0;
     const uint32_t n = mine ? static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin)) : 0;
-    if (firstRound) {
-      // speculate: the state after the lookback window, entered from the
-      // initial state (chunk 0 starts in the known state v0)
-      Walk<STY_FULL, false> sp;
-      sp.begin(pd);
-      const uint32_t lb = (mine && (c > 0)) ? kLookback : 0;  // chunkBytes >= kLookback
-      walk_bytes<STY_FULL, false, Eng>(pd, fast, tab, cls, text + begin - lb, lb, sp);
-      rec.startV = (c == 0) ? v0 : sp.v;
-    }
-    // TRACK: also the last exit from the initial state (three more
-    // instructions per step: only the lazy start search asks for it)
-    Walk<STY_LAST, TRACK> wk;
-    wk.begin(pd);
-    wk.v = rec.startV;
-    wk.mstart = kNoPos;
-    walk_bytes<STY_LAST, TRACK, Eng>(pd, fast, tab, cls, text + begin, n, wk);
+    uint32_t startV[kCand];
+    uint32_t cnt = 0;
     if (mine) {
-      rec.endV = wk.v;
-      rec.accV = wk.accV;
-      rec.accEnd = wk.absorbed ? n : wk.mend;
-      rec.lastLeaveOff = TRACK ? wk.mstart : kNoPos;
-      rec.dirty = 0;
-      recs[c] = rec;
+      if (c == 0) {
+        startV[0] = v0;
+        cnt = 1;
+      }
+      else if (allStates) {
+        for (uint32_t k = 0; k < pd.stateCount; ++k)
+          startV[k] = k * pd.vPerState;
+        cnt = pd.stateCount;
+      }
+      else {
+        // the last byte in the lookback behind which only a few states are
+        // possible; from each of them up to the chunk's start
+        for (uint32_t back = 1; (back <= lookback) && (cnt == 0); ++back) {
+          const uint32_t byte = __ldg(text + begin - back);
+          const uint32_t have = __ldg(pd.resetCount + byte);
+          if (have == 0)
+            continue;
+          for (uint32_t k = 0; k < have; ++k) {
+            uint32_t v = __ldg(pd.resetStates + byte * kCand + k);
+            for (uint32_t i = back - 1; i > 0; --i)
+              v = tab.next(v, cls[__ldg(text + begin - i)]);
+            bool dup = false;
+            for (uint32_t j = 0; j < cnt; ++j)
+              dup |= startV[j] == v;
+            if (!dup)
+              startV[cnt++] = v;
+          }
+        }
+      }
     }
+    const uint32_t most = __reduce_max_sync(0xffffffffu, cnt);
+    for (uint32_t k = 0; k < most; ++k) {
+      const bool go = k < cnt;
+      // TRACK: also the last exit from the initial state (three more
+      // instructions per step: only the lazy start search asks for it)
+      Walk<STY_LAST, TRACK> wk;
+      wk.begin(pd);
+      wk.v = go ? startV[k] : pd.initV;
+      wk.mstart = kNoPos;
+      walk_bytes<STY_LAST, TRACK, Eng>(pd, fast, tab, cls, text + begin, go ? n : 0, wk);
+      if (go) {
+        CandRec rec;
+        rec.startV = startV[k];
+        rec.endV = wk.v;
+        rec.accV = wk.accV;
+        rec.accEnd = wk.absorbed ? n : wk.mend;
+        rec.lastLeaveOff = TRACK ? wk.mstart : kNoPos;
+        cands[c * kCand + k] = rec;
+      }
+    }
+    if (mine)
+      nCand[c] = static_cast<uint8_t>(cnt);
   }
 }
 
-/* confirm chunk i against the end state of chunk i-1; hand the right start
-   state to the ones that fail, count them and find the first */
-__global__ void stream_verify_kernel(ChunkRec *recs, uint64_t nChunks,
-                                     uint32_t v0, StreamSummary *sum) {
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-  unsigned bad = 0;
-  unsigned long long firstBad = ~0ull;
-  for (uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-       c < nChunks; c += stride) {
-    const uint32_t want = (c == 0) ? v0 : recs[c - 1].endV;
-    if (recs[c].startV != want) {
-      recs[c].startV = want;
-      recs[c].dirty = 1;
-      ++bad;
-      firstBad = min(firstBad, static_cast<unsigned long long>(c));
+// a map between the candidates of two chunks: eight 4-bit entries, kNoCand = no image
+__device__ __forceinline__ uint32_t map_then(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < kCand; ++k) {
+    const uint32_t mid = (a >> (4 * k)) & 0xf;
+    const uint32_t to = (mid == kNoCand) ? kNoCand : ((b >> (4 * mid)) & 0xf);
+    r |= to << (4 * k);
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t map_apply(uint32_t m, uint32_t idx) {
+  return (idx == kNoCand) ? kNoCand : ((m >> (4 * idx)) & 0xf);
+}
+constexpr uint32_t kMapIdentity = 0x76543210u;
+
+/* maps[c]: candidate k of chunk c -> the candidate of chunk c + 1 that starts in
+   k's end state (kNoCand if none: chunk c + 1 has no candidates); segMaps[s]:
+   the 32 maps of warp segment s composed.  One lane per chunk. */
+__global__ void __launch_bounds__(256)
+stream_maps_kernel(const CandRec *cands, const uint8_t *nCand, uint64_t nChunks,
+                   uint32_t *maps, uint32_t *segMaps) {
+  const uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t m = kMapIdentity;  // (past the last chunk: harmless)
+  if (c < nChunks) {
+    m = 0;
+    const uint32_t mine = nCand[c];
+    const uint32_t next = (c + 1 < nChunks) ? nCand[c + 1] : 0;
+    for (uint32_t k = 0; k < kCand; ++k) {
+      uint32_t to = kNoCand;
+      if (k < mine) {
+        const uint32_t endV = cands[c * kCand + k].endV;
+        for (uint32_t j = 0; j < next; ++j)
+          if (cands[(c + 1) * kCand + j].startV == endV)
+            to = j;
+        if (c + 1 >= nChunks)
+          to = k;  // nothing behind the last chunk
+      }
+      m |= to << (4 * k);
+    }
+    maps[c] = m;
+  }
+  uint32_t seg = kMapIdentity;
+  for (uint32_t i = 0; i < 32; ++i)
+    seg = map_then(seg, __shfl_sync(0xffffffffu, m, i));
+  if ((lane == 0) && (c < nChunks))
+    segMaps[c >> 5] = seg;
+}
+
+/* ONE block: the candidate index in force at the start of every warp segment
+   (segIn), from index 0 at the start of the window - thread maps, warp maps,
+   a walk over the warp maps, and back down. */
+__global__ void __launch_bounds__(1024)
+stream_scan_kernel(const uint32_t *segMaps, uint64_t nSegs, uint8_t *segIn) {
+  __shared__ uint32_t warpMap[32];
+  __shared__ uint32_t warpIn[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t per = (nSegs + 1023) / 1024;
+  const uint64_t lo = min(nSegs, threadIdx.x * per), hi = min(nSegs, lo + per);
+  uint32_t mine = kMapIdentity;
+  for (uint64_t sgm = lo; sgm < hi; ++sgm)
+    mine = map_then(mine, segMaps[sgm]);
+  uint32_t w = kMapIdentity;
+  for (uint32_t i = 0; i < 32; ++i)
+    w = map_then(w, __shfl_sync(0xffffffffu, mine, i));
+  if (lane == 0)
+    warpMap[warp] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t idx = 0;
+    for (uint32_t i = 0; i < 32; ++i) {
+      warpIn[i] = idx;
+      idx = map_apply(warpMap[i], idx);
     }
   }
-  __syncwarp();
-  if (__any_sync(0xffffffffu, bad != 0)) {
-    bad = __reduce_add_sync(0xffffffffu, bad);
-    for (int d = 16; d > 0; d >>= 1)
-      firstBad = min(firstBad, __shfl_xor_sync(0xffffffffu, firstBad, d));
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&sum->bad, static_cast<unsigned long long>(bad));
-      atomicMin(&sum->firstBad, firstBad);
-    }
+  __syncthreads();
+  uint32_t idx = warpIn[warp];
+  uint32_t myIn = idx;
+  for (uint32_t i = 0; i < 32; ++i) {
+    if (lane == i)
+      myIn = idx;
+    idx = map_apply(__shfl_sync(0xffffffffu, mine, i), idx);
   }
+  idx = myIn;
+  for (uint64_t sgm = lo; sgm < hi; ++sgm) {
+    segIn[sgm] = static_cast<uint8_t>(idx);
+    idx = map_apply(segMaps[sgm], idx);
+  }
+}
+
+/* the true candidate of every chunk -> recs[c]; chunks behind one without
+   candidates stay unresolved (dirty) and are counted in sum->bad */
+__global__ void __launch_bounds__(256)
+stream_apply_kernel(const CandRec *cands, const uint32_t *maps, const uint8_t *segIn,
+                    uint64_t nChunks, ChunkRec *recs, StreamSummary *sum) {
+  const uint64_t c = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t m = (c < nChunks) ? maps[c] : kMapIdentity;
+  uint32_t idx = (c < nChunks) ? segIn[c >> 5] : 0;
+  idx = __shfl_sync(0xffffffffu, idx, 0);
+  uint32_t mineIdx = idx;
+  for (uint32_t i = 0; i < 32; ++i) {
+    if (lane == i)
+      mineIdx = idx;
+    idx = map_apply(__shfl_sync(0xffffffffu, m, i), idx);
+  }
+  bool bad = false;
+  if (c < nChunks) {
+    ChunkRec r{};
+    if (mineIdx == kNoCand) {
+      r.dirty = 1;
+      bad = true;
+    }
+    else {
+      const CandRec k = cands[c * kCand + mineIdx];
+      r.startV = k.startV;
+      r.endV = k.endV;
+      r.accV = k.accV;
+      r.accEnd = k.accEnd;
+      r.lastLeaveOff = k.lastLeaveOff;
+    }
+    recs[c] = r;
+  }
+  const unsigned bads = __ballot_sync(0xffffffffu, bad);
+  if (bads && (lane == 0)) {
+    atomicAdd(&sum->bad, static_cast<unsigned long long>(__popc(bads)));
+    atomicMin(&sum->firstBad, static_cast<unsigned long long>(c + __ffs(bads) - 1));
+  }
+}
+
+/* The chunks from sum->firstBad on, in order, by one thread: the true start
+   state is the end state of the chunk in front; a candidate that starts there
+   is taken, else the chunk is walked here, byte by byte on the full table.
+   Exact for every DFA; only a large automaton that forgets nothing (no byte
+   narrows its state down) comes here for more than the odd chunk. */
+template <bool TRACK>
+__global__ void stream_repair_kernel(const ProgramDev pd, uint32_t wide, const uint8_t *text, uint64_t len,
+                                     uint32_t chunkBytes, uint64_t nChunks, const CandRec *cands,
+                                     const uint8_t *nCand, ChunkRec *recs, StreamSummary *sum) {
+  if ((blockIdx.x != 0) || (threadIdx.x != 0))
+    return;
+  const AnyTable tab = any_table(pd, wide);
+  for (uint64_t c = sum->firstBad; c < nChunks; ++c) {
+    const uint32_t startV = recs[c - 1].endV;  // (chunk 0 always has its candidate)
+    ChunkRec r{};
+    r.startV = startV;
+    bool found = false;
+    for (uint32_t k = 0; (k < nCand[c]) && !found; ++k)
+      if (cands[c * kCand + k].startV == startV) {
+        const CandRec cr = cands[c * kCand + k];
+        r.endV = cr.endV;
+        r.accV = cr.accV;
+        r.accEnd = cr.accEnd;
+        r.lastLeaveOff = cr.lastLeaveOff;
+        found = true;
+      }
+    if (!found) {
+      const uint64_t begin = c * chunkBytes;
+      const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin));
+      Walk<STY_LAST, TRACK> wk;
+      wk.begin(pd);
+      wk.v = startV;
+      wk.mstart = kNoPos;
+      for (uint32_t i = 0; i < n; ++i)
+        if (wk.step(pd, tab, __ldg(pd.clsOffset + __ldg(text + begin + i)), i))
+          break;
+      r.endV = wk.v;
+      r.accV = wk.accV;
+      r.accEnd = wk.absorbed ? n : wk.mend;
+      r.lastLeaveOff = TRACK ? wk.mstart : kNoPos;
+    }
+    recs[c] = r;
+  }
+  sum->bad = 0;
+  sum->firstBad = ~0ull;
 }
 
 /* over the confirmed prefix: first/last chunk with an accepting position, last
@@ -267,6 +460,8 @@ struct TailOut {
   uint32_t accepted;     // an accepting position was found
   uint64_t end;          // one past the last accepting position of the run
   uint64_t lastLeave;    // last position where the initial state was left, or ~0
+  uint32_t open;         // the run of accepting positions was still going at `until`
+  uint32_t accV;         // the last accepting state
 };
 
 /* First / Tangent (and Instant): the reference keeps walking after the first
@@ -276,7 +471,7 @@ struct TailOut {
 template <bool SMEM, int K, class ClsT>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 stream_tail_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
-                   uint64_t from, uint32_t v0, int style, TailOut *out) {
+                   uint64_t from, uint64_t until, uint32_t v0, int style, TailOut *out) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_classes<ClsT>(pd, smem);
   if (SMEM)
@@ -291,36 +486,157 @@ stream_tail_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
   uint32_t v = v0;
   uint32_t accV = kNone;
   uint64_t end = 0, leave = ~0ull;
-  bool absorbed = false;
-  for (uint64_t pos = from; pos < len; ++pos) {
+  bool absorbed = false, broke = false;
+  for (uint64_t pos = from; pos < until; ++pos) {
     const uint32_t nv = tab.next(v, cls[__ldg(text + pos)]);
     if ((v == pd.initV) && (nv != pd.initV))
       leave = pos;
     v = nv;
-    if (v >= pd.pureV)
+    if (v >= pd.pureV) {
+      broke = true;
       break;
+    }
     if (v >= pd.acceptV) {
       if ((style == RED_B200_STY_FIRST) && (accV != kNone) && (v != accV) &&
-          (pd.results[state_index(pd, v)] != pd.results[state_index(pd, accV)]))
+          (pd.results[state_index(pd, v)] != pd.results[state_index(pd, accV)])) {
+        broke = true;
         break;
+      }
       accV = v;
       end = pos + 1;
-      if (style == RED_B200_STY_INSTANT)
+      if (style == RED_B200_STY_INSTANT) {
+        broke = true;
         break;
+      }
       if (v >= pd.absV) {
         absorbed = true;
         break;
       }
     }
     else if (accV != kNone)
-      break;  // First/Tangent: the accepting run is over
+    {
+      broke = true;  // First/Tangent: the accepting run is over
+      break;
+    }
   }
   TailOut o;
   o.accepted = (accV != kNone);
   o.result = o.accepted ? pd.results[state_index(pd, accV)] : 0;
   o.end = absorbed ? len : end;
   o.lastLeave = leave;
+  o.open = (o.accepted && !absorbed && !broke && (until < len)) ? 1 : 0;
+  o.accV = accV;
   *out = o;
+}
+
+/* A run of accepting positions that outlasted the chunk of its first one
+   (Tangent: while the state accepts; First: while it accepts with the same
+   result, Matcher.h:455-476).  Every chunk of the window behind that chunk is
+   walked from its true start state as if the run were still going, up to the
+   first position that would end it. */
+struct BreakRec {
+  uint32_t kind;    // 0 the run goes through the chunk, 1 it breaks at off, 2 it is absorbed (runs to the end of the text)
+  uint32_t off;
+  uint32_t accV;    // the last accepting state in front of the break (or of the chunk's end)
+  uint32_t leave;   // last offset (in front of the break) at which the initial state was left, or kNoPos
+};
+
+template <bool SMEM, int K, class ClsT>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+stream_break_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len, uint32_t chunkBytes,
+                    uint64_t firstChunk, uint64_t nChunks, const ChunkRec *recs, int style,
+                    int32_t runResult, BreakRec *out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_classes<ClsT>(pd, smem);
+  if (SMEM)
+    stage_table(pd, smem + kClsBytes);
+  __syncthreads();
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  using Tab = typename std::conditional<SMEM, SmemTable<K>, GlobalTable>::type;
+  const Tab tab{SMEM ? smem + kClsBytes : static_cast<const unsigned char *>(pd.table)};
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t c = firstChunk + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nChunks;
+       c += stride) {
+    const uint64_t begin = c * chunkBytes;
+    const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin));
+    uint32_t v = recs[c].startV;
+    BreakRec r;
+    r.kind = 0;
+    r.off = n;
+    r.accV = v;
+    r.leave = kNoPos;
+    for (uint32_t i = 0; i < n; ++i) {
+      const uint32_t nv = tab.next(v, cls[__ldg(text + begin + i)]);
+      const bool left = (v == pd.initV) && (nv != pd.initV);
+      v = nv;
+      bool ends = (v >= pd.pureV) || (v < pd.acceptV);
+      if (!ends && (style == RED_B200_STY_FIRST) && (v != r.accV) &&
+          (pd.results[state_index(pd, v)] != runResult))
+        ends = true;
+      if (left)
+        r.leave = i;  // (the reference notes it before it looks at the new state)
+      if (ends) {
+        r.kind = 1;
+        r.off = i;
+        break;
+      }
+      r.accV = v;
+      if (v >= pd.absV) {
+        r.kind = 2;
+        r.off = i;
+        break;
+      }
+    }
+    out[c] = r;
+  }
+}
+
+/* ONE block: the first chunk in [firstChunk, nChunks) at which the run ends,
+   and the last exit from the initial state in front of that point. */
+struct BreakSummary {
+  unsigned long long chunk;   // ~0: the run goes through the whole window
+  uint32_t kind, off, accV;
+  unsigned long long leaveChunk;  // chunk of the last exit from the initial state, ~0: none
+  uint32_t leaveOff;
+  uint32_t endV;              // accV at the window's end when the run goes on
+};
+__global__ void __launch_bounds__(1024)
+stream_break_reduce_kernel(const BreakRec *recs, uint64_t firstChunk, uint64_t nChunks, BreakSummary *out) {
+  __shared__ unsigned long long firstEnd, lastLeave;
+  if (threadIdx.x == 0) {
+    firstEnd = ~0ull;
+    lastLeave = 0;
+  }
+  __syncthreads();
+  unsigned long long mine = ~0ull;
+  for (uint64_t c = firstChunk + threadIdx.x; c < nChunks; c += blockDim.x)
+    if (recs[c].kind != 0) {
+      mine = c;
+      break;
+    }
+  if (mine != ~0ull)
+    atomicMin(&firstEnd, mine);
+  __syncthreads();
+  const unsigned long long stop = firstEnd;
+  const uint64_t upTo = (stop == ~0ull) ? nChunks : stop + 1;  // the breaking chunk's own exits count, too
+  unsigned long long lv = 0;
+  for (uint64_t c = firstChunk + threadIdx.x; c < upTo; c += blockDim.x)
+    if (recs[c].leave != kNoPos)
+      lv = c + 1;
+  if (lv)
+    atomicMax(&lastLeave, lv);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BreakSummary s;
+    s.chunk = stop;
+    s.kind = (stop != ~0ull) ? recs[stop].kind : 0;
+    s.off = (stop != ~0ull) ? recs[stop].off : 0;
+    s.accV = (stop != ~0ull) ? recs[stop].accV : 0;
+    s.leaveChunk = lastLeave ? lastLeave - 1 : ~0ull;
+    s.leaveOff = lastLeave ? recs[lastLeave - 1].leave : 0;
+    s.endV = (nChunks > firstChunk) ? recs[nChunks - 1].accV : 0;
+    *out = s;
+  }
 }
 
 template <bool SMEM, int K, class ClsT>
@@ -340,12 +656,14 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   } while (0)
 
   const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : pd.hotBytes);
-  auto walkPlain = stream_walk_kernel<SMEM, K, ClsT, false>;
-  auto walkTrack = stream_walk_kernel<SMEM, K, ClsT, true>;
+  auto walkPlain = stream_cand_kernel<SMEM, K, ClsT, false>;
+  auto walkTrack = stream_cand_kernel<SMEM, K, ClsT, true>;
   auto tail = stream_tail_kernel<SMEM, K, ClsT>;
+  auto brk = stream_break_kernel<SMEM, K, ClsT>;
   TRY(cudaFuncSetAttribute(walkPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(walkTrack, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TRY(cudaFuncSetAttribute(brk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 
   // chunk size of a window: one chunk per lane of the whole chip if that
   // gives 1 KB .. 16 KB, a multiple of 16
@@ -375,15 +693,35 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   ChunkRec *recs = nullptr, *recs2 = nullptr;
   StreamSummary *dSum = nullptr;
   TailOut *dTail = nullptr;
+  CandRec *cands = nullptr;
+  BreakRec *breaks = nullptr;
+  BreakSummary *dBreak = nullptr;
+  uint8_t *nCand = nullptr, *segIn = nullptr;
+  uint32_t *maps = nullptr, *segMaps = nullptr;
+  const uint64_t maxSegs = (maxChunks + 31) / 32;
   TRY(scratch_alloc(&recs, maxChunks * sizeof(ChunkRec), stream));
   TRY(scratch_alloc(&recs2, maxChunks * sizeof(ChunkRec), stream));
   TRY(scratch_alloc(&dSum, sizeof(StreamSummary), stream));
   TRY(scratch_alloc(&dTail, sizeof(TailOut), stream));
+  TRY(scratch_alloc(&cands, maxChunks * kCand * sizeof(CandRec), stream));
+  TRY(scratch_alloc(&nCand, maxChunks, stream));
+  TRY(scratch_alloc(&maps, maxChunks * 4, stream));
+  TRY(scratch_alloc(&segMaps, maxSegs * 4, stream));
+  TRY(scratch_alloc(&segIn, maxSegs, stream));
+  TRY(scratch_alloc(&breaks, maxChunks * sizeof(BreakRec), stream));
+  TRY(scratch_alloc(&dBreak, sizeof(BreakSummary), stream));
   auto release = [&]() {
     scratch_free(recs, stream);
     scratch_free(recs2, stream);
     scratch_free(dSum, stream);
     scratch_free(dTail, stream);
+    scratch_free(cands, stream);
+    scratch_free(nCand, stream);
+    scratch_free(maps, stream);
+    scratch_free(segMaps, stream);
+    scratch_free(segIn, stream);
+    scratch_free(breaks, stream);
+    scratch_free(dBreak, stream);
   };
   struct Releaser {
     decltype(release) &fn;
@@ -402,47 +740,50 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   init.firstBad = none;
   init.firstAccChunk = none;
 
-  /* One window [base, base + bytes) from the exact state v0: walk, confirm,
-     re-walk until nothing changes (or, with stopEarly, until the confirmed
-     prefix decides the walk).  track: also record the exits from the initial
-     state.  The records stay in `into`. */
+  /* One window [base, base + bytes) from the exact state v0: every chunk from
+     its candidate start states, the maps between neighbouring chunks'
+     candidates composed on the device, the true candidate of every chunk
+     copied to `into`, and the summary of the window.  track: also record the
+     exits from the initial state.  A fixed number of launches and one read
+     back; chunks that had no candidates are resolved by one more launch. */
   auto runWindow = [&](uint64_t base, uint64_t bytes, uint32_t v0, uint64_t chunk, bool track,
                        bool stopEarly, ChunkRec *into, StreamSummary &sum, bool &decided) -> int {
     const uint64_t nChunks = (bytes + chunk - 1) / chunk;
+    const uint64_t nSegs = (nChunks + 31) / 32;
     const uint8_t *wText = dText + base;  // a multiple of 16 bytes
     // a small window is spread over all SMs with few warps each (a lane
     // walks several times faster when its SM is not full)
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, (nChunks + 31) / 32));
     const unsigned threads = static_cast<unsigned>(std::min<uint64_t>(
         kMaxThreads, ((nChunks + grid - 1) / grid + 31) / 32 * 32));
-    const unsigned vgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount * 4, (nChunks + 255) / 256));
+    const unsigned cgrid = static_cast<unsigned>((nChunks + 255) / 256);
     const unsigned rgrid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(geo.smCount, (nChunks + 1023) / 1024)));
     auto walk = track ? walkTrack : walkPlain;
-    walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, into, 1, v0);
-    ++*launches;
-    decided = false;
-    for (uint64_t round = 0;; ++round) {
-      TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
-      stream_verify_kernel<<<vgrid, 256, 0, stream>>>(into, nChunks, v0, dSum);
-      stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(into, nChunks, none, dSum);
-      *launches += 2;
-      TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
-      TRY(cudaStreamSynchronize(stream));
-      // is the walk decided inside the confirmed prefix?
-      if (stopEarly && ((earlyStyle && (sum.firstAccChunk != none)) ||
-                        (sum.reduced && (sum.finalV >= pd.absV)))) {
-        decided = true;
-        break;
-      }
-      if (sum.bad == 0)
-        break;
-      if (round > nChunks) {
-        why = "stream stitching did not converge";
-        return RED_B200_EINTERNAL;
-      }
-      walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, into, 0, v0);
+    walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, cands, nCand,
+                                          v0, kLookback);
+    TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    stream_maps_kernel<<<cgrid, 256, 0, stream>>>(cands, nCand, nChunks, maps, segMaps);
+    stream_scan_kernel<<<1, 1024, 0, stream>>>(segMaps, nSegs, segIn);
+    stream_apply_kernel<<<cgrid, 256, 0, stream>>>(cands, maps, segIn, nChunks, into, dSum);
+    *launches += 4;
+    {
+      // (does nothing unless some chunk had no candidates: then everything
+      // from the first of them on, in order)
+      if (track)
+        stream_repair_kernel<true><<<1, 32, 0, stream>>>(pd, SMEM ? 0u : 1u, wText, bytes,
+                                                          static_cast<uint32_t>(chunk), nChunks, cands, nCand, into, dSum);
+      else
+        stream_repair_kernel<false><<<1, 32, 0, stream>>>(pd, SMEM ? 0u : 1u, wText, bytes,
+                                                           static_cast<uint32_t>(chunk), nChunks, cands, nCand, into, dSum);
       ++*launches;
     }
+    stream_reduce_kernel<<<rgrid, 256, 0, stream>>>(into, nChunks, nChunks, dSum);
+    ++*launches;
+    TRY(cudaMemcpyAsync(&sum, dSum, sizeof(sum), cudaMemcpyDeviceToHost, stream));
+    TRY(cudaStreamSynchronize(stream));
+    // is the walk decided inside this window?
+    decided = stopEarly && ((earlyStyle && (sum.firstAccChunk != none)) ||
+                            (sum.reduced && (sum.finalV >= pd.absV)));
     return RED_B200_OK;
   };
 
@@ -523,7 +864,8 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
       // careful walk from the chunk with the first accepting position
       const uint64_t c = sum.firstAccChunk;
       const uint64_t from = base + c * chunk;
-      tail<<<1, kMaxThreads, smem, stream>>>(pd, dText, len, from, sum.firstAccStartV, style, dTail);
+      const uint64_t until = std::min(len, from + chunk);
+      tail<<<1, kMaxThreads, smem, stream>>>(pd, dText, len, from, until, sum.firstAccStartV, style, dTail);
       ++*launches;
       TailOut t;
       TRY(cudaMemcpyAsync(&t, dTail, sizeof(t), cudaMemcpyDeviceToHost, stream));
@@ -531,12 +873,82 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
       if (t.accepted) {
         out->result = t.result;
         out->end = t.end;
-        // the initial state was last left either inside the tail walk or
-        // somewhere in front of it
         uint64_t leave = t.lastLeave;
-        if ((leave == none) && (from > 0))
+        if (t.open) {
+          /* Tangent / First: the run of accepting positions outlasts its first
+             chunk.  Where it ends is found in parallel: every chunk behind it,
+             from its true start state, reports the first position that breaks
+             the run - in this window, then in the windows that follow. */
+          uint32_t accV = t.accV;
+          uint64_t wBase = base, wBytes = bytes, wChunk = chunk, firstChunk = c + 1;
+          uint64_t nextBase = base + window, nextWindow = window * kWindowGrowth;
+          uint32_t wEndV = sum.finalV;
+          bool found = false;
+          while (!found) {
+            const uint64_t nCh = (wBytes + wChunk - 1) / wChunk;
+            if (firstChunk < nCh) {
+              const unsigned bgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, (nCh - firstChunk + 31) / 32));
+              const unsigned bthreads = static_cast<unsigned>(std::min<uint64_t>(
+                  kMaxThreads, ((nCh - firstChunk + bgrid - 1) / bgrid + 31) / 32 * 32));
+              brk<<<bgrid, bthreads, smem, stream>>>(pd, dText + wBase, wBytes, static_cast<uint32_t>(wChunk), firstChunk,
+                                                     nCh, recs, style, t.result, breaks);
+              stream_break_reduce_kernel<<<1, 1024, 0, stream>>>(breaks, firstChunk, nCh, dBreak);
+              *launches += 2;
+              BreakSummary bs;
+              TRY(cudaMemcpyAsync(&bs, dBreak, sizeof(bs), cudaMemcpyDeviceToHost, stream));
+              TRY(cudaStreamSynchronize(stream));
+              if (bs.leaveChunk != none)
+                leave = wBase + bs.leaveChunk * wChunk + bs.leaveOff;
+              if (bs.chunk != none) {
+                accV = bs.accV;
+                out->end = (bs.kind == 2) ? len : wBase + bs.chunk * wChunk + bs.off;
+                found = true;
+                break;
+              }
+              accV = bs.endV;
+            }
+            // the run goes through the window: the next one, from the exact state
+            if (nextBase >= len) {
+              out->end = len;
+              break;
+            }
+            wBase = nextBase;
+            wBytes = std::min(nextWindow, len - wBase);
+            wChunk = chunkFor(wBytes);
+            StreamSummary s2;
+            bool dummy = false;
+            if ((rc = runWindow(wBase, wBytes, wEndV, wChunk, false, false, recs, s2, dummy)) != RED_B200_OK)
+              return rc;
+            wins.push_back(Win{wBase, wBytes, wChunk, wEndV});
+            wEndV = s2.finalV;
+            firstChunk = 0;
+            nextBase = wBase + nextWindow;
+            nextWindow *= kWindowGrowth;
+          }
+          if (accV != t.accV) {
+            int32_t r2 = t.result;
+            if ((rc = resultOf(accV, r2)) != RED_B200_OK)
+              return rc;
+            out->result = r2;  // (Tangent reports the last accepting state's result)
+          }
+        }
+        // the initial state was last left either inside the walk from `from`
+        // or somewhere in front of it
+        if ((leave == none) && (from > 0)) {
+          // lastLeaveBefore looks at the window `from` lies in - whose records
+          // it expects in recs - and at those in front of it
+          if (wins.back().base > from) {
+            while (wins.back().base > from)
+              wins.pop_back();
+            StreamSummary s2;
+            bool dummy = false;
+            const Win &w = wins.back();
+            if ((rc = runWindow(w.base, w.bytes, w.v0, w.chunk, false, false, recs, s2, dummy)) != RED_B200_OK)
+              return rc;
+          }
           if ((rc = lastLeaveBefore(from, leave)) != RED_B200_OK)
             return rc;
+        }
         out->start = (leave == none) ? 0 : leave;
       }
       return RED_B200_OK;

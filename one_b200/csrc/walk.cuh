@@ -45,6 +45,27 @@ struct GlobalTable {
   }
 };
 
+// the full table in global memory, whichever of the two layouts it has (rare
+// paths: lanes that left the hot set, repairs of the long-stream matcher)
+struct AnyTable {
+  const unsigned char *base;
+  uint32_t shift;  // byte offset of a row = v << shift
+  uint32_t wide;   // 1: u32 entries, 0: u16
+  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
+    const unsigned char *p = base + ((static_cast<size_t>(v) << shift) + co);
+    return wide ? __ldg(reinterpret_cast<const uint32_t *>(p))
+                : static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(p)));
+  }
+};
+
+__device__ __forceinline__ AnyTable any_table(const ProgramDev &pd, uint32_t wide) {
+  AnyTable t;
+  t.base = static_cast<const unsigned char *>(pd.table);
+  t.shift = wide ? 2 : pd.unitShift + 1;
+  t.wide = wide;
+  return t;
+}
+
 // renumbered state index of v = v / vPerState; by multiplication when the
 // uploader found a reciprocal that is exact for every v of this program
 __device__ __forceinline__ uint32_t state_index(const ProgramDev &pd, uint32_t v) {

@@ -33,6 +33,32 @@ def byte_balanced_ranges(lens, world):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+def byte_balanced_ranges_periodic(pool_lens, reps, world):
+    """byte_balanced_ranges(np.tile(pool_lens, reps), world) without building
+    the tiled array: bench.py's corpus is a pool of lines repeated `reps`
+    times, hundreds of millions of lines at eight ranks."""
+    pool_lens = np.asarray(pool_lens, dtype=np.uint64)
+    m = len(pool_lens)
+    n = m * reps
+    if world <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (max(world, 1) - 1)
+    csum = np.cumsum(pool_lens, dtype=np.uint64)
+    per_pool = int(csum[-1])
+    total = per_pool * reps
+    cuts = [0]
+    for r in range(1, world):
+        target = (total * r) // world
+        if target == 0 or per_pool == 0:
+            k = int(np.searchsorted(csum, target, side="left")) if per_pool else 0
+        else:
+            # the first line whose end reaches the target lies in pool copy q
+            q = (target - 1) // per_pool
+            k = q * m + int(np.searchsorted(csum, target - q * per_pool, side="left"))
+        cuts.append(min(max(k, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
 def gather_counts(local_counts, group=None):
     """All ranks get every rank's vector of counts (e.g. matches per result id).
 

@@ -17,14 +17,20 @@ import os
 
 
 def compile_ours(red, rules, fmt=255, max_states=0, exact=False):
+    """exact=False: the reference's minimizer rule (RED_B200_MINIMIZE=reference), for
+    comparing programs with the reference's state by state; exact=True: the
+    product's default, the true minimal DFA."""
     if exact:
-        os.environ["RED_B200_MINIMIZE"] = "exact"
-    else:
         os.environ.pop("RED_B200_MINIMIZE", None)
-    p = red.Parser(max_states=max_states)
-    for pat, res, flags, lang in rules:
-        p.addAs(lang, pat, res, flags)
-    return red.compileToSerialized(p, fmt)
+    else:
+        os.environ["RED_B200_MINIMIZE"] = "reference"
+    try:
+        p = red.Parser(max_states=max_states)
+        for pat, res, flags, lang in rules:
+            p.addAs(lang, pat, res, flags)
+        return red.compileToSerialized(p, fmt)
+    finally:
+        os.environ.pop("RED_B200_MINIMIZE", None)
 
 
 def assert_matches_reference(ours, ref, what):
@@ -189,3 +195,37 @@ def test_live_differential_against_reference(redlib, ref_cls):
     # deviates from the minimal DFA; following its rule recovers most of them
     assert like_ok >= exact_ok
     assert like_ok >= 0.88 * done, (like_ok, exact_ok, done)
+
+
+def test_default_minimizer_keeps_the_rules_meaning(redlib, oracle_cls):
+    """The default (exact) minimizer: a union of rules answers, for every short
+    text, with the smallest result id among the rules that accept it on their
+    own - also where the reference's own minimizer merges states that differ
+    ('(ab|c)'->1, 'b(a|b)*.'->2 on 'bbb')."""
+    import itertools
+    import random
+    rng = random.Random(11)
+    atoms = ["a", "b", "c", ".", "(ab|c)", "(a|b)*", "b+", "[ab]", "[a-c]+", "a?", "(ab|c)(ab|c)", "c*"]
+
+    def rand_regex():
+        return "".join(rng.choice(atoms) for _ in range(rng.randint(1, 4))).encode()
+
+    sets = [[(b"(ab|c)", 1, 2, 1), (b"b(a|b)*.", 2, 2, 1)],
+            [(b"(ab|c)(ab|c)", 1, 2, 1), (b"c", 2, 2, 1), (b"b+[ab]c[a-c]+", 3, 2, 1)]]
+    # (every rule of a set with the same loose-start flag: the reference's union
+    # lets an anchored rule start behind a neighbour's ".*", see
+    # test_reference_quirks_are_kept, and that is kept on purpose)
+    for _ in range(60):
+        k = rng.randint(2, 3)
+        flags = rng.choice([2, 6])
+        sets.append([(rand_regex(), i + 1, flags, 1) for i in range(k)])
+    texts = [bytes(t) for n in range(0, 6) for t in itertools.product(b"abc", repeat=n)]
+    for rules in sets:
+        try:
+            union = oracle_cls(compile_ours(redlib, rules, exact=True))
+            singles = [(oracle_cls(compile_ours(redlib, [r], exact=True)), r[1]) for r in rules]
+        except redlib.RedExcept:
+            continue
+        for t in texts:
+            want = min([rid for prog, rid in singles if prog.run(t, "match", "full")[0] > 0], default=0)
+            assert union.run(t, "match", "full")[0] == want, (rules, t)

@@ -360,6 +360,35 @@ def test_grep_host_blob(gpu_red, vectors, oracle_cls, monkeypatch):
     prog.close()
 
 
+def test_grep_host_short_lines(gpu_red, vectors, oracle_cls, monkeypatch):
+    """Far more lines per piece than the index holds (1-3 byte lines, runs of
+    blank lines between ordinary ones): such a piece is taken again in smaller
+    pieces, in place, and the matches still come out in text order."""
+    from one_b200 import synth
+    case = next(c for c in vectors["cases"] if c["name"] == "union64")
+    blob = unz(case["program"])
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    rng = np.random.RandomState(6)
+    real = synth.make_lines(3000, seed=2)
+    lines = []
+    for i in range(200000):
+        lines.append(real[i % 3000] if i % 50 == 0 else bytes(rng.randint(97, 123, rng.randint(0, 4)).astype(np.uint8)))
+    text, starts, lens = synth.pack_lines(lines)
+    eres, ems, eme = orc.batch(text, starts, lens, "match", "instant")
+    hit = np.nonzero(eres > 0)[0]
+    assert hit.size > 100
+    for piece in ("65536", "1048576", None):
+        if piece:
+            monkeypatch.setenv("RED_B200_HOST_CHUNK_BYTES", piece)
+        else:
+            monkeypatch.delenv("RED_B200_HOST_CHUNK_BYTES")
+        recs, n_lines = prog.grep_host(text, b"\n", "instant")
+        assert n_lines == len(starts), piece
+        assert np.array_equal(recs["line_start"], starts[hit]), piece
+        assert np.array_equal(recs["result"], eres[hit]) and np.array_equal(recs["match_end"], eme[hit]), piece
+    prog.close()
+
+
 def test_match_all_and_collect(gpu_red, oracle_cls):
     """Per line all matches: matchAll() and Red::collect() against the reference's
     outputs (fixture) and against the oracle on a seeded corpus."""

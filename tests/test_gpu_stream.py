@@ -159,3 +159,73 @@ def test_large_dfa_uses_global_table(gpu_red, redlib, oracle_cls):
     assert (eres > 0).sum() > 5000
     check_stream(gpu_red, oracle_cls, blob, text.tobytes()[:400000], "keywords2000")
     prog.close()
+
+
+def dev_repeat(unit, total, tail=b""):
+    """unit repeated up to `total` bytes (+ tail) on the GPU and as bytes"""
+    import torch
+    reps = total // len(unit)
+    d = torch.frombuffer(bytearray(unit), dtype=torch.uint8).cuda().repeat(reps)
+    if tail:
+        d = torch.cat([d, torch.frombuffer(bytearray(tail), dtype=torch.uint8).cuda()])
+    d = torch.cat([d, torch.zeros(64, dtype=torch.uint8, device="cuda")])[:reps * len(unit) + len(tail)]
+    return d, unit * reps + tail
+
+
+def test_stream_1GB_dfa_that_never_forgets(gpu_red, redlib, oracle_cls):
+    """A parity counter over 1 GB: every chunk is walked from each of the DFA's
+    few states, the chunks' state maps are composed on the device - a fixed,
+    small number of launches, exact."""
+    p = redlib.Parser()
+    p.add(b"((a|b)(a|b))*", 1, 0)
+    blob = redlib.compileToSerialized(p)
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    for tail in (b"", b"a"):
+        dt, raw = dev_repeat(b"ab" * 4096, 1 << 30, tail)
+        for sty in ("full", "last", "instant"):
+            before = prog.launch_count
+            got = tuple(prog.match_stream_device(dt, "match", sty))
+            assert prog.launch_count - before <= 40, (sty, prog.launch_count - before)
+            assert got == orc.run(raw, "match", sty, False), (tail, sty, got)
+        del dt, raw
+    prog.close()
+
+
+def test_stream_1GB_accepting_run(gpu_red, redlib, oracle_cls):
+    """Tangent and First keep going while the text accepts: a run of a gigabyte
+    of digits is ended in parallel (every chunk behind the first match reports
+    where the run would break), not by one thread."""
+    p = redlib.Parser()
+    p.add(b"x[0-9]+", 1, 2)        # loose start
+    p.add(b"x[0-9]+y[0-9]*", 2, 2)
+    blob = redlib.compileToSerialized(p)
+    prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+    import torch
+    n = 1 << 30
+    for head, tail in ((b"abc x", b"!rest"), (b"x", b""), (b"zz x", b"y77 ")):
+        raw = head + b"7" * n + tail
+        dt = torch.cat([torch.frombuffer(bytearray(head), dtype=torch.uint8).cuda(),
+                        torch.full((n,), 55, dtype=torch.uint8, device="cuda"),
+                        torch.frombuffer(bytearray(tail + bytes(64)), dtype=torch.uint8).cuda()])[:len(raw)]
+        # the text starts at a 16-byte boundary, as the entry point asks
+        assert dt.data_ptr() % 16 == 0
+        for sty in ("tangent", "first", "last"):
+            before = prog.launch_count
+            got = tuple(prog.match_stream_device(dt, "match", sty))
+            assert prog.launch_count - before <= 60, (sty, prog.launch_count - before)
+            assert got == orc.run(raw, "match", sty, False), (head, tail, sty, got)
+        del dt, raw
+    prog.close()
+
+
+def test_stream_large_dfa_that_forgets_nothing(gpu_red, redlib, oracle_cls):
+    """A counter modulo 10 (more states than a chunk takes candidates, and no
+    byte narrows them down): no chunk has candidates, and the window is resolved
+    in order by the repair launch - slow, bounded, exact."""
+    p = redlib.Parser()
+    p.add(b"(" + b"(a|b)" * 10 + b")*", 1, 0)
+    blob = redlib.compileToSerialized(p)
+    rng = np.random.RandomState(12)
+    for n in (100000, 100005):
+        body = bytes(rng.choice(list(b"ab"), size=n).astype(np.uint8))
+        check_stream(gpu_red, oracle_cls, blob, body, ("mod10", n))

@@ -71,3 +71,16 @@ def test_two_rank_gather_equals_single_process(vectors, oracle_cls):
     res, _, _ = oracle_cls(blob).batch(text, starts, lens, "match", "instant")
     assert np.array_equal(counts, np.bincount(res, minlength=65))
     assert np.array_equal(lines, np.nonzero(res > 0)[0])
+
+
+def test_periodic_ranges_equal_the_explicit_ones():
+    """bench.py cuts a pool of lines repeated many times without building the
+    repeated array: same cuts as byte_balanced_ranges on the array itself."""
+    import numpy as np
+    from one_b200 import shard
+    rng = np.random.RandomState(3)
+    for _ in range(400):
+        m, reps, world = rng.randint(1, 14), rng.randint(1, 9), rng.randint(1, 9)
+        pool = rng.randint(0, 6, m).astype(np.uint32)
+        assert shard.byte_balanced_ranges_periodic(pool, reps, world) == \
+            shard.byte_balanced_ranges(np.tile(pool, reps), world), (pool, reps, world)
