@@ -305,16 +305,37 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
     for (int b = 0; b < 256; ++b)
       img.clsOffset[b] = static_cast<uint16_t>(pp.equiv[b] * 4);
   }
-  // images of the whole state set under one byte (long-stream matcher)
+  // images, under one byte, of the set of states a walk from the initial
+  // state can be in at all (long-stream matcher)
   {
     img.resetCount.assign(256, 0);
     img.resetStates.assign(256 * DeviceImage::kResetMax, 0);
+    std::vector<char> reach(n, 0);  // by new index
+    {
+      std::vector<uint32_t> todo{oldToNew[pp.initialState]};
+      reach[todo[0]] = 1;
+      while (!todo.empty()) {
+        const uint32_t ii = todo.back();
+        todo.pop_back();
+        if (absorbing(ii))
+          continue;
+        for (uint32_t c = 0; c < C; ++c) {
+          const uint32_t to = oldToNew[pp.next[static_cast<size_t>(order[ii]) * C + c]];
+          if (!reach[to]) {
+            reach[to] = 1;
+            todo.push_back(to);
+          }
+        }
+      }
+    }
     std::vector<uint32_t> stamp(n, 0xffffffffu);
     for (uint32_t c = 0; c < C; ++c) {
       uint32_t found[DeviceImage::kResetMax];
       uint32_t cnt = 0;
       bool small = true;
       for (uint32_t ii = 0; (ii < n) && small; ++ii) {
+        if (!reach[ii])
+          continue;
         // (pure dead ends stay where they are, as in the table)
         const uint32_t to = absorbing(ii) ? ii : oldToNew[pp.next[static_cast<size_t>(order[ii]) * C + c]];
         if (stamp[to] != c) {

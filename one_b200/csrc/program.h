@@ -94,7 +94,8 @@ struct DeviceImage {
   std::vector<uint32_t> oldToNew;    // serialized row -> new index
   std::vector<uint8_t> leader;       // class space
   /* For the long-stream matcher: the states the DFA can be in right behind
-     byte b, whatever it was in before - the image of ALL states under b - for
+     byte b, whatever it was in before - the image under b of all the states
+     that can be reached from the initial one - for
      the bytes where those are at most kResetMax (v values, resetCount[b] of
      them; resetCount[b] = 0: more than that).  A chunk's walk can start from
      every one of them behind such a byte and be sure to include the true

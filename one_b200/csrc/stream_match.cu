@@ -70,6 +70,12 @@ struct CandRec {
   uint32_t startV, endV, accV, accEnd, lastLeaveOff;
 };
 
+// a chunk's second, third ... candidate, walked by stream_extra_kernel
+struct ExtraWalk {
+  uint64_t chunk;
+  uint32_t k, startV;
+};
+
 struct ChunkRec {
   uint32_t startV;        // state the walk started from
   uint32_t endV;          // state after the chunk's last byte (or the state
@@ -149,7 +155,7 @@ template <bool SMEM, int K, class ClsT, bool TRACK>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
                    uint32_t chunkBytes, uint64_t nChunks, CandRec *cands, uint8_t *nCand,
-                   uint32_t v0, uint32_t lookback) {
+                   uint32_t v0, uint32_t lookback, ExtraWalk *extras, unsigned long long *nExtras) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   using Eng = Engine<SMEM, K, ClsT>;
   unsigned char *smem = Eng::stage(pd, smemRaw);
@@ -180,28 +186,59 @@ stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
         cnt = pd.stateCount;
       }
       else {
-        // the last byte in the lookback behind which only a few states are
-        // possible; from each of them up to the chunk's start
-        for (uint32_t back = 1; (back <= lookback) && (cnt == 0); ++back) {
+        // a byte in the lookback behind which only a few states are possible;
+        // from each of them up to the chunk's start.  Not the nearest one:
+        // with some text between it and the chunk the candidates have run
+        // together (states that differ only in what lies far behind them
+        // agree again after a byte or two), and every candidate that is left
+        // is a walk of the whole chunk.  (allStates: the loop is not entered.)
+        const uint32_t preferred = min(lookback, 48u);
+        for (uint32_t step = 0; (step < 2 * lookback) && (cnt == 0); ++step) {
+          // preferred, preferred + 1, ... lookback, then preferred - 1 ... 1
+          const uint32_t back = (step <= lookback - preferred) ? preferred + step
+                                                               : preferred - (step - (lookback - preferred));
+          if ((back == 0) || (back > lookback))
+            continue;
           const uint32_t byte = __ldg(text + begin - back);
           const uint32_t have = __ldg(pd.resetCount + byte);
           if (have == 0)
             continue;
-          for (uint32_t k = 0; k < have; ++k) {
-            uint32_t v = __ldg(pd.resetStates + byte * kCand + k);
-            for (uint32_t i = back - 1; i > 0; --i)
-              v = tab.next(v, cls[__ldg(text + begin - i)]);
+          // all of them in step (eight independent lookups per byte; a slot
+          // beyond `have` repeats the last state), duplicates dropped at the end
+          uint32_t v[kCand];
+#pragma unroll
+          for (uint32_t k = 0; k < kCand; ++k)
+            v[k] = __ldg(pd.resetStates + byte * kCand + min(k, have - 1));
+          for (uint32_t i = back - 1; i > 0; --i) {
+            const uint32_t co = cls[__ldg(text + begin - i)];
+#pragma unroll
+            for (uint32_t k = 0; k < kCand; ++k)
+              v[k] = tab.next(v[k], co);
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < kCand; ++k) {
             bool dup = false;
-            for (uint32_t j = 0; j < cnt; ++j)
-              dup |= startV[j] == v;
+#pragma unroll
+            for (uint32_t j = 0; j < k; ++j)
+              dup |= v[j] == v[k];
             if (!dup)
-              startV[cnt++] = v;
+              startV[cnt++] = v[k];
           }
         }
       }
     }
-    const uint32_t most = __reduce_max_sync(0xffffffffu, cnt);
-    for (uint32_t k = 0; k < most; ++k) {
+    // the first candidate is walked here; the others - few chunks have any, but
+    // most warps have such a chunk - go on a list for a launch of their own,
+    // so that no warp waits for one lane's second walk
+    for (uint32_t k = 1; k < cnt; ++k) {
+      ExtraWalk e;
+      e.chunk = c;
+      e.k = k;
+      e.startV = startV[k];
+      extras[atomicAdd(nExtras, 1ull)] = e;
+    }
+    {
+      const uint32_t k = 0;
       const bool go = k < cnt;
       // TRACK: also the last exit from the initial state (three more
       // instructions per step: only the lazy start search asks for it)
@@ -222,6 +259,48 @@ stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
     }
     if (mine)
       nCand[c] = static_cast<uint8_t>(cnt);
+  }
+}
+
+/* the walks stream_cand_kernel put on the list, one lane each */
+template <bool SMEM, int K, class ClsT, bool TRACK>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+stream_extra_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len, uint32_t chunkBytes,
+                    CandRec *cands, const ExtraWalk *extras, const unsigned long long *nExtras) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const unsigned long long total = *nExtras;
+  if (total == 0)
+    return;
+  using Eng = Engine<SMEM, K, ClsT>;
+  unsigned char *smem = Eng::stage(pd, smemRaw);
+  const ClsT *cls = reinterpret_cast<const ClsT *>(smem);
+  const typename Eng::Tab tab = Eng::table(pd, smem);
+  const typename Eng::Fast fast = Eng::fast(pd, smem);
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t rounds = (total + stride - 1) / stride;
+  for (uint64_t r = 0; r < rounds; ++r) {
+    const uint64_t item = first + r * stride;
+    const bool mine = item < total;
+    ExtraWalk e{};
+    if (mine)
+      e = extras[item];
+    const uint64_t begin = e.chunk * chunkBytes;
+    const uint32_t n = mine ? static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin)) : 0;
+    Walk<STY_LAST, TRACK> wk;
+    wk.begin(pd);
+    wk.v = mine ? e.startV : pd.initV;
+    wk.mstart = kNoPos;
+    walk_bytes<STY_LAST, TRACK, Eng>(pd, fast, tab, cls, text + begin, n, wk);
+    if (mine) {
+      CandRec rec;
+      rec.startV = e.startV;
+      rec.endV = wk.v;
+      rec.accV = wk.accV;
+      rec.accEnd = wk.absorbed ? n : wk.mend;
+      rec.lastLeaveOff = TRACK ? wk.mstart : kNoPos;
+      cands[e.chunk * kCand + e.k] = rec;
+    }
   }
 }
 
@@ -658,11 +737,15 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   const size_t smem = kLanesSmemExtra + (SMEM ? pd.tableBytes : pd.hotBytes);
   auto walkPlain = stream_cand_kernel<SMEM, K, ClsT, false>;
   auto walkTrack = stream_cand_kernel<SMEM, K, ClsT, true>;
+  auto extraPlain = stream_extra_kernel<SMEM, K, ClsT, false>;
+  auto extraTrack = stream_extra_kernel<SMEM, K, ClsT, true>;
   auto tail = stream_tail_kernel<SMEM, K, ClsT>;
   auto brk = stream_break_kernel<SMEM, K, ClsT>;
   TRY(cudaFuncSetAttribute(walkPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(walkTrack, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TRY(cudaFuncSetAttribute(extraPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  TRY(cudaFuncSetAttribute(extraTrack, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(brk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
 
   // chunk size of a window: one chunk per lane of the whole chip if that
@@ -696,6 +779,8 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   CandRec *cands = nullptr;
   BreakRec *breaks = nullptr;
   BreakSummary *dBreak = nullptr;
+  ExtraWalk *extras = nullptr;
+  unsigned long long *nExtras = nullptr;
   uint8_t *nCand = nullptr, *segIn = nullptr;
   uint32_t *maps = nullptr, *segMaps = nullptr;
   const uint64_t maxSegs = (maxChunks + 31) / 32;
@@ -709,6 +794,8 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   TRY(scratch_alloc(&segMaps, maxSegs * 4, stream));
   TRY(scratch_alloc(&segIn, maxSegs, stream));
   TRY(scratch_alloc(&breaks, maxChunks * sizeof(BreakRec), stream));
+  TRY(scratch_alloc(&extras, maxChunks * (kCand - 1) * sizeof(ExtraWalk), stream));
+  TRY(scratch_alloc(&nExtras, sizeof(unsigned long long), stream));
   TRY(scratch_alloc(&dBreak, sizeof(BreakSummary), stream));
   auto release = [&]() {
     scratch_free(recs, stream);
@@ -721,6 +808,8 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     scratch_free(segMaps, stream);
     scratch_free(segIn, stream);
     scratch_free(breaks, stream);
+    scratch_free(extras, stream);
+    scratch_free(nExtras, stream);
     scratch_free(dBreak, stream);
   };
   struct Releaser {
@@ -759,8 +848,12 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     const unsigned cgrid = static_cast<unsigned>((nChunks + 255) / 256);
     const unsigned rgrid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(geo.smCount, (nChunks + 1023) / 1024)));
     auto walk = track ? walkTrack : walkPlain;
+    TRY(cudaMemsetAsync(nExtras, 0, sizeof(unsigned long long), stream));
     walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, cands, nCand,
-                                          v0, kLookback);
+                                          v0, kLookback, extras, nExtras);
+    (track ? extraTrack : extraPlain)<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk),
+                                                                       cands, extras, nExtras);
+    ++*launches;
     TRY(cudaMemcpyAsync(dSum, &init, sizeof(init), cudaMemcpyHostToDevice, stream));
     stream_maps_kernel<<<cgrid, 256, 0, stream>>>(cands, nCand, nChunks, maps, segMaps);
     stream_scan_kernel<<<1, 1024, 0, stream>>>(segMaps, nSegs, segIn);
