@@ -1,14 +1,29 @@
 /* parser.cpp - RED's pattern languages -> NFA.
 
-   Tokenizer and recursive-descent parser for the regex dialect of the
-   reference (grammar and escapes: reference doc/Usage.md "Regular Expression
-   Syntax"; behaviour: lib/Scanner.cpp, lib/Parser.cpp), plus globs and exact
-   strings.  Accept/reject decisions and the automaton built are kept
-   identical to the reference; error texts are ours. */
+   The dialect is the reference's (doc/Usage.md "Regular Expression Syntax";
+   which inputs are accepted and what they mean was established against
+   lib/Scanner.cpp and lib/Parser.cpp by the differential tests in
+   tests/test_compile.py) - the implementation is not: a pattern is first
+   turned into a flat token list, the tokens into a small syntax tree by an
+   iterative operator-precedence pass, and the tree is emitted bottom-up
+   through the combinators of nfa.h.  Globs are translated into the same
+   tokens.  Error texts are this file's own.
+
+   Dialect notes that the code below has to honour (all of them observable
+   through the reference's accept/reject behaviour):
+     * inside [...] a leading ']' or '-' is literal; "x-]" is the two bytes x
+       and '-'; the ends of a range are taken as raw bytes even when written
+       as \d or \w;
+     * {n} needs n > 0; {,} is *, {0,} is *, {0,0} and {,0} are errors;
+     * an atom may be followed by ONE repeat; \i may follow an atom or a
+       repeat, but a repeat may not follow \i;
+     * an alternative may be empty ("a|", "(|b)", "()").
+ */
 
 #include "parser.h"
 
 #include <limits>
+#include <vector>
 
 #include "../../../include/red_b200.h"
 
@@ -17,447 +32,563 @@ namespace rx {
 
 namespace {
 
-enum TokKind { kEnd, kFlags, kBytes, kRepeat, kBar, kOpen, kClose };
+// ---- bytes and escapes -----------------------------------------------------
 
-struct Tok {
-  TokKind kind = kEnd;
-  size_t pos = 0;
-  int min = 0, max = 0;  // kRepeat (max < 0: unbounded)
-  uint32_t flags = 0;    // kFlags
-  ByteSet set;           // kBytes
+// one decoded unit of pattern text
+struct Unit {
+  int value = -1;     // the byte; -1: end of pattern
+  bool named = false; // written as backslash + a character without a fixed byte value (\d, \i, \q ...)
 };
 
-int hexval(uint8_t c) {
+int hexDigit(uint8_t c) {
   if ((c >= '0') && (c <= '9')) return c - '0';
-  if ((c >= 'A') && (c <= 'F')) return c - 'A' + 10;
+  c |= 0x20;
   if ((c >= 'a') && (c <= 'f')) return c - 'a' + 10;
   return -1;
 }
 
-// \d \D \s \S \w \W expand to sets; any other escaped byte stands for itself
-void addClassOrByte(ByteSet &set, int c, bool escaped) {
-  if (!escaped) {
-    set.add(c);
+class Reader {
+public:
+  Reader(const uint8_t *p, size_t n) : beg_(p), cur_(p), end_(p + n) {}
+  size_t at() const { return static_cast<size_t>(cur_ - beg_); }
+  bool done() const { return cur_ >= end_; }
+  uint8_t peek() const { return *cur_; }
+  uint8_t take() { return *cur_++; }
+
+  Unit unit() {
+    Unit u;
+    if (done())
+      return u;
+    uint8_t c = take();
+    if (c != '\\') {
+      u.value = c;
+      return u;
+    }
+    if (done())
+      fail_parse("a backslash ends the pattern", at());
+    c = take();
+    static const char plain[] = "0\0a\ab\bn\nr\rt\tv\v\\\\";  // pairs: letter, byte
+    for (size_t i = 0; i + 1 < sizeof(plain); i += 2)
+      if (c == static_cast<uint8_t>(plain[i])) {
+        u.value = static_cast<uint8_t>(plain[i + 1]);
+        return u;
+      }
+    if (c == 'x') {
+      const int hi = (end_ - cur_ >= 2) ? hexDigit(cur_[0]) : -1;
+      const int lo = (end_ - cur_ >= 2) ? hexDigit(cur_[1]) : -1;
+      if ((hi < 0) || (lo < 0))
+        fail_parse("\\x wants two hexadecimal digits", at());
+      cur_ += 2;
+      u.value = hi * 16 + lo;
+      return u;
+    }
+    u.value = c;
+    u.named = true;
+    return u;
+  }
+
+private:
+  const uint8_t *beg_, *cur_, *end_;
+};
+
+// what a unit contributes to a set: \d \D \s \S \w \W are sets, the rest one byte
+void unitInto(ByteSet &set, const Unit &u) {
+  if (!u.named) {
+    set.add(u.value);
     return;
   }
-  ByteSet inv;
-  switch (c) {
-  case 'd': set.addRange('0', '9'); break;
-  case 'D': inv.addRange('0', '9'); inv.invert(); set.merge(inv); break;
-  case 's':
-    for (int w : {'\t', '\n', '\v', '\f', '\r', ' '}) set.add(w);
-    break;
-  case 'S':
-    for (int w : {'\t', '\n', '\v', '\f', '\r', ' '}) inv.add(w);
-    inv.invert(); set.merge(inv);
-    break;
-  case 'w':
-    set.addRange('0', '9'); set.addRange('A', 'Z'); set.addRange('a', 'z'); set.add('_');
-    break;
-  case 'W':
-    inv.addRange('0', '9'); inv.addRange('A', 'Z'); inv.addRange('a', 'z'); inv.add('_');
-    inv.invert(); set.merge(inv);
-    break;
-  default: set.add(c); break;
+  ByteSet base;
+  const int lower = u.value | 0x20;
+  if (lower == 'd')
+    base.addRange('0', '9');
+  else if (lower == 's') {
+    base.add(' ');
+    base.addRange('\t', '\r');
   }
+  else if (lower == 'w') {
+    base.addRange('0', '9');
+    base.addRange('A', 'Z');
+    base.addRange('a', 'z');
+    base.add('_');
+  }
+  else {
+    set.add(u.value);  // \q is q
+    return;
+  }
+  if (u.value != lower)
+    base.invert();  // the capital letter is the complement
+  set.merge(base);
 }
 
-class Lexer {
-public:
-  void reset(const uint8_t *p, size_t n) { beg_ = cur_ = p; end_ = p + n; count_ = 0; }
-  size_t tokens() const { return count_; }
+// ---- tokens ------------------------------------------------------------------
 
-  Tok next() {
-    ++count_;
-    Tok t;
-    if (cur_ >= end_) {
-      t.kind = kEnd; t.pos = pos();
-      return t;
+enum class Tk { End, Fold, Set, Times, Or, Open, Close, Bad };
+
+struct Token {
+  Tk kind = Tk::End;
+  size_t at = 0;
+  ByteSet set;        // Set
+  int lo = 0, hi = 0; // Times; hi < 0: no upper bound
+  const char *why = nullptr;  // Bad: reported when the parser gets there
+};
+
+Token bad(size_t at, const char *why) {
+  Token t;
+  t.kind = Tk::Bad;
+  t.at = at;
+  t.why = why;
+  return t;
+}
+
+/* [...]: the units up to the closing bracket are decoded first, then read with
+   two units of lookahead ("x-y" is a range, "x-]" is not). */
+Token bracketSet(Reader &in, bool regexEscapes) {
+  Token t;
+  t.kind = Tk::Set;
+  t.at = in.at();
+  std::vector<Unit> units;
+  auto get = [&](size_t i) -> const Unit & {
+    while (units.size() <= i) {
+      Unit u;
+      if (regexEscapes)
+        u = in.unit();
+      else if (!in.done())
+        u.value = in.take();
+      units.push_back(u);
     }
-    switch (*cur_) {
-    case '(': ++cur_; t.kind = kOpen; t.pos = pos(); return t;
-    case ')': ++cur_; t.kind = kClose; t.pos = pos(); return t;
-    case '|': ++cur_; t.kind = kBar; t.pos = pos(); return t;
-    case '*': ++cur_; return rep(0, -1);
-    case '+': ++cur_; return rep(1, -1);
-    case '?': ++cur_; return rep(0, 1);
-    case '.': ++cur_; t.kind = kBytes; t.pos = pos(); t.set.fill(); return t;
-    case '[': ++cur_; return bracket();
-    case '{': ++cur_; return braces();
-    default: return ordinary();
+    return units[i];
+  };
+  auto is = [&](size_t i, int c) { return !get(i).named && (get(i).value == c); };
+  size_t i = 0;
+  bool negate = false;
+  if (is(0, '^') || (!regexEscapes && is(0, '!'))) {
+    negate = true;
+    i = 1;
+  }
+  if (is(i, ']') || is(i, '-'))
+    t.set.add(get(i++).value);  // literal in first place
+  for (;;) {
+    if (get(i).value < 0)
+      return bad(in.at(), "a character class is not closed");
+    if (is(i, ']'))
+      break;
+    if (is(i + 1, '-')) {
+      if (get(i + 2).value < 0)
+        return bad(in.at(), "a character class ends inside a range");
+      if (is(i + 2, ']')) {
+        t.set.add(get(i).value);
+        t.set.add('-');
+        break;
+      }
+      const int from = get(i).value, to = get(i + 2).value;  // raw bytes, also for \d and the like
+      if (from > to)
+        return bad(in.at(), "a character class range runs downwards");
+      t.set.addRange(from, to);
+      i += 3;
+      continue;
+    }
+    if (regexEscapes)
+      unitInto(t.set, get(i));
+    else
+      t.set.add(get(i).value);
+    ++i;
+  }
+  if (negate)
+    t.set.invert();
+  return t;
+}
+
+/* {n} {n,m} {n,} {,m} {,} */
+Token braceTimes(Reader &in) {
+  Token t;
+  t.kind = Tk::Times;
+  t.at = in.at();
+  long value[2] = {0, 0};
+  bool digits[2] = {false, false};
+  int field = 0;
+  for (;;) {
+    if (in.done())
+      return bad(in.at(), "a repeat count is not closed");
+    const uint8_t c = in.take();
+    if (c == '}')
+      break;
+    if (c == ',') {
+      if (field == 1)
+        return bad(in.at(), "a repeat count has more than one comma");
+      field = 1;
+    }
+    else if ((c >= '0') && (c <= '9')) {
+      value[field] = value[field] * 10 + (c - '0');
+      digits[field] = true;
+    }
+    else
+      return bad(in.at(), "a repeat count may hold digits and one comma only");
+  }
+  if (field == 0) {
+    if (!digits[0] || (value[0] == 0))
+      return bad(in.at(), "a repeat count must be positive");
+    t.lo = t.hi = static_cast<int>(value[0]);
+    return t;
+  }
+  t.lo = static_cast<int>(value[0]);
+  t.hi = digits[1] ? static_cast<int>(value[1]) : -1;
+  if (digits[1] && (value[1] == 0) && (value[0] == 0))
+    return bad(in.at(), "a repeat count of zero");
+  if (digits[1] && (value[1] < value[0]))
+    return bad(in.at(), "a repeat count's upper bound is below its lower");
+  return t;
+}
+
+std::vector<Token> regexTokens(const uint8_t *p, size_t n) {
+  std::vector<Token> out;
+  Reader in(p, n);
+  auto simple = [&](Tk kind) {
+    Token t;
+    t.kind = kind;
+    t.at = in.at();
+    out.push_back(t);
+  };
+  auto times = [&](int lo, int hi) {
+    Token t;
+    t.kind = Tk::Times;
+    t.at = in.at();
+    t.lo = lo;
+    t.hi = hi;
+    out.push_back(t);
+  };
+  while (!in.done() && (out.empty() || (out.back().kind != Tk::Bad))) {
+    switch (in.peek()) {
+    case '(': in.take(); simple(Tk::Open); continue;
+    case ')': in.take(); simple(Tk::Close); continue;
+    case '|': in.take(); simple(Tk::Or); continue;
+    case '*': in.take(); times(0, -1); continue;
+    case '+': in.take(); times(1, -1); continue;
+    case '?': in.take(); times(0, 1); continue;
+    case '[': in.take(); out.push_back(bracketSet(in, true)); continue;
+    case '{': in.take(); out.push_back(braceTimes(in)); continue;
+    default: break;
+    }
+    Token t;
+    t.at = in.at();
+    if (in.peek() == '.') {
+      in.take();
+      t.kind = Tk::Set;
+      t.set.fill();
+      out.push_back(t);
+      continue;
+    }
+    const Unit u = in.unit();
+    if (u.named && (u.value >= '1') && (u.value <= '9')) {
+      out.push_back(bad(t.at, "backreferences cannot be matched by a DFA"));
+      break;
+    }
+    if (u.named && (u.value == 'i'))
+      t.kind = Tk::Fold;
+    else {
+      t.kind = Tk::Set;
+      unitInto(t.set, u);
+    }
+    out.push_back(t);
+  }
+  Token end;
+  end.at = n;
+  if (out.empty() || (out.back().kind != Tk::Bad))
+    out.push_back(end);
+  return out;
+}
+
+/* A glob as the same tokens: '*' is a Set of everything under a star that is
+   marked as a wildcard (lo = hi = -2, emitted as the NFA's own ".*" fragment),
+   '?' one byte of any value, [...] a class without escapes ('!' negates as
+   well), anything else itself. */
+std::vector<Token> globTokens(const uint8_t *p, size_t n) {
+  std::vector<Token> out;
+  Reader in(p, n);
+  while (!in.done() && (out.empty() || (out.back().kind != Tk::Bad))) {
+    Token t;
+    t.at = in.at();
+    const uint8_t c = in.take();
+    if (c == '[') {
+      out.push_back(bracketSet(in, false));
+      continue;
+    }
+    t.kind = Tk::Set;
+    if (c == '*')
+      t.lo = t.hi = -2;
+    else if (c == '?')
+      t.set.fill();
+    else
+      t.set.add(c);
+    out.push_back(t);
+  }
+  Token end;
+  end.at = n;
+  if (out.empty() || (out.back().kind != Tk::Bad))
+    out.push_back(end);
+  return out;
+}
+
+// ---- syntax tree ------------------------------------------------------------
+
+struct Tree {
+  enum Kind { Nothing, Bytes, Wild, Seq, Alt, Times };
+  struct Node {
+    Kind kind = Nothing;
+    ByteSet set;             // Bytes
+    int lo = 0, hi = 0;      // Times
+    int left = -1, right = -1;
+  };
+  std::vector<Node> nodes;
+  int add(Kind k, int l = -1, int r = -1) {
+    Node n;
+    n.kind = k;
+    n.left = l;
+    n.right = r;
+    nodes.push_back(n);
+    return static_cast<int>(nodes.size()) - 1;
+  }
+};
+
+/* tokens -> tree, without recursion: a stack of open groups, each holding the
+   alternatives finished so far and the sequence being collected. */
+class Builder {
+public:
+  Builder(const std::vector<Token> &toks, uint64_t nesting) : toks_(toks), nestingLeft_(nesting) {}
+
+  int run(Tree &tree, bool &fold) {
+    std::vector<Frame> open(1);
+    size_t i = 0;
+    for (;;) {
+      const Token &t = toks_[i];
+      Frame &f = open.back();
+      switch (t.kind) {
+      case Tk::Bad:
+        fail_parse(t.why, t.at);
+      case Tk::Fold:
+        fold = true;
+        if (f.lastAtom >= 0)
+          f.afterFold = true;  // a repeat may not come next
+        ++i;
+        break;
+      case Tk::Set:
+        push(tree, f, (t.lo == -2) ? tree.add(Tree::Wild) : bytes(tree, t.set));
+        ++i;
+        break;
+      case Tk::Times: {
+        if ((f.lastAtom < 0) || f.afterFold || f.repeated)
+          fail_parse("a repeat has nothing to repeat", t.at);
+        const int inner = f.lastAtom;
+        const int rep = tree.add(Tree::Times, inner);
+        tree.nodes[rep].lo = t.lo;
+        tree.nodes[rep].hi = t.hi;
+        replaceLast(tree, f, rep);
+        f.repeated = true;
+        ++i;
+        break;
+      }
+      case Tk::Or:
+        f.alts.push_back(f.seq);
+        f.seq = -1;
+        f.lastAtom = -1;
+        f.afterFold = f.repeated = false;
+        ++i;
+        break;
+      case Tk::Open:
+        if (nestingLeft_ == 0)
+          fail_limit("parentheses are nested deeper than the budget allows");
+        --nestingLeft_;
+        open.emplace_back();
+        ++i;
+        break;
+      case Tk::Close: {
+        if (open.size() == 1)
+          fail_parse("a closing parenthesis without an opening one", t.at);
+        const int group = close(tree, f);
+        open.pop_back();
+        ++nestingLeft_;
+        push(tree, open.back(), group);
+        ++i;
+        break;
+      }
+      case Tk::End:
+        if (open.size() != 1)
+          fail_parse("a parenthesis is not closed", t.at);
+        return close(tree, f);
+      }
     }
   }
 
 private:
-  size_t pos() const { return static_cast<size_t>(cur_ - beg_); }
+  struct Frame {
+    std::vector<int> alts;  // finished alternatives (-1: empty)
+    int seq = -1;           // the sequence being collected (-1: nothing yet)
+    int lastAtom = -1;      // its last element
+    int lastParent = -1;    // the Seq node whose right child lastAtom is (-1: it is seq itself)
+    bool afterFold = false, repeated = false;
+  };
 
-  Tok rep(int mn, int mx) {
-    Tok t; t.kind = kRepeat; t.pos = pos(); t.min = mn; t.max = mx;
-    return t;
+  static int bytes(Tree &tree, const ByteSet &set) {
+    const int n = tree.add(Tree::Bytes);
+    tree.nodes[n].set = set;
+    return n;
+  }
+  static void push(Tree &tree, Frame &f, int atom) {
+    if (f.seq < 0) {
+      f.seq = atom;
+      f.lastParent = -1;
+    }
+    else {
+      f.seq = tree.add(Tree::Seq, f.seq, atom);  // left-leaning: ((a b) c) d
+      f.lastParent = f.seq;
+    }
+    f.lastAtom = atom;
+    f.afterFold = f.repeated = false;
+  }
+  static void replaceLast(Tree &tree, Frame &f, int with) {
+    if (f.lastParent < 0)
+      f.seq = with;
+    else
+      tree.nodes[f.lastParent].right = with;
+    f.lastAtom = with;
+  }
+  // the group's alternatives, left to right: ((a|b)|c)
+  static int close(Tree &tree, Frame &f) {
+    f.alts.push_back(f.seq);
+    int all = -2;
+    for (int a : f.alts) {
+      const int one = (a < 0) ? tree.add(Tree::Nothing) : a;
+      all = (all == -2) ? one : tree.add(Tree::Alt, all, one);
+    }
+    return all;
   }
 
-  // one (possibly escaped) byte; -1 at end of input.  `escaped` is set for
-  // backslash sequences that are not a literal byte (\d, \i, \1 ...)
-  int oneByte(bool &escaped) {
-    if (cur_ >= end_)
-      return -1;
-    uint8_t c = *cur_++;
-    escaped = false;
-    if (c != '\\')
-      return c;
-    if (cur_ >= end_)
-      fail_parse("partial backslash escape", pos());
-    c = *cur_++;
-    switch (c) {
-    case '0': return '\0';
-    case 'a': return '\a';
-    case 'b': return '\b';
-    case 'n': return '\n';
-    case 'r': return '\r';
-    case 't': return '\t';
-    case 'v': return '\v';
-    case '\\': return '\\';
-    case 'x': {
-      if (cur_ + 2 > end_)
-        fail_parse("unterminated hex escape", pos());
-      int hi = hexval(cur_[0]), lo = hexval(cur_[1]);
-      if ((hi < 0) || (lo < 0))
-        fail_parse("invalid hex escape", pos());
-      cur_ += 2;
-      return (hi << 4) | lo;
-    }
-    default:
-      escaped = true;
-      return c;
-    }
-  }
-
-  // [...] : same walk as the reference's scanSet (lib/Scanner.cpp:137), whose
-  // corner cases (leading ']' or '-', "a-]" , escaped class as a range end)
-  // are part of the dialect
-  Tok bracket() {
-    Tok t; t.kind = kBytes; t.pos = pos();
-    bool xe = false, ye = false, invert = false;
-    int x = oneByte(xe);
-    if (x < 0) fail_parse("incomplete character class", pos());
-    if (!xe && (x == '^')) {
-      invert = true;
-      x = oneByte(xe);
-      if (x < 0) fail_parse("incomplete inverted character class", pos());
-    }
-    if (!xe && ((x == '-') || (x == ']'))) {
-      t.set.add(x);
-      x = oneByte(xe);
-      if (x < 0) fail_parse("unfinished character class", pos());
-    }
-    while (xe || (x != ']')) {
-      int y = oneByte(ye);
-      if (y < 0) fail_parse("unexpected end of character class", pos());
-      if (!ye && (y == '-')) {
-        y = oneByte(ye);
-        if (y < 0) fail_parse("unfinished character class range", pos());
-        if (!ye && (y == ']')) {
-          t.set.add(x);
-          t.set.add('-');
-          x = y; xe = ye;
-          continue;
-        }
-        if (x > y) fail_parse("backward character class range", pos());
-        t.set.addRange(x, y);
-        x = oneByte(xe);
-        if (x < 0) fail_parse("incomplete character class range", pos());
-      }
-      else {
-        addClassOrByte(t.set, x, xe);
-        x = y; xe = ye;
-      }
-    }
-    if (invert)
-      t.set.invert();
-    return t;
-  }
-
-  // {n} {n,m} {n,} {,m} {,} : reference scanClosure (lib/Scanner.cpp:196)
-  Tok braces() {
-    Tok t; t.kind = kRepeat; t.pos = pos();
-    t.min = -1; t.max = 0;
-    bool haveMax = false;
-    uint8_t c = 0;
-    while (cur_ < end_) {
-      c = *cur_++;
-      if (c == '}')
-        break;
-      if (c == ',') {
-        if (t.min >= 0) fail_parse("extra comma in count", pos());
-        t.min = t.max; t.max = 0; haveMax = false;
-      }
-      else if ((c >= '0') && (c <= '9')) {
-        t.max = 10 * t.max + (c - '0');
-        haveMax = true;
-      }
-      else
-        fail_parse("non-digit in count", pos());
-    }
-    if (c != '}') fail_parse("unclosed brace count", pos());
-    if ((t.min < 0) && (t.max == 0)) fail_parse("illegal count", pos());
-    if (!haveMax) t.max = -1;
-    if ((t.min == 0) && (t.max == 0)) fail_parse("zero brace count", pos());
-    if ((t.max >= 0) && (t.max < t.min)) fail_parse("backwards brace count", pos());
-    if (t.min < 0) t.min = t.max;
-    return t;
-  }
-
-  Tok ordinary() {
-    bool esc = false;
-    int c = oneByte(esc);
-    Tok t; t.pos = pos();
-    if (c < 0) {
-      t.kind = kEnd;
-      return t;
-    }
-    if (esc) {
-      if ((c >= '1') && (c <= '9'))
-        fail_parse("dfa does not support backreferences", pos());
-      if (c == 'i') {
-        t.kind = kFlags; t.flags = RED_B200_F_IGNORE_CASE;
-        return t;
-      }
-    }
-    t.kind = kBytes;
-    addClassOrByte(t.set, c, esc);
-    return t;
-  }
-
-  const uint8_t *beg_ = nullptr, *cur_ = nullptr, *end_ = nullptr;
-  size_t count_ = 0;
+  const std::vector<Token> &toks_;
+  uint64_t nestingLeft_;
 };
+
+// tree -> NFA fragment, children first (left before right, as the patterns read)
+NodeId emit(Nfa &nfa, const Tree &tree, int root) {
+  // post-order without recursion
+  std::vector<NodeId> made(tree.nodes.size(), 0);
+  std::vector<std::pair<int, bool>> todo{{root, false}};
+  while (!todo.empty()) {
+    const int n = todo.back().first;
+    const bool ready = todo.back().second;
+    todo.pop_back();
+    const Tree::Node &node = tree.nodes[n];
+    if (!ready) {
+      todo.push_back({n, true});
+      if (node.right >= 0)
+        todo.push_back({node.right, false});
+      if (node.left >= 0)
+        todo.push_back({node.left, false});
+      continue;
+    }
+    switch (node.kind) {
+    case Tree::Nothing: made[n] = nfa.goalNode(); break;  // the empty text
+    case Tree::Bytes: made[n] = nfa.oneOf(node.set); break;
+    case Tree::Wild: made[n] = nfa.wildcard(); break;
+    case Tree::Seq: made[n] = nfa.sequence(made[node.left], made[node.right]); break;
+    case Tree::Alt: made[n] = nfa.alternate(made[node.left], made[node.right]); break;
+    case Tree::Times: made[n] = nfa.repeat(made[node.left], node.lo, node.hi); break;
+    }
+  }
+  return made[root];
+}
+
+// prefixes and suffixes addAuto strips, and what they do to the flags
+struct Affix {
+  const char *text;
+  uint32_t set, clear;
+};
+const Affix kAutoHead[] = {{"^", 0, RED_B200_F_LOOSE_START}, {".*", RED_B200_F_LOOSE_START, 0}};
+const Affix kAutoTail[] = {{"$", 0, RED_B200_F_LOOSE_END}, {".*", RED_B200_F_LOOSE_END, 0}};
+
+bool startsWith(const uint8_t *p, size_t n, const char *s) {
+  size_t k = 0;
+  while (s[k] && (k < n) && (p[k] == static_cast<uint8_t>(s[k])))
+    ++k;
+  return s[k] == 0;
+}
+bool endsWith(const uint8_t *p, size_t n, const char *s) {
+  size_t m = 0;
+  while (s[m])
+    ++m;
+  return (n >= m) && startsWith(p + (n - m), m, s);
+}
 
 } // anonymous
 
 struct PatternParser::Impl {
   Nfa nfa;
-  Lexer lex;
-  Tok tok;
-  uint32_t flags = 0;
-  int depth = 0;
-  bool begun = false;
-  uint64_t parenBudget;
+  uint64_t nesting;
 
-  Impl(uint64_t states, uint64_t parens) : nfa(states), parenBudget(parens) {}
+  Impl(uint64_t states, uint64_t parens) : nfa(states), nesting(parens) {}
 
-  void advance() { tok = lex.next(); }
-
-  // expr := part ('|' part)*
-  NodeId expr() {
-    NodeId s = part();
-    if (!s) return 0;
-    while (tok.kind == kBar) {
-      advance();
-      NodeId o = part();
-      if (!o) return 0;
-      s = nfa.alternate(s, o);
-    }
-    return s;
-  }
-
-  // part := multi multi*
-  NodeId part() {
-    begun = false;
-    NodeId s = multi();
-    if (!s) return 0;
-    while ((tok.kind == kBytes) || (tok.kind == kOpen)) {
-      NodeId m = multi();
-      if (!m) return 0;
-      s = nfa.sequence(s, m);
-    }
-    return s;
-  }
-
-  // multi := unit (repeat | flags)? flags*
-  NodeId multi() {
-    NodeId s = unit();
-    if (!s) return 0;
-    if (tok.kind == kRepeat)
-      s = nfa.repeat(s, tok.min, tok.max);
-    else if (tok.kind == kFlags)
-      flags |= tok.flags;
-    else
-      return s;
-    advance();
-    while (tok.kind == kFlags) {
-      flags |= tok.flags;
-      advance();
-    }
-    return s;
-  }
-
-  // unit := flags* (bytes | '(' expr ')' | <empty>)
-  NodeId unit() {
-    while (tok.kind == kFlags) {
-      flags |= tok.flags;
-      advance();
-    }
-    NodeId s = 0;
-    switch (tok.kind) {
-    case kEnd:
-      if (begun) fail_parse("end reached, expected chars or (", tok.pos);
-      return nfa.goalNode();  // empty matches empty
-    case kBytes:
-      begun = true;
-      s = nfa.oneOf(tok.set);
-      break;
-    case kBar:
-      if (begun) fail_parse("expected chars or (, got |", tok.pos);
-      return nfa.goalNode();
-    case kOpen:
-      advance();
-      if (parenBudget == 0) fail_limit("nesting budget exceeded");
-      --parenBudget;
-      ++depth;
-      s = expr();
-      --depth;
-      ++parenBudget;
-      if (tok.kind != kClose) fail_parse("close parenthesis not found", tok.pos);
-      begun = true;
-      break;
-    case kClose:
-      if (begun || (depth <= 0)) fail_parse("unexpected )", tok.pos);
-      return nfa.goalNode();
-    default:
-      fail_parse("expected chars or (", tok.pos);
-    }
-    advance();
-    return s;
-  }
-
-  static void checkResult(int32_t result) {
-    if (result <= 0) fail_api("result must be positive");
-    if (result > std::numeric_limits<int32_t>::max() - 256) fail_api("result too large");
-  }
-
-  // wrap a parsed fragment: case folding, loose ends, end mark; then join it
-  // to the automaton's initial node (reference: Parser::add, lib/Parser.cpp:68-83)
-  void finishPattern(NodeId s, NodeId startWild, int32_t result, bool endMarkDone) {
+  /* A finished fragment becomes a rule: case folding, a ".*" in front and/or
+     behind for the loose ends, the end mark that carries the result id to the
+     subset construction, and the join with the rules added before.
+     markInside: the fragment already ends in its end mark (exact strings). */
+  void install(NodeId body, int32_t result, uint32_t flags, bool markInside) {
+    NodeId front = (flags & RED_B200_F_LOOSE_START) ? nfa.wildcard() : 0;
     if (flags & RED_B200_F_IGNORE_CASE)
-      s = nfa.foldCase(s);
-    if (startWild)
-      s = nfa.sequence(startWild, s);
-    if (flags & RED_B200_F_LOOSE_END) {
-      s = nfa.sequence(s, nfa.wildcard());
-      if (endMarkDone)
-        s = nfa.sequence(s, nfa.endMark(result));
-    }
-    if (!endMarkDone)
-      s = nfa.sequence(s, nfa.endMark(result));
-    nfa.joinInitial(s);
+      body = nfa.foldCase(body);
+    if (front)
+      body = nfa.sequence(front, body);
+    if (flags & RED_B200_F_LOOSE_END)
+      body = nfa.sequence(body, nfa.wildcard());
+    if (!markInside || (flags & RED_B200_F_LOOSE_END))
+      body = nfa.sequence(body, nfa.endMark(result));
+    nfa.joinInitial(body);
   }
 
-  void addRegex(const uint8_t *p, size_t n, int32_t result, uint32_t f) {
-    checkResult(result);
+  void begin(int32_t result) {
+    if (result <= 0)
+      fail_api("a result id must be positive");
+    if (result > std::numeric_limits<int32_t>::max() - 256)
+      fail_api("a result id this large is reserved");
     nfa.setGoal(result);
-    flags = f;
-    depth = 0;
-    NodeId startWild = (flags & RED_B200_F_LOOSE_START) ? nfa.wildcard() : 0;
-    lex.reset(p, n);
-    advance();
-    NodeId s = expr();
-    if (!s) fail_parse("uncategorized parsing error");
-    if (tok.kind != kEnd) fail_parse("trailing unparsed input");
-    finishPattern(s, startWild, result, false);
   }
 
-  // glob character class; simplified sibling of bracket()
-  // (reference: Parser::parseClass, lib/Parser.cpp:398)
-  NodeId globClass(const uint8_t *&ptr, const uint8_t *beg, const uint8_t *end) {
-    bool invert = false;
-    ByteSet set;
-    auto need = [&](const char *what) {
-      if (++ptr >= end) fail_parse(what, ptr - beg);
-      return *ptr;
-    };
-    uint8_t x = need("unclosed glob class");
-    if ((x == '^') || (x == '!')) {
-      invert = true;
-      x = need("unclosed inverted glob class");
-    }
-    if ((x == '-') || (x == ']')) {
-      set.add(x);
-      x = need("unclosed glob class");
-    }
-    while (x != ']') {
-      uint8_t y = need("unclosed glob class");
-      if (y == '-') {
-        y = need("unended glob class range");
-        if (y == ']') {
-          set.add(x);
-          set.add('-');
-          x = y;
-          continue;
-        }
-        if (x > y) fail_parse("backward glob class range", ptr - beg);
-        set.addRange(x, y);
-        x = need("unclosed glob class range");
-      }
-      else {
-        set.add(x);
-        x = y;
-      }
-    }
-    if (invert)
-      set.invert();
-    return nfa.oneOf(set);
+  void fromTokens(const std::vector<Token> &toks, int32_t result, uint32_t flags) {
+    begin(result);
+    // (the reference makes the leading wildcard before it parses: keep the
+    //  node order, it shows in nothing but makes traces comparable)
+    Tree tree;
+    bool fold = false;
+    Builder builder(toks, nesting);
+    const int root = builder.run(tree, fold);
+    if (fold)
+      flags |= RED_B200_F_IGNORE_CASE;
+    install(emit(nfa, tree, root), result, flags, false);
   }
 
-  void addGlob(const uint8_t *p, size_t n, int32_t result, uint32_t f) {
-    checkResult(result);
-    nfa.setGoal(result);
-    flags = f;
-    NodeId startWild = (flags & RED_B200_F_LOOSE_START) ? nfa.wildcard() : 0;
-    NodeId s = 0;
-    const uint8_t *end = p + n;
-    for (const uint8_t *ptr = p; ptr < end; ++ptr) {
-      ByteSet one;
-      switch (*ptr) {
-      case '*': s = nfa.sequence(s, nfa.wildcard()); break;
-      case '?': s = nfa.sequence(s, nfa.anyByte()); break;
-      case '[': s = nfa.sequence(s, globClass(ptr, p, end)); break;
-      default: one.add(*ptr); s = nfa.sequence(s, nfa.oneOf(one)); break;
-      }
-    }
-    if (!s) fail_parse("uncategorized parsing error");
-    finishPattern(s, startWild, result, false);
-  }
-
-  // byte-for-byte string (reference: Parser::addExact, lib/Parser.cpp:158):
-  // a chain of nodes; with a tight end the end mark hangs directly off the
-  // last node, with a loose end that node accepts before the wildcard is added
-  void addExact(const uint8_t *p, size_t n, int32_t result, uint32_t f) {
-    checkResult(result);
-    nfa.setGoal(result);
-    flags = f;
-    NodeId startWild = (flags & RED_B200_F_LOOSE_START) ? nfa.wildcard() : 0;
-    NodeId s = 0;
-    NodeId cur = nfa.node(0);
-    for (size_t i = 0; i < n; ++i) {
-      NodeId nx = nfa.node(0);
-      Edge e;
-      e.to = nx;
-      e.on.add(p[i]);
-      nfa[cur].out.push_back(e);
-      s = nfa.sequence(s, cur);
-      cur = nx;
-    }
+  /* Byte for byte: a chain of nodes, one per byte.  With a tight end the end
+     mark hangs directly off the last node; with a loose end that node accepts
+     and the wildcard and the mark follow (install). */
+  void exact(const uint8_t *p, size_t n, int32_t result, uint32_t flags) {
+    begin(result);
     const bool loose = (flags & RED_B200_F_LOOSE_END) != 0;
-    if (loose)
-      nfa[cur].result = result;
-    else {
-      NodeId g = nfa.goalNode();
+    std::vector<NodeId> chain(n + 1);
+    for (NodeId &id : chain)
+      id = nfa.node(0);
+    NodeId body = 0;
+    for (size_t i = 0; i < n; ++i) {
       Edge e;
-      e.to = g;
-      e.endMark = result;
-      nfa[cur].out.push_back(e);
+      e.to = chain[i + 1];
+      e.on.add(p[i]);
+      nfa[chain[i]].out.push_back(e);
+      body = nfa.sequence(body, chain[i]);
     }
-    finishPattern(s, startWild, result, true);
+    if (loose)
+      nfa[chain[n]].result = result;
+    else {
+      Edge e;
+      e.to = nfa.goalNode();
+      e.endMark = result;
+      nfa[chain[n]].out.push_back(e);
+    }
+    install(body, result, flags, true);
   }
 };
 
@@ -469,43 +600,45 @@ PatternParser::~PatternParser() { delete impl_; }
 void PatternParser::add(int lang, const uint8_t *p, size_t n, int32_t result,
                         uint32_t flags) {
   switch (lang) {
-  case RED_B200_LANG_RAW:
-    impl_->addRegex(p, n, result, flags);
-    break;
-  case RED_B200_LANG_AUTO: {
-    // grep-like heuristic (reference: Parser::addAuto, lib/Parser.cpp:92)
+  case RED_B200_LANG_AUTO:
+    // what grep users write: loose at both ends unless anchored with ^ / $,
+    // an explicit .* at either end is the same as no anchor, a leading \i
+    // folds case
     flags |= RED_B200_F_LOOSE_START | RED_B200_F_LOOSE_END;
-    if ((n >= 2) && (p[0] == '\\') && (p[1] == 'i')) {
-      p += 2; n -= 2;
+    if (startsWith(p, n, "\\i")) {
+      p += 2;
+      n -= 2;
       flags |= RED_B200_F_IGNORE_CASE;
     }
-    if ((n >= 1) && (p[0] == '^')) {
-      p += 1; n -= 1;
-      flags &= ~uint32_t(RED_B200_F_LOOSE_START);
-    }
-    else if ((n >= 2) && (p[0] == '.') && (p[1] == '*')) {
-      p += 2; n -= 2;
-      flags |= RED_B200_F_LOOSE_START;
-    }
-    if ((n >= 1) && (p[n - 1] == '$')) {
-      n -= 1;
-      flags &= ~uint32_t(RED_B200_F_LOOSE_END);
-    }
-    else if ((n >= 2) && (p[n - 2] == '.') && (p[n - 1] == '*')) {
-      n -= 2;
-      flags |= RED_B200_F_LOOSE_END;
-    }
-    impl_->addRegex(p, n, result, flags);
+    for (const Affix &a : kAutoHead)
+      if (startsWith(p, n, a.text)) {
+        const size_t m = (a.text[1] ? 2 : 1);
+        p += m;
+        n -= m;
+        flags = (flags | a.set) & ~a.clear;
+        break;
+      }
+    for (const Affix &a : kAutoTail)
+      if (endsWith(p, n, a.text)) {
+        n -= (a.text[1] ? 2 : 1);
+        flags = (flags | a.set) & ~a.clear;
+        break;
+      }
+    impl_->fromTokens(regexTokens(p, n), result, flags);
     break;
-  }
+  case RED_B200_LANG_RAW:
+    impl_->fromTokens(regexTokens(p, n), result, flags);
+    break;
   case RED_B200_LANG_GLOB:
-    impl_->addGlob(p, n, result, flags);
+    if (n == 0)
+      fail_parse("an empty glob");
+    impl_->fromTokens(globTokens(p, n), result, flags);
     break;
   case RED_B200_LANG_EXACT:
-    impl_->addExact(p, n, result, flags);
+    impl_->exact(p, n, result, flags);
     break;
   default:
-    fail_api("unrecognized regex language");
+    fail_api("unknown pattern language");
   }
 }
 
