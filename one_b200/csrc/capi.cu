@@ -149,9 +149,10 @@ __global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, 
    breadth-first order when there are none) and puts it on the device.  Buffers
    of an earlier image stay allocated until the program is freed: kernels
    launched with them may still be running on other streams. */
-static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bool asciiRows, HotDev &out) {
+static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bool asciiRows, bool acceptSticks,
+                              HotDev &out) {
   HotImage hot;
-  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, asciiRows, hot);
+  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, asciiRows, acceptSticks, hot);
   void *dTab = nullptr, *dC2v = nullptr, *dCodeOf = nullptr;
   cudaError_t err;
   if ((err = cudaMalloc(&dTab, hot.table.size())) != cudaSuccess)
@@ -183,6 +184,7 @@ static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bo
   hd.cPure = hot.cPure;
   hd.initCode = hot.initCode;
   hd.coverage = hot.coverage;
+  hd.acceptSticks = hot.acceptSticks ? 1 : 0;
   hd.wideTable = prog->smemTable ? 0 : 1;
   out = hd;
   return cudaSuccess;
@@ -243,8 +245,8 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
     const uint64_t highBytes = visits[2 * static_cast<size_t>(nStates) + 1];
     const bool ascii = prog->hotAsciiRows ? (prog->hotAsciiRows > 0) : (highBytes * 2000 <= allBytes);
     HotDev instant, whole;
-    if ((upload_hot(prog, visits.data(), ascii, instant) == cudaSuccess) &&
-        (upload_hot(prog, visits.data() + nStates, ascii, whole) == cudaSuccess)) {
+    if ((upload_hot(prog, visits.data(), ascii, true, instant) == cudaSuccess) &&
+        (upload_hot(prog, visits.data() + nStates, ascii, false, whole) == cudaSuccess)) {
       prog->hotDev[0] = instant;
       prog->hotDev[1] = whole;
     }
@@ -492,12 +494,12 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   if (const char *env = getenv("RED_B200_HOT_SLOT_BYTES"))
     prog->hotTune.slotBytes = atoi(env);
   if (prog->hotEnabled) {
-    if ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, prog->hotDev[0])) != cudaSuccess) {
+    if (((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, true, prog->hotDev[0])) != cudaSuccess) ||
+        ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, false, prog->hotDev[1])) != cudaSuccess)) {
       for (void *p : prog->hotBuffers)
         cudaFree(p);
       return cleanup(err, "upload of the hot image");
     }
-    prog->hotDev[1] = prog->hotDev[0];
   }
 
   *out = prog;

@@ -22,6 +22,7 @@ struct HotDev {
   uint32_t initCode = 0;
   uint32_t wideTable = 0;             // full table: 1 = u32 entries (global mode), 0 = u16
   uint32_t coverage = 1000;           // per mille of the profiled state entries that the hot set holds
+  uint32_t acceptSticks = 0;          // accepting codes loop to themselves (the image of style Instant)
 };
 
 struct HotTuning {

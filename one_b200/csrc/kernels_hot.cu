@@ -46,7 +46,7 @@ using namespace dev;
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr uint32_t kMaxBatch = 256;       // lines per batch (and per claimed sub-block)
-constexpr uint32_t kSortBuckets = 32;     // by the number of 16-byte chunks a lane walks
+constexpr uint32_t kSortBuckets = 256;    // by the line's length in bytes (longer lines share the first bucket)
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
 constexpr uint32_t kMaxSlots = 12;
 constexpr uint32_t kMaxProducers = 4;
@@ -208,6 +208,47 @@ __device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, 
   return lds8(c * STRIDE + hx.tab + byte);
 }
 
+/* A lane's line starts at any byte of its slot, but the lanes of a tile are to
+   walk in step *by position in their lines* (byte 0 of every line in the same
+   instruction: lines of a log look alike at equal positions, and lanes in like
+   states on like bytes share shared-memory words instead of colliding in the
+   banks - measured on the union64 corpus: 2.0 -> 1.3 wavefronts per lookup).
+   The bulk copy cannot shift a line (source and destination of cp.async.bulk
+   are 16-byte aligned, and the tensor form faults on a coordinate that is not:
+   tools/micro/tma_lines.cu), so the lane re-aligns in registers: two aligned
+   16-byte blocks, a two-level select by the word offset, a byte permute by the
+   byte offset - 16 ALU operations per 16 bytes, none in the load/store pipe. */
+struct Feed {
+  uint32_t blk;   // address of the next aligned block to load
+  uint4 cur;      // the block in front of it
+  uint32_t sel;   // PRMT selector of the byte offset: 0x3210 + 0x1111 * (start & 3)
+  bool w1, w2;    // bits of the word offset (start >> 2) & 3
+};
+__device__ __forceinline__ void feed_begin(Feed &f, const uint32_t textAddr) {
+  f.blk = textAddr & ~15u;
+  f.cur = lds128(f.blk);
+  f.blk += 16;
+  f.sel = 0x3210u + 0x1111u * (textAddr & 3u);
+  f.w1 = (textAddr & 4u) != 0;
+  f.w2 = (textAddr & 8u) != 0;
+}
+// the next 16 bytes of the line (whatever follows the line's end comes along)
+__device__ __forceinline__ uint4 feed_next(Feed &f) {
+  const uint4 n = lds128(f.blk);
+  f.blk += 16;
+  const uint32_t u0 = f.w1 ? f.cur.y : f.cur.x, u1 = f.w1 ? f.cur.z : f.cur.y, u2 = f.w1 ? f.cur.w : f.cur.z,
+                 u3 = f.w1 ? n.x : f.cur.w, u4 = f.w1 ? n.y : n.x, u5 = f.w1 ? n.z : n.y, u6 = f.w1 ? n.w : n.z;
+  const uint32_t y0 = f.w2 ? u2 : u0, y1 = f.w2 ? u3 : u1, y2 = f.w2 ? u4 : u2, y3 = f.w2 ? u5 : u3,
+                 y4 = f.w2 ? u6 : u4;
+  uint4 r;
+  r.x = __byte_perm(y0, y1, f.sel);
+  r.y = __byte_perm(y1, y2, f.sel);
+  r.z = __byte_perm(y2, y3, f.sel);
+  r.w = __byte_perm(y3, y4, f.sel);
+  f.cur = n;
+  return r;
+}
+
 /* The fast pass over one aligned 16-byte chunk of one line per lane: no
    decisions, only the largest code per quarter and the code at each quarter's
    end.  [lo, hi): the bytes of the chunk that belong to the line; FULL16: they
@@ -261,6 +302,65 @@ __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const
   }
   j = max(j, lo);
   return true;
+}
+
+/* The fast pass where codes that need a decision STICK (style Full: absorbing
+   and dead states, the sink; style Instant on an image built with
+   acceptSticks): no running maximum - the code behind the chunk tells whether
+   anything happened in it.  Returns that code, or 255 for a chunk of an
+   ASCII-row image that holds a byte >= 128.  hi: bytes of the chunk that
+   belong to the line (FULL16: all 16). */
+template <bool FULL16, int STRIDE>
+__device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, uint4 w, const uint32_t hi, uint32_t c) {
+  constexpr bool kAscii = STRIDE == static_cast<int>(kHotStrideAscii);
+  if (kAscii && !FULL16) {
+    /* Rows of 128 columns have four more bytes, and those hold the row's own
+       code: byte 0x80 is a step that changes nothing.  The bytes behind the
+       line's end are replaced by it, and the tail chunk is walked like a whole
+       one - no predicated lookups. */
+    const uint32_t lowBits = 8 * min(hi, 8u), highBits = 8 * (max(hi, 8u) - 8);
+    const unsigned long long keepLo = (lowBits >= 64) ? ~0ull : ((1ull << lowBits) - 1);
+    const unsigned long long keepHi = (highBits >= 64) ? ~0ull : ((1ull << highBits) - 1);
+    const uint32_t k0 = static_cast<uint32_t>(keepLo), k1 = static_cast<uint32_t>(keepLo >> 32),
+                   k2 = static_cast<uint32_t>(keepHi), k3 = static_cast<uint32_t>(keepHi >> 32);
+    w.x = (w.x & k0) | (0x80808080u & ~k0);
+    w.y = (w.y & k1) | (0x80808080u & ~k1);
+    w.z = (w.z & k2) | (0x80808080u & ~k2);
+    w.w = (w.w & k3) | (0x80808080u & ~k3);
+    // a byte >= 128 of the line itself (not the filler)
+    if ((((w.x & k0) | (w.y & k1) | (w.z & k2) | (w.w & k3)) & 0x80808080u) != 0)
+      return 255u;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (FULL16 || kAscii || (static_cast<uint32_t>(4 * q + jj) < hi))
+        c = hot_next<STRIDE>(hx, c, word, jj);
+  }
+  if (kAscii && FULL16 && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
+    return 255u;
+  return c;
+}
+
+/* Behind hot_run on an image whose accepting codes stick: how many bytes of
+   the chunk come before the one that entered the code the run ended in (the
+   same 16 lookups again, counting the codes below the limit). */
+template <int STRIDE>
+__device__ __forceinline__ uint32_t hot_locate(const HotCtx &hx, const uint4 &w, const uint32_t hi, uint32_t c) {
+  uint32_t n = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (static_cast<uint32_t>(4 * q + jj) < hi) {
+        c = hot_next<STRIDE>(hx, c, word, jj);
+        n += (c < hx.cLimit) ? 1u : 0u;
+      }
+  }
+  return n;
 }
 
 /* The careful pass: bytes [j, hi) of the chunk at chunkAddr one by one with
@@ -429,23 +529,28 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       }
       return s;
     };
-    /* The sort key of a line at slot offset off: the number of 16-byte chunks
-       a lane walks (the lanes of a tile are in step), longest first: the tile
-       that takes longest is then the first to be claimed, and the slot is not
-       held up by a late starter. */
+    /* The sort key of a line: its length in bytes, longest first (the lanes of
+       a tile walk in step from byte 0 of their lines, so a tile takes as long
+       as its longest line - and the tile that takes longest is the first to
+       be claimed, so the slot is not held up by a late starter).  Lines of
+       equal length are very often lines of the same shape, whose walks sit in
+       the same states at the same time. */
     auto bucketOf = [](uint32_t off, uint32_t len) -> uint32_t {
-      const uint32_t chunks = ((off != kUnstaged) && (len != 0)) ? min(31u, ((off & 15) + len + 15u) >> 4) : 0;
-      return 31 - chunks;
+      return ((off != kUnstaged) && (len != 0)) ? (kSortBuckets - 1) - min(kSortBuckets - 2, len) : kSortBuckets - 1;
     };
     // counting sort: bucket[] in, position in the sorted order out
     auto sortPositions = [&](const uint32_t (&bucket)[kPer], const bool (&valid)[kPer], uint32_t (&pos)[kPer]) {
-      sts32(histA + 4 * lane, 0);
+      static_assert(kSortBuckets == 256, "every lane scans eight buckets");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(histA + 32 * lane), "r"(0u) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(histA + 32 * lane + 16), "r"(0u) : "memory");
       __syncwarp();
 #pragma unroll
       for (uint32_t k = 0; k < kPer; ++k)
         pos[k] = valid[k] ? atomicAdd(sHist + bucket[k], 1u) : 0;
       __syncwarp();
-      const uint32_t mine = lds32(histA + 4 * lane);
+      // exclusive prefix over the buckets: lane l owns buckets 8 l .. 8 l + 7
+      const uint4 h0 = lds128(histA + 32 * lane), h1 = lds128(histA + 32 * lane + 16);
+      const uint32_t mine = h0.x + h0.y + h0.z + h0.w + h1.x + h1.y + h1.z + h1.w;
       uint32_t incl = mine;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -453,10 +558,23 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         if (lane >= static_cast<uint32_t>(d))
           incl += up;
       }
-      const uint32_t excl = incl - mine;
+      uint4 e0, e1;
+      e0.x = incl - mine;
+      e0.y = e0.x + h0.x;
+      e0.z = e0.y + h0.y;
+      e0.w = e0.z + h0.z;
+      e1.x = e0.w + h0.w;
+      e1.y = e1.x + h1.x;
+      e1.z = e1.y + h1.y;
+      e1.w = e1.z + h1.z;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(histA + 32 * lane), "r"(e0.x), "r"(e0.y), "r"(e0.z), "r"(e0.w) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(histA + 32 * lane + 16), "r"(e1.x), "r"(e1.y), "r"(e1.z), "r"(e1.w) : "memory");
+      __syncwarp();
 #pragma unroll
       for (uint32_t k = 0; k < kPer; ++k)
-        pos[k] += __shfl_sync(kFullMask, excl, bucket[k]);
+        if (valid[k])
+          pos[k] += lds32(histA + 4 * bucket[k]);
+      __syncwarp();
     };
     auto finishBatch = [&](uint32_t s, uint64_t first, uint32_t count) {
       if (lane == 0) {
@@ -597,14 +715,16 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       claimed = atomicAdd(blockCounter, 1ull);
     uint64_t block = __shfl_sync(kFullMask, claimed, 0);
     const long long tStart = hp.dbg ? clock64() : 0;
-    while (block * SUB < n) {
-      const long long tI0 = hp.dbg ? clock64() : 0;
-      const uint64_t base = block * SUB;
-      const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base));
-      // the sub-block's index entries, lane + 32 k: coalesced, all in flight at once
-      uint64_t st[kPer];
-      uint32_t ln[kPer];
-      bool valid[kPer];
+    /* The index entries of a sub-block (lane + 32 k: coalesced, all in flight
+       at once) are loaded one sub-block ahead - as soon as the registers of the
+       current one are free - so that their latency lies behind the wait for a
+       slot and the hand-over instead of in front of the sort. */
+    uint64_t st[kPer];
+    uint32_t ln[kPer];
+    bool valid[kPer];
+    auto loadIndex = [&](uint64_t blk) {
+      const uint64_t base = blk * SUB;
+      const uint32_t cnt = (base < n) ? static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base)) : 0;
 #pragma unroll
       for (uint32_t k = 0; k < kPer; ++k) {
         const uint32_t i = lane + 32 * k;
@@ -612,6 +732,12 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         st[k] = valid[k] ? __ldg(args.starts + base + i) : 0;
         ln[k] = valid[k] ? __ldg(args.lens + base + i) : 0;
       }
+    };
+    loadIndex(block);
+    while (block * SUB < n) {
+      const long long tI0 = hp.dbg ? clock64() : 0;
+      const uint64_t base = block * SUB;
+      const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base));
       if (lane == 0)
         claimed = atomicAdd(blockCounter, 1ull);  // the next sub-block; looked at below
       // the span of the sub-block's text
@@ -649,6 +775,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
             sts16(scrA + 4 * kMaxBatch + 2 * pos[k], min(ln[k], 0xffffu));
           }
         __syncwarp();
+        block = __shfl_sync(kFullMask, claimed, 0);
+        loadIndex(block);
         const uint32_t s = acquire();
         const uint32_t bytes = static_cast<uint32_t>(hiA - loA);
         if ((lane == 0) && bytes) {
@@ -666,9 +794,11 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         }
         finishBatch(s, base, cnt);
       }
-      else
+      else {
         slowPath(base, cnt);
-      block = __shfl_sync(kFullMask, claimed, 0);
+        block = __shfl_sync(kFullMask, claimed, 0);
+        loadIndex(block);
+      }
     }
     if (hp.dbg && (lane == 0)) {
       atomicAdd(hp.dbg + 0, static_cast<unsigned long long>(clock64() - tStart));
@@ -721,17 +851,20 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       if (mbar_try_wait(barsAddr + 8 * s, (qq / R) & 1)) {
         if (lds32_volatile(seqAddr) == qq)
           break;
-        __nanosleep(64);  // an earlier phase: batch qq - R is still to come
+        __nanosleep(200);  // an earlier phase: batch qq - R is still to come
       }
       // not there yet: is there such a batch at all?  (looked at every so
       // often only: a poll is a shared-memory wavefront the walkers want)
-      if ((spins & 15) == 15) {
+      if ((spins & 7) == 7) {
         if (qq >= lds32_volatile(ctlAddr + 12)) {
           ended = true;
           break;
         }
       }
-      __nanosleep(20);  // (a spinning warp takes issue slots from the walkers)
+      // a spinning warp takes issue slots from the walkers (measured: a wait
+      // with a suspend-time hint wakes up on every arrival at any barrier of
+      // the CTA and spins just as much)
+      __nanosleep(100);
     }
     if (ended)
       break;
@@ -782,127 +915,110 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     uint32_t code = hd.initCode;
     bool done = false;  // the outcome is in wk (the walk stopped, or it went on the full table)
 
+    bool active = has && (off != kUnstaged) && (len != 0);
+    const uint32_t tb = slotA + off;  // the line's first byte
+    Feed fd;
+    fd.blk = 0;
+    fd.cur = make_uint4(0, 0, 0, 0);
+    fd.sel = 0x3210u;
+    fd.w1 = fd.w2 = false;
+    if (active)
+      feed_begin(fd, tb);
+    uint32_t rem = active ? len : 0;  // bytes of the line from the current chunk on
+    // chunks that are whole for every lane of the tile: a loop without masks
+    const uint32_t kFull = __reduce_min_sync(kFullMask, active ? (len >> 4) : 0xffffffffu);
+
     if (DEFER) {
       /* Lean walk for the styles that end at the first state that needs a
-         decision.  Live per lane: the address of the current chunk, the bytes
-         left from there to the end of the line, the state; a flagged lane
-         freezes them (plus the byte its careful pass starts at) and steps
-         aside.  A chunk is loaded right before it is walked: the other warps
-         cover that latency, and there is no second chunk to keep. */
-      bool active = has && (off != kUnstaged) && (len != 0);
-      uint32_t addr = (slotA + off) & ~15u;
-      uint32_t rem = active ? ((slotA + off) & 15u) + len : 0;   // bytes from addr to the line's end
-      uint32_t pj = 0xffu;                                        // flagged: first byte of the careful pass
-      const uint32_t nCh = (rem + 15u) >> 4;
-      const uint32_t kMin = __reduce_min_sync(kFullMask, active ? nCh : 0xffffffffu);
-      if (active) {
-        // the head chunk
-        const uint4 w = lds128(addr);
-        uint32_t j = 0, cj = 0;
-        if (hot_fast<false, STRIDE>(hx, w, (slotA + off) & 15u, min(16u, rem), code, j, cj)) {
-          pj = j;
-          code = cj;
-          active = false;
-        }
-        else if (rem <= 16)
-          active = false;
-        else {
-          addr += 16;
-          rem -= 16;
-        }
-      }
-      if (kMin != 0xffffffffu) {
-        // chunks 1 .. kMin-2 are whole for every lane still walking
-        for (uint32_t k = 1; k + 1 < kMin; ++k) {
+         decision, on an image where such a state sticks.  Live per lane: the
+         text feed, the bytes left, the state in front of the chunk; a flagged
+         lane freezes them and steps aside. */
+      uint32_t fc = 0xffffffffu;  // flagged: the code the chunk's run ended in
+      if (kFull != 0xffffffffu) {
+#pragma unroll 2
+        for (uint32_t k = 0; k < kFull; ++k) {
           if (active) {
-            const uint4 w = lds128(addr);
-            uint32_t j = 0, cj = 0;
-            if (hot_fast<true, STRIDE>(hx, w, 0, 16, code, j, cj)) {
-              pj = j;
-              code = cj;
+            const uint4 w = feed_next(fd);
+            const uint32_t c2 = hot_run<true, STRIDE>(hx, w, 16, code);
+            if (c2 >= hx.cLimit) {
+              fc = c2;
               active = false;
             }
             else {
-              addr += 16;
+              code = c2;
               rem -= 16;
             }
           }
         }
       }
+      active = active && (rem != 0);
       while (__any_sync(kFullMask, active)) {
         if (active) {
-          const uint4 w = lds128(addr);
-          uint32_t j = 0, cj = 0;
-          if (hot_fast<false, STRIDE>(hx, w, 0, min(16u, rem), code, j, cj)) {
-            pj = j;
-            code = cj;
+          const uint4 w = feed_next(fd);
+          const uint32_t c2 = hot_run<false, STRIDE>(hx, w, min(16u, rem), code);
+          if (c2 >= hx.cLimit) {
+            fc = c2;
             active = false;
           }
-          else if (rem <= 16)
-            active = false;
           else {
-            addr += 16;
-            rem -= 16;
+            code = c2;
+            if (rem <= 16)
+              active = false;
+            else
+              rem -= 16;
           }
         }
       }
-      if (pj != 0xffu) {
-        // the flagged chunk byte by byte; a walk that goes on behind it (it left
-        // the hot set and came back) takes the rest of its line on its own
-        wk.begin(pd);
-        const uint32_t tb = slotA + off;
-        bool stopped = hot_careful<STYLE, STRIDE>(pd, hx, addr, pj, min(16u, rem), addr - tb, code, wk);
-        while (!stopped && (rem > 16)) {
-          addr += 16;
-          rem -= 16;
-          const uint4 w = lds128(addr);
-          stopped = hot_chunk<STYLE, false, STRIDE>(pd, hx, w, addr, 0, min(16u, rem), addr - tb, code, wk);
+      if (__any_sync(kFullMask, fc != 0xffffffffu)) {
+        /* Flagged lanes, together.  Nearly always the run ended in a state
+           that settles the line: an accepting one (Instant: where it was
+           entered is counted out by a second run over the chunk), an absorbing
+           or a dead one (no position needed).  What is left - the walk left
+           the hot set, a byte >= 128 on 128-column rows - goes byte by byte
+           from the chunk's start, to the line's end if it has to. */
+        const bool settled = (fc != 0xffffffffu) && (fc != 255u) && (fc != hx.sink);
+        if (settled) {
+          if ((STYLE == STY_INSTANT) && (fc < hx.cPure)) {
+            Feed f2;
+            feed_begin(f2, tb + (len - rem));
+            const uint4 w = feed_next(f2);
+            wk.mend = (len - rem) + hot_locate<STRIDE>(hx, w, min(16u, rem), code) + 1;
+            wk.absorbed = false;
+            done = true;
+          }
+          code = fc;
         }
-        done = true;
+        else if (fc != 0xffffffffu) {
+          wk.begin(pd);
+          hot_careful<STYLE, STRIDE>(pd, hx, tb, len - rem, len, 0, code, wk);
+          done = true;
+        }
       }
     }
     else {
-      bool active = has && (off != kUnstaged) && (len != 0);
-      const uint32_t tb = slotA + off;
-      const uint32_t skip = active ? (tb & 15) : 0;
-      const uint32_t blk = tb - skip;
-      const uint32_t total = skip + len;
       wk.begin(pd);
       done = true;
-      uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-      if (active)
-        cur = lds128(blk);
-      uint32_t k = 0;
-      // one chunk of this lane; full16: no byte of it outside the line
-      auto step = [&](auto full16) {
-        const uint32_t rem = total - k * 16;
-        const uint32_t lo = (!full16.value && (k == 0)) ? skip : 0;
-        const uint32_t hi = full16.value ? 16u : min(16u, rem);
-        const bool lastChunk = !full16.value && (rem <= 16);
-        if (!lastChunk)
-          nxt = lds128(blk + 16 * (k + 1));
-        const bool stopped = hot_chunk<STYLE, full16.value, STRIDE>(pd, hx, cur, blk + 16 * k, lo, hi, k * 16 - skip, code, wk);
-        if (stopped || lastChunk)
-          active = false;
-      };
-      const uint32_t kMin = __reduce_min_sync(kFullMask, active ? ((total + 15u) >> 4) : 0xffffffffu);
-      if (kMin != 0xffffffffu) {
-        if (active)
-          step(std::false_type());  // the head chunk
-        ++k;
-        cur = nxt;
-        // chunks 1 .. kMin-2 are whole for every lane still walking: a loop
-        // without masks or per-lane bookkeeping
-        for (; k + 1 < kMin; ++k) {
-          if (active)
-            step(std::true_type());
-          cur = nxt;
+      uint32_t at = 0;  // position of the current chunk in the line
+      if (kFull != 0xffffffffu) {
+        for (uint32_t k = 0; k < kFull; ++k) {
+          if (active) {
+            const uint4 w = feed_next(fd);
+            if (hot_chunk<STYLE, true, STRIDE>(pd, hx, w, tb + at, 0, 16, at, code, wk))
+              active = false;
+            at += 16;
+          }
         }
-        while (__any_sync(kFullMask, active)) {
-          if (active)
-            step(std::false_type());
-          ++k;
-          cur = nxt;
+      }
+      while (__any_sync(kFullMask, active)) {
+        if (active) {
+          if (at >= len)
+            active = false;
+          else {
+            const uint4 w = feed_next(fd);
+            if (hot_chunk<STYLE, false, STRIDE>(pd, hx, w, tb + at, 0, min(16u, len - at), at, code, wk))
+              active = false;
+            at += 16;
+          }
         }
       }
     }
@@ -1110,7 +1226,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   hp.tilesPerBatch = batchLines / 32;
   hp.oMeta = take(slots * hp.metaBytes, 16);
   hp.oSlots = take(slots * slotBytes, 128);
-  const size_t smemBytes = at + 256;  // alignment pad
+  const size_t smemBytes = at + 256 + 32;  // alignment pad; a feed reads one block past its line's last
   if (smemBytes > static_cast<size_t>(geo.maxSmemOptin))
     return cudaErrorNotSupported;
 
@@ -1119,7 +1235,9 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
     return err;
   // careful passes together at the end of a tile - unless the hot set leaves
   // so much out that lanes would often go on alone behind theirs
-  const bool defer = tune.defer ? (tune.defer > 0) : (hd.coverage >= 999);
+  bool defer = tune.defer ? (tune.defer > 0) : (hd.coverage >= 999);
+  if ((style == STY_INSTANT) && !hd.acceptSticks)
+    defer = false;  // the lean walk needs an image whose accepting codes stick
   constexpr int W = kHotStrideWide, A = kHotStrideAscii;
   const bool ascii = hd.stride == kHotStrideAscii;
   auto kern = (style == STY_LAST)

@@ -365,7 +365,8 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
 }
 
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
-                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, HotImage &hot) {
+                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, bool acceptSticks,
+                     HotImage &hot) {
   const uint32_t n = pp.stateCount;
   const uint32_t C = pp.classCount;
   maxHot = std::max(1u, std::min(maxHot, kHotMax));
@@ -441,6 +442,9 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
   hot.cAbs = below(img.absV);
   hot.cPure = below(img.pureV);
   hot.initCode = hot.codeOf[init];
+  // (a walk that STARTS in an accepting state leaves it by its real row)
+  if (hot.initCode >= hot.cAccept)
+    acceptSticks = false;
   hot.stride = asciiRows ? kHotStrideAscii : kHotStrideWide;
   const uint32_t columns = hot.stride - 4;
   const size_t bytes = (static_cast<size_t>(hot.nHot + 1) * hot.stride + 15) & ~size_t(15);
@@ -448,8 +452,13 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
   for (uint32_t c = 0; c < hot.nHot; ++c) {
     uint8_t *row = &hot.table[static_cast<size_t>(c) * hot.stride];
     for (uint32_t b = 0; b < columns; ++b)
-      row[b] = hot.codeOf[nextOf(cand[c], b)];
+      row[b] = (acceptSticks && (c >= hot.cAccept)) ? static_cast<uint8_t>(c) : hot.codeOf[nextOf(cand[c], b)];
+    // the four bytes behind a row of 128 columns: "byte 0x80 .. 0x83" leaves
+    // the state as it is (the staged kernel fills a line's last chunk with it)
+    for (uint32_t b = columns; b < hot.stride; ++b)
+      row[b] = static_cast<uint8_t>(c);
   }
+  hot.acceptSticks = acceptSticks;
 }
 
 } // namespace red_b200

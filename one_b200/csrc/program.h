@@ -139,13 +139,20 @@ struct HotImage {
   uint32_t initCode = 0;
   uint32_t stride = kHotStrideWide; // bytes per row
   uint32_t coverage = 1000;       // per mille of the counted state entries that the hot set holds
+  bool acceptSticks = false;      // rows of accepting codes loop to themselves (see build_hot_image)
   std::vector<uint8_t> table;     // (nHot + 1) * stride, padded to 16 bytes
   std::vector<uint32_t> codeToV;  // 256 entries: v of the full image
   std::vector<uint8_t> codeOf;    // by renumbered state index; nHot = not hot
 };
 
-// visits: per renumbered state index, or nullptr (breadth-first order then)
+/* visits: per renumbered state index, or nullptr (breadth-first order then).
+   acceptSticks: the image of style Instant, whose walk ends in the first
+   accepting state - every accepting code's row loops to itself, so that a code
+   >= cAccept, once reached, is still there at the end of a 16-byte chunk and
+   the fast pass needs no running maximum (the sink and the absorbing and dead
+   states stick anyway). */
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
-                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, HotImage &hot);
+                     const uint64_t *visits, uint32_t maxHot, bool asciiRows, bool acceptSticks,
+                     HotImage &hot);
 
 } // namespace red_b200
