@@ -318,11 +318,12 @@ __device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, uint4 w, const uin
        code: byte 0x80 is a step that changes nothing.  The bytes behind the
        line's end are replaced by it, and the tail chunk is walked like a whole
        one - no predicated lookups. */
-    const uint32_t lowBits = 8 * min(hi, 8u), highBits = 8 * (max(hi, 8u) - 8);
-    const unsigned long long keepLo = (lowBits >= 64) ? ~0ull : ((1ull << lowBits) - 1);
-    const unsigned long long keepHi = (highBits >= 64) ? ~0ull : ((1ull << highBits) - 1);
-    const uint32_t k0 = static_cast<uint32_t>(keepLo), k1 = static_cast<uint32_t>(keepLo >> 32),
-                   k2 = static_cast<uint32_t>(keepHi), k3 = static_cast<uint32_t>(keepHi >> 32);
+    // k_q: the low min(max(hi - 4 q, 0), 4) bytes of word q
+    const int h = static_cast<int>(hi);
+    const uint32_t k0 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h, 0), 4)));
+    const uint32_t k1 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 4, 0), 4)));
+    const uint32_t k2 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 8, 0), 4)));
+    const uint32_t k3 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 12, 0), 4)));
     w.x = (w.x & k0) | (0x80808080u & ~k0);
     w.y = (w.y & k1) | (0x80808080u & ~k1);
     w.z = (w.z & k2) | (0x80808080u & ~k2);
@@ -761,7 +762,11 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       if ((hi >= lo) && (hiA - loA <= hp.slotBytes)) {
         // the usual shape: the whole sub-block's text fits a slot (whatever the
         // order of its lines).  Sort in the scratch, then take a slot, start
-        // the copy and hand the sorted arrays over.
+        // the copy and hand the sorted arrays over.  The text is asked into L2
+        // now: the copy itself starts only when a slot is free, and what it
+        // takes from there on is time the slot stands empty.
+        if ((lane == 0) && (hiA > loA))
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(loA), "r"(static_cast<uint32_t>(hiA - loA)) : "memory");
         uint32_t bucket[kPer], pos[kPer];
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k)
@@ -848,7 +853,11 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     bool ended = false;
     const uint32_t seqAddr = sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq;
     for (uint32_t spins = 0;; ++spins) {
-      if (mbar_try_wait(barsAddr + 8 * s, (qq / R) & 1)) {
+      // (the wait is left to the hardware, which suspends the warp until the
+      // barrier's phase completes - or, as measured, until anything arrives at
+      // any barrier of the CTA; still the quickest to notice: sleeping 20 or
+      // 100 ns between polls instead costs 3 %)
+      if (mbar_try_wait_for(barsAddr + 8 * s, (qq / R) & 1, 4000)) {
         if (lds32_volatile(seqAddr) == qq)
           break;
         __nanosleep(200);  // an earlier phase: batch qq - R is still to come
@@ -861,10 +870,6 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           break;
         }
       }
-      // a spinning warp takes issue slots from the walkers (measured: a wait
-      // with a suspend-time hint wakes up on every arrival at any barrier of
-      // the CTA and spins just as much)
-      __nanosleep(100);
     }
     if (ended)
       break;
