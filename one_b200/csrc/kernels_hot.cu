@@ -452,7 +452,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
   const uint32_t nConsumers = (blockDim.x >> 5) - P;
   const uint32_t R = hp.nSlots;
   const uint32_t TPB = hp.tilesPerBatch;
-  const uint32_t barsAddr = sBase + hp.oBars;      // full[0..R), empty[0..R)
+  const uint32_t barsAddr = sBase + hp.oBars;      // full[0..R), empty[0..R), ready[0..R)
   const uint32_t ctlAddr = sBase + hp.oCtl;        // +0 ticket, +4 next batch number, +8 producers done, +12 endQ, +16 batches that have their slot
   const uint64_t n = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
 
@@ -474,6 +474,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       for (uint32_t s = 0; s < R; ++s) {
         mbar_init(barsAddr + 8 * s, 1);
         mbar_init(barsAddr + 8 * (R + s), TPB);
+        mbar_init(barsAddr + 8 * (2 * R + s), 1);
         sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaDone, 0);
         sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq, 0xffffffffu);
       }
@@ -852,19 +853,22 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        is even published.  The slot's sequence number says whose phase it was. */
     bool ended = false;
     const uint32_t seqAddr = sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq;
+    /* The bytes of a bulk copy arrive at full[s] piece by piece, and every
+       piece wakes whoever waits there (measured: ~50 wake-ups per wait, the
+       waiters' instructions a quarter of all the kernel issued).  So only the
+       warp with the batch's first tile waits at full[s]; it then arrives at
+       ready[s], where the others sleep through the copy and wake up once. */
+    const uint32_t waitBar = barsAddr + 8 * ((t == 0) ? s : 2 * R + s);
     for (uint32_t spins = 0;; ++spins) {
-      // (the wait is left to the hardware, which suspends the warp until the
-      // barrier's phase completes - or, as measured, until anything arrives at
-      // any barrier of the CTA; still the quickest to notice: sleeping 20 or
-      // 100 ns between polls instead costs 3 %)
-      if (mbar_try_wait_for(barsAddr + 8 * s, (qq / R) & 1, 4000)) {
+      if (mbar_try_wait(waitBar, (qq / R) & 1)) {
         if (lds32_volatile(seqAddr) == qq)
           break;
         __nanosleep(200);  // an earlier phase: batch qq - R is still to come
       }
-      // not there yet: is there such a batch at all?  (looked at every so
-      // often only: a poll is a shared-memory wavefront the walkers want)
-      if ((spins & 7) == 7) {
+      // not there yet: is there such a batch at all?  (at full[s] looked at
+      // every so often only: a poll is a shared-memory wavefront the walkers
+      // want; a wait that nothing ends comes back after a few microseconds)
+      if ((t != 0) || ((spins & 7) == 7)) {
         if (qq >= lds32_volatile(ctlAddr + 12)) {
           ended = true;
           break;
@@ -873,6 +877,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     }
     if (ended)
       break;
+    if ((t == 0) && (lane == 0))
+      mbar_arrive(barsAddr + 8 * (2 * R + s));
     const long long tc1 = hp.dbg ? clock64() : 0;
     const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
     const uint32_t cnt = lds32(mA + kMetaCnt);
@@ -1182,7 +1188,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   hp.nProducers = producers;
   hp.prodBytes = (kProdBytes + 15u) & ~15u;
   hp.oC2v = take(2048, 16);
-  hp.oBars = take(2 * kMaxSlots * 8, 16);
+  hp.oBars = take(3 * kMaxSlots * 8, 16);
   hp.oCtl = take(32, 16);
   hp.oProd = take(producers * hp.prodBytes, 16);
   hp.oDeal = take(32 * 32, 16);
