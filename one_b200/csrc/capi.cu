@@ -150,15 +150,16 @@ __global__ void span_check_kernel(const uint64_t *starts, const uint32_t *lens, 
    of an earlier image stay allocated until the program is freed: kernels
    launched with them may still be running on other streams. */
 static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bool asciiRows, bool acceptSticks,
-                              HotDev &out) {
+                              HotDev &out, uint32_t wideStates = 0) {
   HotImage hot;
-  build_hot_image(prog->parsed, prog->img, visits, prog->hotMaxStates, asciiRows, acceptSticks, hot);
+  build_hot_image(prog->parsed, prog->img, visits, wideStates ? wideStates : prog->hotMaxStates, asciiRows,
+                  acceptSticks, hot, wideStates != 0);
   void *dTab = nullptr, *dC2v = nullptr, *dCodeOf = nullptr;
   cudaError_t err;
   if ((err = cudaMalloc(&dTab, hot.table.size())) != cudaSuccess)
     return err;
   prog->hotBuffers.push_back(dTab);
-  if ((err = cudaMalloc(&dC2v, 1024)) != cudaSuccess)
+  if ((err = cudaMalloc(&dC2v, hot.codeToV.size() * 4)) != cudaSuccess)
     return err;
   prog->hotBuffers.push_back(dC2v);
   if ((err = cudaMalloc(&dCodeOf, hot.codeOf.size())) != cudaSuccess)
@@ -166,7 +167,7 @@ static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bo
   prog->hotBuffers.push_back(dCodeOf);
   if ((err = cudaMemcpy(dTab, hot.table.data(), hot.table.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
     return err;
-  if ((err = cudaMemcpy(dC2v, hot.codeToV.data(), 1024, cudaMemcpyHostToDevice)) != cudaSuccess)
+  if ((err = cudaMemcpy(dC2v, hot.codeToV.data(), hot.codeToV.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
     return err;
   if ((err = cudaMemcpy(dCodeOf, hot.codeOf.data(), hot.codeOf.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
     return err;
@@ -178,6 +179,7 @@ static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bo
   hd.codeOf = static_cast<const uint8_t *>(dCodeOf);
   hd.tableBytes = static_cast<uint32_t>(hot.table.size());
   hd.stride = hot.stride;
+  hd.entryBytes = hot.entryBytes;
   hd.nHot = hot.nHot;
   hd.cAccept = hot.cAccept;
   hd.cAbs = hot.cAbs;
@@ -196,7 +198,8 @@ static cudaError_t upload_hot(red_b200_program *prog, const uint64_t *visits, bo
    style Instant, whose walks end at the first accepting state, one for the
    styles that go on.  Synchronises the stream once.  Skipped while the stream
    is being captured. */
-static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStream_t stream) {
+static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStream_t stream,
+                        bool realLines = true) {
   std::lock_guard<std::mutex> lock(prog->hotMu);
   if (prog->hotProfiled.load())
     return;
@@ -236,7 +239,7 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
     return;
   }
   const uint64_t samples = (args.nLines + stride - 1) / stride;
-  if (samples)
+  if (samples && realLines)
     prog->avgLineBytes.store(static_cast<uint32_t>(std::min<uint64_t>(visits[2 * static_cast<size_t>(nStates)] / samples, 1u << 20)));
   {
     // rows of 128 columns when (nearly) all of the text is ASCII: half the
@@ -249,6 +252,19 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
         (upload_hot(prog, visits.data() + nStates, ascii, false, whole) == cudaSuccess)) {
       prog->hotDev[0] = instant;
       prog->hotDev[1] = whole;
+      // the long-stream matcher's: every state the text enters, two-byte codes
+      // if a byte cannot name them all (as many as fit beside the text stages)
+      prog->hotStream = whole;
+      if (whole.coverage < 1000) {
+        const uint32_t rowBytes = (ascii ? 128u : 256u) * 2 + 4;
+        const uint32_t fit = (prog->geo.maxSmemOptin > 140 * 1024) ? (prog->geo.maxSmemOptin - 140 * 1024) / rowBytes : 0;
+        HotDev wide;
+        if ((fit > kHotMax + 1) &&
+            (upload_hot(prog, visits.data() + nStates, ascii, false, wide, std::min(fit - 1, kHotMaxWide)) == cudaSuccess))
+          prog->hotStream = wide;
+        else
+          cudaGetLastError();
+      }
     }
     else
       cudaGetLastError();
@@ -500,6 +516,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
         cudaFree(p);
       return cleanup(err, "upload of the hot image");
     }
+    prog->hotStream = prog->hotDev[1];
   }
 
   *out = prog;
@@ -1388,7 +1405,44 @@ int red_b200_match_stream_device(const red_b200_program *cprog,
   DeviceGuard guard(prog->device);
   std::string why;
   int launches = 0;
-  int rc = match_stream(prog->dev, prog->smemTable, prog->img, prog->geo,
+  /* The main walk runs on the hot image (stream_hot_kernel).  A program that
+     has seen no batch yet has no profile: take one from this text - pieces of
+     256 bytes spread over it, each walked from the initial state (what a DFA
+     that forgets enters behind an arbitrary cut is what it enters anywhere). */
+  HotDev hot;
+  bool haveHot = false;
+  if (prog->hotEnabled) {
+    if (prog->hotProfileWanted && !prog->hotProfiled.load() && (len >= (1u << 20))) {
+      const uint64_t pieces = 32768, pieceLen = 256;
+      const uint64_t step = (len - pieceLen) / pieces;
+      std::vector<uint64_t> hs(pieces);
+      std::vector<uint32_t> hl(pieces, static_cast<uint32_t>(pieceLen));
+      for (uint64_t i = 0; i < pieces; ++i)
+        hs[i] = i * step;
+      uint64_t *dS = nullptr;
+      uint32_t *dL = nullptr;
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if ((cudaMalloc(&dS, pieces * 8) == cudaSuccess) && (cudaMalloc(&dL, pieces * 4) == cudaSuccess) &&
+          (cudaMemcpyAsync(dS, hs.data(), pieces * 8, cudaMemcpyHostToDevice, st) == cudaSuccess) &&
+          (cudaMemcpyAsync(dL, hl.data(), pieces * 4, cudaMemcpyHostToDevice, st) == cudaSuccess) &&
+          (cudaStreamSynchronize(st) == cudaSuccess)) {
+        BatchArgs a{};
+        a.text = d_text;
+        a.starts = dS;
+        a.lens = dL;
+        a.nLines = pieces;
+        profile_hot(prog, a, st, false);
+      }
+      else
+        cudaGetLastError();
+      cudaFree(dS);
+      cudaFree(dL);
+    }
+    std::lock_guard<std::mutex> lock(prog->hotMu);
+    hot = prog->hotStream;
+    haveHot = true;
+  }
+  int rc = match_stream(prog->dev, prog->smemTable, prog->img, haveHot ? &hot : nullptr, prog->geo,
                         d_text, len, style, out,
                         static_cast<cudaStream_t>(stream), &launches, why);
   prog->launches += launches;

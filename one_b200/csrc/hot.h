@@ -13,9 +13,10 @@ namespace red_b200 {
 // device copy of a HotImage (program.h); all pointers are device pointers
 struct HotDev {
   const uint8_t *table = nullptr;     // (nHot + 1) rows of `stride` bytes
-  uint32_t stride = 0;                // kHotStrideWide or kHotStrideAscii (program.h)
-  const uint32_t *codeToV = nullptr;  // [256]
-  const uint8_t *codeOf = nullptr;    // [stateCount] by renumbered state index
+  uint32_t stride = 0;                // columns * entryBytes + 4 (program.h)
+  uint32_t entryBytes = 1;            // 1, or 2 (the long-stream matcher's image: more than 255 states)
+  const uint32_t *codeToV = nullptr;  // [max(256, nHot + 1)]
+  const uint8_t *codeOf = nullptr;    // [stateCount] entries of entryBytes, by renumbered state index
   uint32_t tableBytes = 0;            // multiple of 16
   uint32_t nHot = 0;                  // the sink code
   uint32_t cAccept = 0, cAbs = 0, cPure = 0;

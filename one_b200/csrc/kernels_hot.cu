@@ -31,9 +31,7 @@
    as many lines per batch as fit a slot.  A line longer than a slot is walked
    from global memory on the full table. */
 
-#include "hot.h"
-#include "program.h"
-#include "walk.cuh"
+#include "hot_walk.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -42,9 +40,6 @@ namespace red_b200 {
 
 namespace {
 
-using namespace dev;
-
-constexpr unsigned kFullMask = 0xffffffffu;
 constexpr uint32_t kMaxBatch = 256;       // lines per batch (and per claimed sub-block)
 constexpr uint32_t kSortBuckets = 256;    // by the line's length in bytes (longer lines share the first bucket)
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
@@ -75,364 +70,6 @@ constexpr uint32_t kProdMeta = 0;                             // sorted idx/off/
 constexpr uint32_t kProdOff = kProdMeta + 6 * kMaxBatch;      // u16[256] text offsets by line (gather path)
 constexpr uint32_t kProdHist = kProdOff + 2 * kMaxBatch;      // u32[kSortBuckets]
 constexpr uint32_t kProdBytes = kProdHist + 4 * kSortBuckets;
-
-// ---- PTX helpers ----------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-               "selp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// as mbar_try_wait, but the hardware may keep the thread suspended for up to `ns`
-__device__ __forceinline__ bool mbar_try_wait_for(uint32_t bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-               "selp.u32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// 1-D bulk-async copy global -> shared; completion counted on `bar` in bytes
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-  uint32_t r;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint32_t r;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t r;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
-  return r;
-}
-__device__ __forceinline__ uint32_t lds32_volatile(uint32_t a) {
-  uint32_t r;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
-  return r;
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<uint16_t>(v)) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-
-// (AnyTable - the full table wherever it lives, the cold path - is in walk.cuh)
-
-/* Walks n bytes at p (generic pointer: a slot or global memory) on the full
-   table with the reference's per-byte decisions (walk.cuh).  True = the walk is
-   over; wk.mstart then holds the number of bytes consumed.  Rare: lanes that
-   left the hot set, lines longer than a slot. */
-template <int STYLE>
-__device__ __noinline__ bool cold_bytes(const ProgramDev &pd, uint32_t wide, Walk<STYLE, false> &wk,
-                                        const uint8_t *p, uint32_t n, uint32_t pos) {
-  const AnyTable tab = any_table(pd, wide);
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t co = __ldg(pd.clsOffset + p[i]);
-    if (wk.step(pd, tab, co, pos + i)) {
-      wk.mstart = pos + i + 1;
-      return true;
-    }
-  }
-  return false;
-}
-
-/* One byte on the full table (a lane that left the hot set); true = the walk is
-   over. */
-template <int STYLE>
-__device__ __noinline__ bool cold_step(const ProgramDev &pd, uint32_t wide, Walk<STYLE, false> &wk,
-                                       uint32_t byte, uint32_t pos) {
-  const AnyTable tab = any_table(pd, wide);
-  return wk.step(pd, tab, __ldg(pd.clsOffset + byte), pos);
-}
-
-struct HotCtx {
-  uint32_t tab;     // shared address of the hot table
-  uint32_t c2v;     // shared address of codeToV; codeToResult sits 1024 bytes behind it
-  uint32_t sink;    // = nHot
-  uint32_t cLimit;  // codes >= cLimit need a decision
-  uint32_t cAbs, cPure;
-  uint32_t wide;
-  const uint8_t *codeOf;
-};
-
-// hx.tab has a zero low byte, so PRMT puts a text byte and the table base
-// together in one instruction: a step is PRMT, IMAD, LDS.U8
-template <int STRIDE>
-__device__ __forceinline__ uint32_t hot_next(const HotCtx &hx, uint32_t c, uint32_t word, int jj) {
-  return lds8(c * STRIDE + __byte_perm(word, hx.tab, 0x7650 | jj));
-}
-template <int STRIDE>
-__device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, uint32_t byte) {
-  return lds8(c * STRIDE + hx.tab + byte);
-}
-
-/* A lane's line starts at any byte of its slot, but the lanes of a tile are to
-   walk in step *by position in their lines* (byte 0 of every line in the same
-   instruction: lines of a log look alike at equal positions, and lanes in like
-   states on like bytes share shared-memory words instead of colliding in the
-   banks - measured on the union64 corpus: 2.0 -> 1.3 wavefronts per lookup).
-   The bulk copy cannot shift a line (source and destination of cp.async.bulk
-   are 16-byte aligned, and the tensor form faults on a coordinate that is not:
-   tools/micro/tma_lines.cu), so the lane re-aligns in registers: two aligned
-   16-byte blocks, a two-level select by the word offset, a byte permute by the
-   byte offset - 16 ALU operations per 16 bytes, none in the load/store pipe. */
-struct Feed {
-  uint32_t blk;   // address of the next aligned block to load
-  uint4 cur;      // the block in front of it
-  uint32_t sel;   // PRMT selector of the byte offset: 0x3210 + 0x1111 * (start & 3)
-  bool w1, w2;    // bits of the word offset (start >> 2) & 3
-};
-__device__ __forceinline__ void feed_begin(Feed &f, const uint32_t textAddr) {
-  f.blk = textAddr & ~15u;
-  f.cur = lds128(f.blk);
-  f.blk += 16;
-  f.sel = 0x3210u + 0x1111u * (textAddr & 3u);
-  f.w1 = (textAddr & 4u) != 0;
-  f.w2 = (textAddr & 8u) != 0;
-}
-// the next 16 bytes of the line (whatever follows the line's end comes along)
-__device__ __forceinline__ uint4 feed_next(Feed &f) {
-  const uint4 n = lds128(f.blk);
-  f.blk += 16;
-  const uint32_t u0 = f.w1 ? f.cur.y : f.cur.x, u1 = f.w1 ? f.cur.z : f.cur.y, u2 = f.w1 ? f.cur.w : f.cur.z,
-                 u3 = f.w1 ? n.x : f.cur.w, u4 = f.w1 ? n.y : n.x, u5 = f.w1 ? n.z : n.y, u6 = f.w1 ? n.w : n.z;
-  const uint32_t y0 = f.w2 ? u2 : u0, y1 = f.w2 ? u3 : u1, y2 = f.w2 ? u4 : u2, y3 = f.w2 ? u5 : u3,
-                 y4 = f.w2 ? u6 : u4;
-  uint4 r;
-  r.x = __byte_perm(y0, y1, f.sel);
-  r.y = __byte_perm(y1, y2, f.sel);
-  r.z = __byte_perm(y2, y3, f.sel);
-  r.w = __byte_perm(y3, y4, f.sel);
-  f.cur = n;
-  return r;
-}
-
-/* The fast pass over one aligned 16-byte chunk of one line per lane: no
-   decisions, only the largest code per quarter and the code at each quarter's
-   end.  [lo, hi): the bytes of the chunk that belong to the line; FULL16: they
-   all do.  Returns false when no code reached hx.cLimit (code is then the
-   state behind the chunk); true when one did: (j, cj) is where the careful
-   pass has to start, code is unchanged. */
-template <bool FULL16, int STRIDE>
-__device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const uint32_t lo, const uint32_t hi,
-                                         uint32_t &code, uint32_t &j, uint32_t &cj) {
-  uint32_t c = code;
-  uint32_t mq0 = 0, mq1 = 0, mq2 = 0, mq3 = 0;
-  uint32_t cp0 = 0, cp1 = 0, cp2 = 0;
-  const uint32_t mask = FULL16 ? 0xffffu : ((0xffffu >> (16 - hi)) & (0xffffu << lo));
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
-    uint32_t m = 0;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      // a byte outside the line: no lookup at all (a predicated load), the
-      // lane's lookups would only collide with the others' in the banks
-      if (FULL16 || (mask & (1u << (4 * q + jj))))
-        c = hot_next<STRIDE>(hx, c, word, jj);
-      m = max(m, c);
-    }
-    if (q == 0) { mq0 = m; cp0 = c; }
-    if (q == 1) { mq1 = m; cp1 = c; }
-    if (q == 2) { mq2 = m; cp2 = c; }
-    if (q == 3) { mq3 = m; }
-  }
-  // rows of 128 columns: a byte >= 128 anywhere in the chunk and the lookups
-  // above mean nothing (they stayed inside shared memory: codes are bytes)
-  const bool high = (STRIDE == static_cast<int>(kHotStrideAscii)) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0);
-  if (!high && (max(max(mq0, mq1), max(mq2, mq3)) < hx.cLimit)) {
-    code = c;
-    return false;
-  }
-  // the careful pass starts at the first flagged quarter
-  j = 0;
-  cj = code;
-  if (high) {
-    j = lo;
-    return true;
-  }
-  if (mq0 < hx.cLimit) {
-    j = 4; cj = cp0;
-    if (mq1 < hx.cLimit) {
-      j = 8; cj = cp1;
-      if (mq2 < hx.cLimit) { j = 12; cj = cp2; }
-    }
-  }
-  j = max(j, lo);
-  return true;
-}
-
-/* The fast pass where codes that need a decision STICK (style Full: absorbing
-   and dead states, the sink; style Instant on an image built with
-   acceptSticks): no running maximum - the code behind the chunk tells whether
-   anything happened in it.  Returns that code, or 255 for a chunk of an
-   ASCII-row image that holds a byte >= 128.  hi: bytes of the chunk that
-   belong to the line (FULL16: all 16). */
-template <bool FULL16, int STRIDE>
-__device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, uint4 w, const uint32_t hi, uint32_t c) {
-  constexpr bool kAscii = STRIDE == static_cast<int>(kHotStrideAscii);
-  if (kAscii && !FULL16) {
-    /* Rows of 128 columns have four more bytes, and those hold the row's own
-       code: byte 0x80 is a step that changes nothing.  The bytes behind the
-       line's end are replaced by it, and the tail chunk is walked like a whole
-       one - no predicated lookups. */
-    // k_q: the low min(max(hi - 4 q, 0), 4) bytes of word q
-    const int h = static_cast<int>(hi);
-    const uint32_t k0 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h, 0), 4)));
-    const uint32_t k1 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 4, 0), 4)));
-    const uint32_t k2 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 8, 0), 4)));
-    const uint32_t k3 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 12, 0), 4)));
-    w.x = (w.x & k0) | (0x80808080u & ~k0);
-    w.y = (w.y & k1) | (0x80808080u & ~k1);
-    w.z = (w.z & k2) | (0x80808080u & ~k2);
-    w.w = (w.w & k3) | (0x80808080u & ~k3);
-    // a byte >= 128 of the line itself (not the filler)
-    if ((((w.x & k0) | (w.y & k1) | (w.z & k2) | (w.w & k3)) & 0x80808080u) != 0)
-      return 255u;
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (FULL16 || kAscii || (static_cast<uint32_t>(4 * q + jj) < hi))
-        c = hot_next<STRIDE>(hx, c, word, jj);
-  }
-  if (kAscii && FULL16 && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
-    return 255u;
-  return c;
-}
-
-/* Behind hot_run on an image whose accepting codes stick: how many bytes of
-   the chunk come before the one that entered the code the run ended in (the
-   same 16 lookups again, counting the codes below the limit). */
-template <int STRIDE>
-__device__ __forceinline__ uint32_t hot_locate(const HotCtx &hx, const uint4 &w, const uint32_t hi, uint32_t c) {
-  uint32_t n = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (static_cast<uint32_t>(4 * q + jj) < hi) {
-        c = hot_next<STRIDE>(hx, c, word, jj);
-        n += (c < hx.cLimit) ? 1u : 0u;
-      }
-  }
-  return n;
-}
-
-/* The careful pass: bytes [j, hi) of the chunk at chunkAddr one by one with
-   the style's decisions; on the hot table while the state is hot, on the full
-   table while it is not (First/Tangent are not walked here: the limit never
-   changes).  c: the state in front of byte j in, behind the last byte taken
-   out (hx.sink: it is in wk.v).  Returns true when the walk is over. */
-template <int STYLE, int STRIDE>
-__device__ __forceinline__ bool hot_careful(const ProgramDev &pd, const HotCtx &hx, const uint32_t chunkAddr,
-                                            uint32_t j, const uint32_t hi, const uint32_t pos0,
-                                            uint32_t &c, Walk<STYLE, false> &wk) {
-#pragma unroll 1
-  for (; j < hi; ++j) {
-    const uint32_t byte = lds8(chunkAddr + j);
-    bool stopped = false;
-    if (c == hx.sink) {
-      // (a copy goes through the call, so that wk itself can stay in registers)
-      Walk<STYLE, false> tmp = wk;
-      stopped = cold_step<STYLE>(pd, hx.wide, tmp, byte, pos0 + j);
-      wk = tmp;
-      if (!stopped)
-        c = hx.codeOf[state_index(pd, wk.v)];
-    }
-    else {
-      const uint32_t nc = ((STRIDE == static_cast<int>(kHotStrideAscii)) && (byte >= 128))
-          ? hx.sink : hot_next_byte<STRIDE>(hx, c, byte);
-      if (nc >= hx.cLimit) {
-        if (nc == hx.sink) {
-          // leaves the hot set: this byte again, on the full table
-          wk.v = lds32(hx.c2v + 4 * c);
-          c = hx.sink;
-          --j;
-          continue;
-        }
-        if (nc >= hx.cPure)
-          stopped = true;  // pure dead end (Matcher.h:478)
-        else if (STYLE == STY_FULL)
-          stopped = true;  // absorbing accept: the outcome is known
-        else {
-          wk.accV = 0x80000000u | lds32(hx.c2v + 1024 + 4 * nc);  // tagged: the result id itself
-          wk.mend = pos0 + j + 1;
-          if (STYLE == STY_INSTANT)
-            stopped = true;
-          else if (nc >= hx.cAbs) {
-            wk.absorbed = true;
-            stopped = true;
-          }
-        }
-      }
-      c = nc;
-    }
-    if (stopped) {
-      wk.mstart = pos0 + j + 1;  // bytes consumed
-      return true;
-    }
-  }
-  return false;
-}
-
-// fast pass, and the careful pass right behind it where it is needed
-template <int STYLE, bool FULL16, int STRIDE>
-__device__ __forceinline__ bool hot_chunk(const ProgramDev &pd, const HotCtx &hx, const uint4 &w,
-                                          const uint32_t chunkAddr, const uint32_t lo, const uint32_t hi,
-                                          const uint32_t pos0, uint32_t &code, Walk<STYLE, false> &wk) {
-  uint32_t j = lo, cj = code;
-  if ((code != hx.sink) && !hot_fast<FULL16, STRIDE>(hx, w, lo, hi, code, j, cj))
-    return false;
-  const bool stopped = hot_careful<STYLE, STRIDE>(pd, hx, chunkAddr, j, hi, pos0, cj, wk);
-  code = cj;
-  return stopped;
-}
 
 /* DEFER (styles whose walk ends at the first state that needs a decision:
    Instant, Full): a lane whose chunk was flagged steps aside, and the careful

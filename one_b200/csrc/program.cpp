@@ -366,10 +366,10 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
 
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
                      const uint64_t *visits, uint32_t maxHot, bool asciiRows, bool acceptSticks,
-                     HotImage &hot) {
+                     HotImage &hot, bool wideCodes) {
   const uint32_t n = pp.stateCount;
   const uint32_t C = pp.classCount;
-  maxHot = std::max(1u, std::min(maxHot, kHotMax));
+  maxHot = std::max(1u, std::min(maxHot, wideCodes ? kHotMaxWide : kHotMax));
   const uint32_t firstPure = img.pureV / img.vPerState;
   // successor in renumbered indices; pure dead ends loop to themselves, as in
   // the full image
@@ -428,10 +428,11 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
   else
     hot.coverage = (cand.size() == bfs.size()) ? 1000 : 0;  // no profile: unknown unless every state is hot
   hot.nHot = static_cast<uint32_t>(cand.size());
-  hot.codeOf.assign(n, static_cast<uint8_t>(hot.nHot));
-  hot.codeToV.assign(256, 0);
+  hot.entryBytes = wideCodes ? 2 : 1;
+  std::vector<uint32_t> codeOf(n, hot.nHot);
+  hot.codeToV.assign(std::max<size_t>(256, hot.nHot + 1), 0);
   for (uint32_t c = 0; c < hot.nHot; ++c) {
-    hot.codeOf[cand[c]] = static_cast<uint8_t>(c);
+    codeOf[cand[c]] = c;
     hot.codeToV[c] = cand[c] * img.vPerState;
   }
   auto below = [&](uint32_t v) {
@@ -441,23 +442,35 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
   hot.cAccept = below(img.acceptV);
   hot.cAbs = below(img.absV);
   hot.cPure = below(img.pureV);
-  hot.initCode = hot.codeOf[init];
+  hot.initCode = codeOf[init];
   // (a walk that STARTS in an accepting state leaves it by its real row)
   if (hot.initCode >= hot.cAccept)
     acceptSticks = false;
-  hot.stride = asciiRows ? kHotStrideAscii : kHotStrideWide;
-  const uint32_t columns = hot.stride - 4;
+  const uint32_t columns = asciiRows ? 128 : 256;
+  const uint32_t E = hot.entryBytes;
+  hot.stride = columns * E + 4;
   const size_t bytes = (static_cast<size_t>(hot.nHot + 1) * hot.stride + 15) & ~size_t(15);
-  hot.table.assign(bytes, static_cast<uint8_t>(hot.nHot));
-  for (uint32_t c = 0; c < hot.nHot; ++c) {
+  hot.table.assign(bytes, 0);
+  auto put = [&](uint8_t *at, uint32_t code) {
+    at[0] = static_cast<uint8_t>(code);
+    if (E == 2)
+      at[1] = static_cast<uint8_t>(code >> 8);
+  };
+  for (uint32_t c = 0; c <= hot.nHot; ++c) {
     uint8_t *row = &hot.table[static_cast<size_t>(c) * hot.stride];
     for (uint32_t b = 0; b < columns; ++b)
-      row[b] = (acceptSticks && (c >= hot.cAccept)) ? static_cast<uint8_t>(c) : hot.codeOf[nextOf(cand[c], b)];
-    // the four bytes behind a row of 128 columns: "byte 0x80 .. 0x83" leaves
-    // the state as it is (the staged kernel fills a line's last chunk with it)
-    for (uint32_t b = columns; b < hot.stride; ++b)
-      row[b] = static_cast<uint8_t>(c);
+      put(row + b * E, ((c == hot.nHot) || (acceptSticks && (c >= hot.cAccept))) ? c : codeOf[nextOf(cand[c], b)]);
+    // the four bytes behind a row of 128 one-byte columns: "byte 0x80 .. 0x83"
+    // leaves the state as it is (the staged kernel fills a line's last chunk
+    // with it)
+    for (uint32_t b = columns * E; b < hot.stride; b += E)
+      put(row + b, c);
   }
+  for (size_t i = static_cast<size_t>(hot.nHot + 1) * hot.stride; i + E <= bytes; i += E)
+    put(&hot.table[i], hot.nHot);
+  hot.codeOf.assign(static_cast<size_t>(n) * E, 0);
+  for (uint32_t st = 0; st < n; ++st)
+    put(&hot.codeOf[static_cast<size_t>(st) * E], codeOf[st]);
   hot.acceptSticks = acceptSticks;
 }
 

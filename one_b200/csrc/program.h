@@ -130,6 +130,10 @@ void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img,
 constexpr uint32_t kHotStrideWide = 260;
 constexpr uint32_t kHotStrideAscii = 132;
 constexpr uint32_t kHotMax = 255;
+/* The long-stream matcher's image may hold more states than a byte can name:
+   two-byte entries then (rows of 2 * columns + 4 bytes), as many states as the
+   kernel's shared memory takes beside its text stages. */
+constexpr uint32_t kHotMaxWide = 1024;
 
 struct HotImage {
   uint32_t nHot = 0;              // codes 0 .. nHot-1; nHot = sink
@@ -140,9 +144,10 @@ struct HotImage {
   uint32_t stride = kHotStrideWide; // bytes per row
   uint32_t coverage = 1000;       // per mille of the counted state entries that the hot set holds
   bool acceptSticks = false;      // rows of accepting codes loop to themselves (see build_hot_image)
+  uint32_t entryBytes = 1;        // 1: one-byte codes (at most kHotMax states); 2: two-byte codes
   std::vector<uint8_t> table;     // (nHot + 1) * stride, padded to 16 bytes
-  std::vector<uint32_t> codeToV;  // 256 entries: v of the full image
-  std::vector<uint8_t> codeOf;    // by renumbered state index; nHot = not hot
+  std::vector<uint32_t> codeToV;  // max(256, nHot + 1) entries: v of the full image
+  std::vector<uint8_t> codeOf;    // by renumbered state index (entryBytes each); nHot = not hot
 };
 
 /* visits: per renumbered state index, or nullptr (breadth-first order then).
@@ -153,6 +158,6 @@ struct HotImage {
    states stick anyway). */
 void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
                      const uint64_t *visits, uint32_t maxHot, bool asciiRows, bool acceptSticks,
-                     HotImage &hot);
+                     HotImage &hot, bool wideCodes = false);
 
 } // namespace red_b200

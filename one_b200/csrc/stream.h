@@ -9,6 +9,7 @@
 
 #include "../../include/red_b200.h"
 #include "device_program.h"
+#include "hot.h"
 #include "program.h"
 
 namespace red_b200 {
@@ -65,7 +66,8 @@ int compact_matches_n(const int32_t *dResults, uint64_t capLines, const uint64_t
                       uint64_t *dIndices, uint64_t *dCount, SplitScratch &scratch,
                       cudaStream_t stream, std::string &why);
 
-int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &img,
+// hot: the hot image of the styles that walk on behind a match (hot.h), or null
+int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &img, const HotDev *hot,
                  const LaunchGeometry &geo, const uint8_t *dText, uint64_t len,
                  int style, red_b200_outcome *out, cudaStream_t stream,
                  int *launches, std::string &why);

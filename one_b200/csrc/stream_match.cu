@@ -45,6 +45,7 @@
 
 #include "stream.h"
 #include "chunk_engine.cuh"
+#include "hot_walk.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -155,7 +156,8 @@ template <bool SMEM, int K, class ClsT, bool TRACK>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
                    uint32_t chunkBytes, uint64_t nChunks, CandRec *cands, uint8_t *nCand,
-                   uint32_t v0, uint32_t lookback, ExtraWalk *extras, unsigned long long *nExtras) {
+                   uint32_t v0, uint32_t lookback, ExtraWalk *extras, unsigned long long *nExtras,
+                   const bool walkFirst) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   using Eng = Engine<SMEM, K, ClsT>;
   unsigned char *smem = Eng::stage(pd, smemRaw);
@@ -237,7 +239,12 @@ stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
       e.startV = startV[k];
       extras[atomicAdd(nExtras, 1ull)] = e;
     }
-    {
+    if (!walkFirst) {
+      // the first candidate's walk is stream_hot_kernel's: only its start state
+      if (cnt > 0)
+        cands[c * kCand].startV = startV[0];
+    }
+    else {
       const uint32_t k = 0;
       const bool go = k < cnt;
       // TRACK: also the last exit from the initial state (three more
@@ -259,6 +266,374 @@ stream_cand_kernel(const ProgramDev pd, const uint8_t *text, uint64_t len,
     }
     if (mine)
       nCand[c] = static_cast<uint8_t>(cnt);
+  }
+}
+
+/* The first candidate's walk of every chunk on the HOT IMAGE (program.h), the
+   text staged through shared memory.
+
+   What bounded the walk above (ncu: the LSU data pipe, 91 %): two lookups per
+   byte, and a 16-byte text load per lane and step that is a wavefront of its
+   own - the lanes of a warp are a whole chunk apart.  Here a step is one
+   lookup in the hot image (kernels_hot.cu's, from the same profile), and the
+   text comes in stages of 64 bytes per lane: the warp copies the 32 rows of a
+   stage together (cp.async, four lanes per row, so a request covers whole
+   64-byte pieces) into rows of 80 bytes - an odd number of 16-byte units, so
+   that the LDS.128 of eight consecutive lanes hit eight bank groups - two
+   stages per warp, the next one in flight while the current one is walked.
+   Lanes that leave the hot set go on on the full table, byte by byte, until
+   they are back (hot_careful).  Style Last without start tracking, as the
+   kernel above: end state, last accepting position and state. */
+constexpr uint32_t kStageBytes = 64;
+constexpr uint32_t kStagePitch = 80;
+constexpr uint32_t kStageBuf = 32 * kStagePitch;
+constexpr uint32_t kHotStreamMaxWarps = 28;
+
+// shared-memory layout of stream_hot_kernel (byte offsets behind the hot table)
+struct HotStreamParams {
+  uint32_t oC2v, oCls, oCodeOf, oStage, oMirror;
+  uint32_t codeOfBytes;  // 0: codeOf stays in global memory
+  uint32_t mirrorBytes;  // leading bytes of the full table kept in shared memory
+};
+
+/* Where a lane that left the hot set walks: the full table, its leading rows
+   (the states nearest the initial one) in shared memory, the rest in global
+   memory; the class map and - if it fits - the state-to-code map in shared
+   memory too.  Nearly every chunk has SOME lane of the warp out of the hot set
+   for a byte or two (a 255-state hot set holds 99 % of the entries of a
+   1191-state union, not all), and a byte on a table in L2 is two round trips
+   with the warp waiting. */
+// a step on the stream's image: entries of W bytes (hot_walk.cuh's hot_next is the W = 1 form)
+template <int STRIDE, int W>
+__device__ __forceinline__ uint32_t stream_next(const HotCtx &hx, uint32_t c, uint32_t word, int jj) {
+  if (W == 1)
+    return hot_next<STRIDE>(hx, c, word, jj);
+  return lds16(c * STRIDE + hx.tab + 2 * byte_of(word, jj));
+}
+template <int STRIDE, int W>
+__device__ __forceinline__ uint32_t stream_next_byte(const HotCtx &hx, uint32_t c, uint32_t byte) {
+  if (W == 1)
+    return hot_next_byte<STRIDE>(hx, c, byte);
+  return lds16(c * STRIDE + hx.tab + 2 * byte);
+}
+
+struct StreamCold {
+  const unsigned char *base;
+  uint32_t shift, wide;
+  uint32_t mirA, mirBytes;
+  uint32_t clsA;
+  uint32_t codeOfA;          // 0: not in shared memory
+  const uint8_t *codeOfG;
+  uint32_t codeWide;         // 1: two-byte codes
+  __device__ __forceinline__ uint32_t next(uint32_t v, uint32_t co) const {
+    const uint32_t off = (v << shift) + co;
+    if (off < mirBytes)
+      return wide ? lds32(mirA + off) : lds16(mirA + off);
+    return wide ? __ldg(reinterpret_cast<const uint32_t *>(base + off))
+                : static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(base + off)));
+  }
+  __device__ __forceinline__ uint32_t code_of(uint32_t idx) const {
+    if (codeWide)
+      return codeOfA ? lds16(codeOfA + 2 * idx)
+                     : static_cast<uint32_t>(__ldg(reinterpret_cast<const uint16_t *>(codeOfG) + idx));
+    return codeOfA ? lds8(codeOfA + idx) : static_cast<uint32_t>(__ldg(codeOfG + idx));
+  }
+};
+
+/* Bytes [j, hi) of the chunk at chunkAddr one by one, style Last: on the hot
+   table while the state is hot, on the full table while it is not.  c: the
+   code in front of byte j in, behind the last byte taken out (hx.sink: the
+   state is in wk.v).  True = the walk is over (a state that is never left). */
+template <int STRIDE, int W>
+__device__ __noinline__ bool stream_careful(const ProgramDev &pd, const HotCtx &hx, const StreamCold &sc,
+                                               const uint32_t chunkAddr, uint32_t j, const uint32_t hi,
+                                               const uint32_t pos0, uint32_t &c, Walk<STY_LAST, false> &wk) {
+  constexpr bool kAsciiRows = STRIDE == 128 * W + 4;
+#pragma unroll 1
+  for (; j < hi; ++j) {
+    const uint32_t byte = lds8(chunkAddr + j);
+    bool stopped = false;
+    if (c == hx.sink) {
+      stopped = wk.step(pd, sc, lds16(sc.clsA + 2 * byte), pos0 + j);
+      if (!stopped)
+        c = sc.code_of(state_index(pd, wk.v));
+    }
+    else {
+      const uint32_t nc = (kAsciiRows && (byte >= 128)) ? hx.sink : stream_next_byte<STRIDE, W>(hx, c, byte);
+      if (nc >= hx.cLimit) {
+        if (nc == hx.sink) {
+          // leaves the hot set: this byte again, on the full table
+          wk.v = lds32(hx.c2v + 4 * c);
+          c = hx.sink;
+          --j;
+          continue;
+        }
+        if (nc >= hx.cPure)
+          stopped = true;
+        else {
+          wk.accV = lds32(hx.c2v + 4 * nc);
+          wk.mend = pos0 + j + 1;
+          if (nc >= hx.cAbs) {
+            wk.absorbed = true;
+            stopped = true;
+          }
+        }
+      }
+      c = nc;
+    }
+    if (stopped)
+      return true;
+  }
+  return false;
+}
+
+// (a copy goes through the call, so that wk and the code themselves can stay in registers)
+template <int STRIDE, int W>
+__device__ __forceinline__ bool stream_careful_call(const ProgramDev &pd, const HotCtx &hx, const StreamCold &sc,
+                                                    const uint32_t chunkAddr, const uint32_t j, const uint32_t hi,
+                                                    const uint32_t pos0, uint32_t &c, Walk<STY_LAST, false> &wk) {
+  Walk<STY_LAST, false> tmp = wk;
+  uint32_t cc = c;
+  const bool stopped = stream_careful<STRIDE, W>(pd, hx, sc, chunkAddr, j, hi, pos0, cc, tmp);
+  wk = tmp;
+  c = cc;
+  return stopped;
+}
+
+/* The chunk a lane noted last: its bytes again, from global memory, for the
+   last accepting position in it (no state >= cAbs was entered there). */
+template <int STRIDE, int W>
+__device__ __forceinline__ void stream_resolve(const HotCtx &hx, const uint8_t *chunkText, const uint32_t hi,
+                                               const uint32_t pos0, uint32_t c, Walk<STY_LAST, false> &wk) {
+  const uint4 w = __ldg(reinterpret_cast<const uint4 *>(chunkText));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const uint32_t idx = static_cast<uint32_t>(4 * q + jj);
+      if (idx < hi) {
+        c = stream_next<STRIDE, W>(hx, c, word, jj);
+        if (c >= hx.cLimit) {
+          wk.accV = lds32(hx.c2v + 4 * c);
+          wk.mend = pos0 + idx + 1;
+        }
+      }
+    }
+  }
+}
+
+/* One 16-byte chunk, style Last.  The fast pass keeps the largest code of the
+   chunk.  An accepting state entered in it needs no attention now: of all the
+   accepting positions of a lane's walk only the LAST one goes into the record,
+   so the lane just remembers where the latest such chunk began and in which
+   state (flagPos, flagCode) and looks into it once, when its walk is over
+   (stream_resolve).  Only a state that is never left, the way out of the hot
+   set, or a byte >= 128 on 128-column rows is dealt with on the spot. */
+template <bool FULL16, int STRIDE, int W>
+__device__ __forceinline__ bool stream_chunk_body(const ProgramDev &pd, const HotCtx &hx, const StreamCold &sc,
+                                                  const uint4 &w, const uint32_t chunkAddr, const uint32_t hi,
+                                                  const uint32_t pos0, uint32_t &code, Walk<STY_LAST, false> &wk,
+                                                  uint32_t &flagPos, uint32_t &flagCode,
+                                                  const uint8_t *laneText, const uint32_t laneBytes) {
+  bool careful = code == hx.sink;
+  uint32_t c = code, m = 0;
+  if (!careful) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (FULL16 || (static_cast<uint32_t>(4 * q + jj) < hi))
+          c = stream_next<STRIDE, W>(hx, c, word, jj);
+        m = max(m, c);
+      }
+    }
+    if ((STRIDE == 128 * W + 4) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
+      careful = true;
+    else if (m < hx.cAbs) {
+      if (m >= hx.cLimit) {
+        flagPos = pos0;
+        flagCode = code;
+      }
+      code = c;
+      return false;
+    }
+    else
+      careful = true;
+  }
+  // what was noted before is settled first: an accepting position recorded
+  // from here on lies behind it
+  if (flagPos != kNoPos) {
+    stream_resolve<STRIDE, W>(hx, laneText + flagPos, min(16u, laneBytes - flagPos), flagPos, flagCode, wk);
+    flagPos = kNoPos;
+  }
+  return stream_careful_call<STRIDE, W>(pd, hx, sc, chunkAddr, 0, hi, pos0, code, wk);
+}
+
+// (the kernel's loop holds ONE copy of the whole-chunk form; a chunk's ragged
+// end - once per 1-16 KB - goes through a call)
+template <int STRIDE, int W>
+__device__ __noinline__ bool stream_chunk_tail(const ProgramDev &pd, const HotCtx &hx, const StreamCold &sc,
+                                               const uint4 &w, const uint32_t chunkAddr, const uint32_t hi,
+                                               const uint32_t pos0, uint32_t &code, Walk<STY_LAST, false> &wk,
+                                               uint32_t &flagPos, uint32_t &flagCode,
+                                               const uint8_t *laneText, const uint32_t laneBytes) {
+  return stream_chunk_body<false, STRIDE, W>(pd, hx, sc, w, chunkAddr, hi, pos0, code, wk, flagPos, flagCode,
+                                          laneText, laneBytes);
+}
+template <int STRIDE, int W>
+__device__ __forceinline__ bool stream_chunk_tail_call(const ProgramDev &pd, const HotCtx &hx, const StreamCold &sc,
+                                                       const uint4 &w, const uint32_t chunkAddr, const uint32_t hi,
+                                                       const uint32_t pos0, uint32_t &code, Walk<STY_LAST, false> &wk,
+                                                       uint32_t &flagPos, uint32_t &flagCode,
+                                                       const uint8_t *laneText, const uint32_t laneBytes) {
+  Walk<STY_LAST, false> tmp = wk;
+  uint32_t cc = code, fp = flagPos, fc = flagCode;
+  const uint4 ww = w;
+  const bool stopped = stream_chunk_tail<STRIDE, W>(pd, hx, sc, ww, chunkAddr, hi, pos0, cc, tmp, fp, fc, laneText,
+                                                 laneBytes);
+  wk = tmp;
+  code = cc;
+  flagPos = fp;
+  flagCode = fc;
+  return stopped;
+}
+
+template <int STRIDE, int W>
+__global__ void __launch_bounds__(kHotStreamMaxWarps * 32, 1)
+stream_hot_kernel(const ProgramDev pd, const HotDev hd, const HotStreamParams sp, const uint8_t *text, uint64_t len,
+                  uint32_t chunkBytes, uint64_t nChunks, CandRec *cands, const uint8_t *nCand) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  unsigned char *smem = smemRaw + ((256u - (smem_addr(smemRaw) & 255u)) & 255u);
+  const uint32_t sBase = smem_addr(smem);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t nWarps = blockDim.x >> 5;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(hd.table);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < (hd.tableBytes >> 4); i += blockDim.x)
+      dst[i] = __ldg(src + i);
+    uint32_t *c2v = reinterpret_cast<uint32_t *>(smem + sp.oC2v);
+    for (uint32_t i = threadIdx.x; i <= hd.nHot; i += blockDim.x)
+      c2v[i] = __ldg(hd.codeToV + i);
+    uint16_t *cls = reinterpret_cast<uint16_t *>(smem + sp.oCls);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+      cls[i] = __ldg(pd.clsOffset + i);
+    for (uint32_t i = threadIdx.x; i < sp.codeOfBytes; i += blockDim.x)
+      smem[sp.oCodeOf + i] = (i < pd.stateCount * W) ? __ldg(hd.codeOf + i) : static_cast<uint8_t>(0);
+    const uint4 *tsrc = reinterpret_cast<const uint4 *>(pd.table);
+    uint4 *tdst = reinterpret_cast<uint4 *>(smem + sp.oMirror);
+    for (uint32_t i = threadIdx.x; i < (sp.mirrorBytes >> 4); i += blockDim.x)
+      tdst[i] = __ldg(tsrc + i);
+  }
+  __syncthreads();
+  HotCtx hx;
+  hx.tab = sBase;
+  hx.c2v = sBase + sp.oC2v;
+  hx.sink = hd.nHot;
+  hx.cLimit = hd.cAccept;
+  hx.cAbs = hd.cAbs;
+  hx.cPure = hd.cPure;
+  hx.wide = hd.wideTable;
+  hx.codeOf = hd.codeOf;
+  StreamCold sc;
+  sc.base = static_cast<const unsigned char *>(pd.table);
+  sc.wide = hd.wideTable;
+  sc.shift = hd.wideTable ? 2 : pd.unitShift + 1;
+  sc.mirA = sBase + sp.oMirror;
+  sc.mirBytes = sp.mirrorBytes;
+  sc.clsA = sBase + sp.oCls;
+  sc.codeOfA = sp.codeOfBytes ? sBase + sp.oCodeOf : 0;
+  sc.codeOfG = hd.codeOf;
+  sc.codeWide = (W == 2) ? 1 : 0;
+
+  const uint32_t bufA = sBase + sp.oStage + warp * 2 * kStageBuf;
+  const uint32_t rowA = lane * kStagePitch;
+  const uint32_t nStages = (chunkBytes + kStageBytes - 1) / kStageBytes;
+  const uint64_t totalWarps = static_cast<uint64_t>(gridDim.x) * nWarps;
+  for (uint64_t g = static_cast<uint64_t>(blockIdx.x) * nWarps + warp; g * 32 < nChunks; g += totalWarps) {
+    const uint64_t c0 = g * 32;
+    const uint64_t c = c0 + lane;
+    const bool mine = c < nChunks;
+    const uint64_t begin = mine ? c * chunkBytes : 0;
+    const uint32_t n = mine ? static_cast<uint32_t>(min(static_cast<uint64_t>(chunkBytes), len - begin)) : 0;
+    const bool go = mine && (__ldg(nCand + c) != 0);
+    const uint32_t startV = go ? cands[c * kCand].startV : pd.initV;
+    Walk<STY_LAST, false> wk;
+    wk.begin(pd);
+    wk.v = startV;
+    uint32_t code = sc.code_of(state_index(pd, startV));
+    bool active = go && (n != 0);
+    uint32_t flagPos = kNoPos, flagCode = 0;  // the last chunk in which an accepting state was entered
+
+    // the rows this lane copies in every stage: row (lane / 4) + 8 i, piece lane % 4
+    const uint32_t piece = (lane & 3) * 16;
+    auto issue = [&](uint32_t st, uint32_t buf) {
+#pragma unroll
+      for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t row = i * 8 + (lane >> 2);
+        const uint64_t rc = c0 + row;
+        const uint64_t rBegin = rc * chunkBytes;
+        const uint64_t rBytes = (rc < nChunks) ? min(static_cast<uint64_t>(chunkBytes), len - rBegin) : 0;
+        const uint64_t off = static_cast<uint64_t>(st) * kStageBytes + piece;
+        const bool valid = off < rBytes;  // (a piece that starts inside the text lies in its last 16-byte block at most)
+        cp_async16(buf + row * kStagePitch + piece, text + (valid ? rBegin + off : 0), valid ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    issue(0, bufA);
+    for (uint32_t st = 0; st < nStages; ++st) {
+      const uint32_t cur = bufA + (st & 1) * kStageBuf;
+      const bool more = st + 1 < nStages;
+      if (more)
+        issue(st + 1, bufA + ((st + 1) & 1) * kStageBuf);
+      // the text a few stages on into L2, so that the copies find it there
+      if (active && ((st & 1) == 0)) {
+        const uint64_t ahead = static_cast<uint64_t>(st + 6) * kStageBytes;
+        if (ahead < n)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(text + begin + ahead));
+      }
+      if (more)
+        cp_async_wait<1>();
+      else
+        cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j = 0; j < kStageBytes / 16; ++j) {
+        const uint32_t pos = st * kStageBytes + 16 * j;
+        if (active && (pos < n)) {
+          const uint32_t a = cur + rowA + 16 * j;
+          const uint4 w = lds128(a);
+          const uint32_t rem = n - pos;
+          const bool stopped = (rem >= 16)
+              ? stream_chunk_body<true, STRIDE, W>(pd, hx, sc, w, a, 16, pos, code, wk, flagPos, flagCode,
+                                                   text + begin, n)
+              : stream_chunk_tail_call<STRIDE, W>(pd, hx, sc, w, a, rem, pos, code, wk, flagPos, flagCode,
+                                                  text + begin, n);
+          if (stopped || (rem <= 16))
+            active = false;
+        }
+      }
+      __syncwarp();  // everybody is through with `cur` before the stage after next lands in it
+      if (!__any_sync(kFullMask, active)) {
+        cp_async_wait<0>();
+        __syncwarp();
+        break;
+      }
+    }
+    if (go && (flagPos != kNoPos))
+      stream_resolve<STRIDE, W>(hx, text + begin + flagPos, min(16u, n - flagPos), flagPos, flagCode, wk);
+    if (go) {
+      CandRec rec;
+      rec.startV = startV;
+      rec.endV = (code != hx.sink) ? lds32(hx.c2v + 4 * code) : wk.v;
+      rec.accV = wk.accV;
+      rec.accEnd = wk.absorbed ? n : wk.mend;
+      rec.lastLeaveOff = kNoPos;
+      cands[c * kCand] = rec;
+    }
   }
 }
 
@@ -719,7 +1094,7 @@ stream_break_reduce_kernel(const BreakRec *recs, uint64_t firstChunk, uint64_t n
 }
 
 template <bool SMEM, int K, class ClsT>
-int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
+int run_stream(const ProgramDev &pd, const HotDev *hot, const LaunchGeometry &geo,
                const uint8_t *dText, uint64_t len, int style,
                red_b200_outcome *out, cudaStream_t stream, int *launches,
                std::string &why) {
@@ -747,6 +1122,51 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
   TRY(cudaFuncSetAttribute(extraPlain, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(extraTrack, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   TRY(cudaFuncSetAttribute(brk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+
+  /* The main walk (style Last, no start tracking) on the hot image where the
+     program has one that holds (nearly) every state the profiled text enters:
+     stream_hot_kernel.  RED_B200_STREAM_HOT=0 keeps it out, =1 takes it
+     whatever the profile's coverage. */
+  bool useHot = (hot != nullptr) && (hot->table != nullptr) && (hot->coverage >= 990);
+  if (const char *env = getenv("RED_B200_STREAM_HOT"))
+    useHot = (hot != nullptr) && (hot->table != nullptr) && (atoi(env) != 0);
+  HotStreamParams hsp{};
+  uint32_t hotWarpsMax = 0, hotFixed = 0;
+  if (useHot) {
+    uint32_t at = (hot->tableBytes + 15u) & ~15u;
+    hsp.oC2v = at;
+    at += ((hot->nHot + 1) * 4 + 15u) & ~15u;
+    hsp.oCls = at;
+    at += 512;
+    hsp.codeOfBytes = (pd.stateCount <= 8192) ? ((pd.stateCount * hot->entryBytes + 15u) & ~15u) : 0;
+    hsp.oCodeOf = at;
+    at += hsp.codeOfBytes;
+    hsp.oStage = at;
+    const uint32_t room = (static_cast<uint32_t>(geo.maxSmemOptin) > at + 256) ? geo.maxSmemOptin - at - 256 : 0;
+    // staging for as many warps as keep the load/store pipe busy, the rest of
+    // the shared memory for the leading rows of the full table
+    hotWarpsMax = std::min<uint32_t>(kHotStreamMaxWarps, room / (2 * kStageBuf));
+    const uint32_t wantWarps = 24;
+    if ((hot->coverage < 1000) && (hotWarpsMax > wantWarps) && (room - wantWarps * 2 * kStageBuf < pd.tableBytes))
+      hotWarpsMax = wantWarps;
+    if (const char *env = getenv("RED_B200_STREAM_HOT_WARPS"))
+      hotWarpsMax = std::max(1u, std::min<uint32_t>(hotWarpsMax, static_cast<uint32_t>(atoi(env))));
+    hsp.oMirror = hsp.oStage + hotWarpsMax * 2 * kStageBuf;
+    hsp.mirrorBytes = (hotWarpsMax >= 4)
+        ? std::min<uint32_t>(pd.tableBytes & ~15u, (room - hotWarpsMax * 2 * kStageBuf) & ~15u) : 0;
+    hotFixed = hsp.oMirror + hsp.mirrorBytes + 256;
+  }
+  if (hotWarpsMax < 4)
+    useHot = false;
+  auto hotWalk = stream_hot_kernel<132, 1>;
+  if (useHot) {
+    if (hot->entryBytes == 2)
+      hotWalk = (hot->stride == 260) ? stream_hot_kernel<260, 2> : stream_hot_kernel<516, 2>;
+    else
+      hotWalk = (hot->stride == kHotStrideAscii) ? stream_hot_kernel<132, 1> : stream_hot_kernel<260, 1>;
+  }
+  if (useHot)
+    TRY(cudaFuncSetAttribute(hotWalk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hotFixed)));
 
   // chunk size of a window: one chunk per lane of the whole chip if that
   // gives 1 KB .. 16 KB, a multiple of 16
@@ -849,8 +1269,17 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
     const unsigned rgrid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(geo.smCount, (nChunks + 1023) / 1024)));
     auto walk = track ? walkTrack : walkPlain;
     TRY(cudaMemsetAsync(nExtras, 0, sizeof(unsigned long long), stream));
+    const bool hotNow = useHot && !track;
     walk<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk), nChunks, cands, nCand,
-                                          v0, kLookback, extras, nExtras);
+                                          v0, kLookback, extras, nExtras, !hotNow);
+    if (hotNow) {
+      const uint64_t warpsNeeded = (nChunks + 31) / 32;
+      const unsigned hgrid = static_cast<unsigned>(std::min<uint64_t>(geo.smCount, warpsNeeded));
+      const unsigned hwarps = static_cast<unsigned>(std::min<uint64_t>(hotWarpsMax, (warpsNeeded + hgrid - 1) / hgrid));
+      hotWalk<<<hgrid, hwarps * 32, hotFixed, stream>>>(
+          pd, *hot, hsp, wText, bytes, static_cast<uint32_t>(chunk), nChunks, cands, nCand);
+      ++*launches;
+    }
     (track ? extraTrack : extraPlain)<<<grid, threads, smem, stream>>>(pd, wText, bytes, static_cast<uint32_t>(chunk),
                                                                        cands, extras, nExtras);
     ++*launches;
@@ -1088,7 +1517,7 @@ int run_stream(const ProgramDev &pd, const LaunchGeometry &geo,
 
 } // anonymous
 
-int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &,
+int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &, const HotDev *hot,
                  const LaunchGeometry &geo, const uint8_t *dText, uint64_t len,
                  int style, red_b200_outcome *out, cudaStream_t stream,
                  int *launches, std::string &why) {
@@ -1105,18 +1534,18 @@ int match_stream(const ProgramDev &pd, bool smemTable, const DeviceImage &,
   const bool cls8 = pd.clsMaxOffset < 256;
   if (smemTable) {
     if (pd.unitShift == 0)
-      return cls8 ? run_stream<true, 1, uint8_t>(pd, geo, dText, len, style, out, stream, launches, why)
-                  : run_stream<true, 1, uint16_t>(pd, geo, dText, len, style, out, stream, launches, why);
+      return cls8 ? run_stream<true, 1, uint8_t>(pd, hot, geo, dText, len, style, out, stream, launches, why)
+                  : run_stream<true, 1, uint16_t>(pd, hot, geo, dText, len, style, out, stream, launches, why);
     if (pd.unitShift == 1)
-      return cls8 ? run_stream<true, 2, uint8_t>(pd, geo, dText, len, style, out, stream, launches, why)
-                  : run_stream<true, 2, uint16_t>(pd, geo, dText, len, style, out, stream, launches, why);
+      return cls8 ? run_stream<true, 2, uint8_t>(pd, hot, geo, dText, len, style, out, stream, launches, why)
+                  : run_stream<true, 2, uint16_t>(pd, hot, geo, dText, len, style, out, stream, launches, why);
     if (pd.unitShift == 8)
-      return run_stream<true, 9, uint16_t>(pd, geo, dText, len, style, out, stream, launches, why);
+      return run_stream<true, 9, uint16_t>(pd, hot, geo, dText, len, style, out, stream, launches, why);
     why = "unsupported table layout";
     return RED_B200_EINTERNAL;
   }
-  return cls8 ? run_stream<false, 0, uint8_t>(pd, geo, dText, len, style, out, stream, launches, why)
-              : run_stream<false, 0, uint16_t>(pd, geo, dText, len, style, out, stream, launches, why);
+  return cls8 ? run_stream<false, 0, uint8_t>(pd, hot, geo, dText, len, style, out, stream, launches, why)
+              : run_stream<false, 0, uint16_t>(pd, hot, geo, dText, len, style, out, stream, launches, why);
 }
 
 } // namespace red_b200

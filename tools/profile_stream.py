@@ -19,12 +19,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gb", type=float, default=4.0)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--program", default="union64")
+    ap.add_argument("--regex", default=None, help="a loose-start regex instead of --program")
     a = ap.parse_args()
     pool = bench.host_pool(1234)
     tp = torch.from_numpy(pool[0].copy()).cuda()
     reps = int(a.gb * (1 << 30)) // tp.numel() + 1
     text = tp.repeat(reps)
-    prog = red.Program(bench.load_program_blob("union64"))
+    if a.regex:
+        rp = red.Parser()
+        rp.add(a.regex.encode(), 1, 2)
+        prog = red.compile(rp)
+        a.program = "regex"
+    else:
+        prog = red.Program(bench.load_program_blob(a.program))
     styles = ["last"] if a.once else ["instant", "first", "tangent", "last", "full"]
     for sty in styles:
         o = prog.match_stream_device(text, "match", sty)
@@ -37,7 +45,7 @@ def main():
             o = prog.match_stream_device(text, "match", sty)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / 3 * 1e3
-        print("union64 %-8s %6.2f GB  %8.3f ms  %8.1f GB/s  %4.1f launches/call  outcome %s" % (
+        print(a.program + " %-8s %6.2f GB  %8.3f ms  %8.1f GB/s  %4.1f launches/call  outcome %s" % (
             sty, text.numel() / 1e9, ms, text.numel() / ms / 1e6, (prog.launch_count - l0) / 3, tuple(o)), flush=True)
     prog.close()
     if a.once:
