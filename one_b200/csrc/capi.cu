@@ -257,7 +257,9 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
       prog->hotStream = whole;
       if (whole.coverage < 1000) {
         const uint32_t rowBytes = (ascii ? 128u : 256u) * 2 + 4;
-        const uint32_t fit = (prog->geo.maxSmemOptin > 140 * 1024) ? (prog->geo.maxSmemOptin - 140 * 1024) / rowBytes : 0;
+        uint32_t fit = (prog->geo.maxSmemOptin > 140 * 1024) ? (prog->geo.maxSmemOptin - 140 * 1024) / rowBytes : 0;
+        if (prog->hotStreamStates)  // RED_B200_STREAM_HOT_STATES (tests: lanes that leave the image)
+          fit = std::min(fit, std::max(prog->hotStreamStates, kHotMax + 2) + 1);
         HotDev wide;
         if ((fit > kHotMax + 1) &&
             (upload_hot(prog, visits.data() + nStates, ascii, false, wide, std::min(fit - 1, kHotMaxWide)) == cudaSuccess))
@@ -509,6 +511,8 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     prog->hotTune.batchLines = atoi(env);
   if (const char *env = getenv("RED_B200_HOT_SLOT_BYTES"))
     prog->hotTune.slotBytes = atoi(env);
+  if (const char *env = getenv("RED_B200_STREAM_HOT_STATES"))
+    prog->hotStreamStates = static_cast<uint32_t>(std::max(0, atoi(env)));
   if (prog->hotEnabled) {
     if (((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, true, prog->hotDev[0])) != cudaSuccess) ||
         ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, false, prog->hotDev[1])) != cudaSuccess)) {

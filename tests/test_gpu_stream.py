@@ -43,6 +43,30 @@ def test_stream_union64_on_log_text(gpu_red, vectors, oracle_cls):
     check_stream(gpu_red, oracle_cls, blob, b"Quarantined " + noise, "head")
 
 
+@pytest.mark.parametrize("env", [
+    {"RED_B200_STREAM_HOT": "0"},                                        # the walk on the full table (chunk engine)
+    {"RED_B200_STREAM_HOT": "1", "RED_B200_STREAM_HOT_STATES": "257"},   # two-byte codes, lanes leave the image
+    {"RED_B200_STREAM_HOT": "1", "RED_B200_HOT_PROFILE": "0"},           # one-byte codes by breadth-first order
+    {"RED_B200_HOT_ASCII": "-1"},                                        # 256-column rows
+    {"RED_B200_HOT_ASCII": "1"},                                         # 128-column rows whatever the text holds
+    {"RED_B200_STREAM_HOT_WARPS": "5"},
+])
+def test_stream_hot_kernel_variants(gpu_red, vectors, oracle_cls, monkeypatch, env):
+    """stream_hot_kernel: code widths, row widths, the way out of the image and
+    back, bytes >= 128 - all against the oracle."""
+    from one_b200 import synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    blob = unz(next(c for c in vectors["cases"] if c["name"] == "union64")["program"])
+    text, _, _ = synth.make_corpus(30000, seed=33)
+    raw = bytearray(text.tobytes())
+    check_stream(gpu_red, oracle_cls, blob, bytes(raw), ("plain", env))
+    rng = np.random.RandomState(9)
+    for at in rng.randint(0, len(raw), size=400):
+        raw[at] = 0x80 + (at % 120)
+    check_stream(gpu_red, oracle_cls, blob, bytes(raw), ("high bytes", env))
+
+
 def test_stream_edge_sizes(gpu_red, vectors, oracle_cls):
     case = next(c for c in vectors["cases"] if c["name"] == "newyork")
     blob = unz(case["program"])
