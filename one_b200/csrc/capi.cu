@@ -360,7 +360,7 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
 
   auto cleanup = [&](cudaError_t e, const char *what) {
     cudaFree(prog->dTable); cudaFree(prog->dCls); cudaFree(prog->dResults);
-    cudaFree(prog->dLeader); cudaFree(prog->dCounters);
+    cudaFree(prog->dLeader);
     delete prog;
     return cuda_fail(e, what);
   };
@@ -393,8 +393,6 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
       return cleanup(err, "cudaMemcpy(leader)");
   }
 
-  if ((err = cudaMalloc(&prog->dCounters, kCounters * sizeof(unsigned long long))) != cudaSuccess)
-    return cleanup(err, "cudaMalloc(counters)");
   {
     // [256 * 8 reset states | 256 reset counts]
     const size_t statesBytes = img.resetStates.size() * 4;
@@ -548,7 +546,6 @@ void red_b200_program_free(red_b200_program *prog) {
   cudaFree(prog->dCls);
   cudaFree(prog->dResults);
   cudaFree(prog->dLeader);
-  cudaFree(prog->dCounters);
   delete prog;
 }
 

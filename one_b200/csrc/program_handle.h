@@ -23,7 +23,6 @@ using red_b200::LaunchGeometry;
 using red_b200::ParsedProgram;
 using red_b200::ProgramDev;
 
-constexpr unsigned kCounters = 256;
 
 struct red_b200_program {
   int device = 0;
@@ -39,8 +38,6 @@ struct red_b200_program {
   void *dCls = nullptr;
   void *dResults = nullptr;
   void *dLeader = nullptr;
-  unsigned long long *dCounters = nullptr;  // kCounters block counters, used round-robin
-  std::atomic<unsigned> nextCounter{0};  // launches may come from several host threads
   BatchTuning tune;
   std::mutex mu;        // guards the lazily created host pipeline
   HostPipe *pipe = nullptr;

@@ -56,30 +56,11 @@ def launch_list(src, dst, summary):
     return agg
 
 
-def main():
-    for a, b in (("r2_bench.json", "r2_bench_full_100M.json"), ("r2_sweep_instant.txt", "r2_sweep_instant.txt"),
-                 ("r2_sweep_last.txt", "r2_sweep_last.txt"), ("r2_sweep_full.txt", "r2_sweep_full.txt"),
-                 ("r2_sweep_single.txt", "r2_sweep_single.txt"), ("r2_stream.txt", "r2_stream.txt")):
-        if os.path.exists(os.path.join(SRC, a)):
-            shutil.copy(os.path.join(SRC, a), os.path.join(DST, b))
-    agg = launch_list(os.path.join(SRC, "r2_launches.csv"), os.path.join(DST, "r2_launches.csv"),
-                      os.path.join(DST, "r2_launches_summary.csv"))
-    if os.path.exists(os.path.join(SRC, "r2_stream_launches.csv")):
-        launch_list(os.path.join(SRC, "r2_stream_launches.csv"), os.path.join(DST, "r2_stream_launches.csv"),
-                    os.path.join(DST, "r2_stream_launches_summary.csv"))
-    hot = next(v for k, v in agg.items() if "batch_hot_kernel" in k)
-    per_line = hot[2] / hot[0] / LINES
-    with open(os.path.join(DST, "traffic.json"), "w") as fh:
-        json.dump({"dram_bytes_per_line": per_line, "lines_in_capture": LINES,
-                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of one step = one batch_hot_kernel launch "
-                           "(ncu, profiles/r2_launches.csv), scaled by lines"}, fh)
-    # the full capture of one batch_hot_kernel launch
-    rep = os.path.join(SRC, "r2_hot.ncu-rep")
+def ncu_summary(rep, dst, command):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
-    out = {"kernel": vals[hdr.index("Kernel Name")], "command": "bench.py --lines 20000000 --steps 3 --warmup 3 --no-e2e "
-           "--no-cpu --no-configs (4th launch of the kernel)", "metrics": {}}
+    out = {"kernel": vals[hdr.index("Kernel Name")], "command": command, "metrics": {}}
     for h, u, v in zip(hdr, units, vals):
         if h in KEEP:
             try:
@@ -106,8 +87,33 @@ def main():
             except ValueError:
                 pass
     out["memory_instructions"] = {k: {"executed": a[0], "shared_wavefronts": a[1], "ideal": a[2]} for k, a in ops.items()}
-    with open(os.path.join(DST, "r2_hot_ncu_summary.json"), "w") as fh:
+    with open(dst, "w") as fh:
         json.dump(out, fh, indent=1)
+
+
+def main():
+    for a, b in (("r2_bench.json", "r2_bench_full_100M.json"), ("r2_sweep_instant.txt", "r2_sweep_instant.txt"),
+                 ("r2_sweep_last.txt", "r2_sweep_last.txt"), ("r2_sweep_full.txt", "r2_sweep_full.txt"),
+                 ("r2_sweep_single.txt", "r2_sweep_single.txt"), ("r2_stream.txt", "r2_stream.txt")):
+        if os.path.exists(os.path.join(SRC, a)):
+            shutil.copy(os.path.join(SRC, a), os.path.join(DST, b))
+    agg = launch_list(os.path.join(SRC, "r2_launches.csv"), os.path.join(DST, "r2_launches.csv"),
+                      os.path.join(DST, "r2_launches_summary.csv"))
+    if os.path.exists(os.path.join(SRC, "r2_stream_launches.csv")):
+        launch_list(os.path.join(SRC, "r2_stream_launches.csv"), os.path.join(DST, "r2_stream_launches.csv"),
+                    os.path.join(DST, "r2_stream_launches_summary.csv"))
+    hot = next(v for k, v in agg.items() if "batch_hot_kernel" in k)
+    per_line = hot[2] / hot[0] / LINES
+    with open(os.path.join(DST, "traffic.json"), "w") as fh:
+        json.dump({"dram_bytes_per_line": per_line, "lines_in_capture": LINES,
+                   "note": "dram__bytes_read.sum + dram__bytes_write.sum of one step = one batch_hot_kernel launch "
+                           "(ncu, profiles/r2_launches.csv), scaled by lines"}, fh)
+    # the full captures: one batch_hot_kernel launch, one stream_hot_kernel launch
+    ncu_summary(os.path.join(SRC, "r2_hot.ncu-rep"), os.path.join(DST, "r2_hot_ncu_summary.json"),
+                "bench.py --lines 20000000 --steps 3 --warmup 3 --no-e2e --no-cpu --no-configs (4th launch of the kernel)")
+    if os.path.exists(os.path.join(SRC, "r2_stream_hot.ncu-rep")):
+        ncu_summary(os.path.join(SRC, "r2_stream_hot.ncu-rep"), os.path.join(DST, "r2_stream_hot_ncu_summary.json"),
+                    "tools/profile_stream.py --once (union64 over 4.3 GB, style last: the main window's walk)")
     # SASS excerpt: the bulk copy, the barrier instructions, the interior loop
     sass = subprocess.run([os.path.join(ROOT, "tools", "sass_of.sh"),
                            os.path.join(ROOT, "one_b200", "_build", "kernels_hot.cu.o"),
@@ -122,8 +128,8 @@ def main():
     keep.update(range(max(0, best - 12), min(len(sass), best + 90)))
     with open(os.path.join(DST, "r2_hot_sass_excerpt.txt"), "w") as fh:
         fh.write("# cuobjdump -sass of batch_hot_kernel<Instant, deferred, 128-column rows> (one_b200/_build/kernels_hot.cu.o):\n"
-                 "# the bulk-async copy (UBLKCP), the mbarrier instructions (SYNCS), the index prefetch (LDGSTS),\n"
-                 "# the text loads (LDS.128) and the interior loop (16 x PRMT / IMAD / LDS.U8 per chunk).\n"
+                 "# the bulk-async copy (UBLKCP), the mbarrier instructions (SYNCS), the text loads (LDS.128), the\n"
+                 "# re-alignment (SEL / PRMT) and the interior loop (16 x PRMT / IMAD / LDS.U8 per chunk).\n"
                  "# counts in the whole kernel: %s\n" % ", ".join(
                      "%s %d" % (k, sum(1 for ln in sass if k in ln)) for k in ("UBLKCP", "SYNCS", "LDGSTS", "LDS.128", "LDS.U8", "LDG")))
         last = -2
