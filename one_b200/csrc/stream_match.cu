@@ -568,12 +568,15 @@ stream_hot_kernel(const ProgramDev pd, const HotDev hd, const HotStreamParams sp
     bool active = go && (n != 0);
     uint32_t flagPos = kNoPos, flagCode = 0;  // the last chunk in which an accepting state was entered
 
-    // the rows this lane copies in every stage: row (lane / 4) + 8 i, piece lane % 4
-    const uint32_t piece = (lane & 3) * 16;
+    // the rows this lane copies in every stage: row (lane % 8) + 8 i, piece lane / 8
+    // (the eight lanes of a quarter warp write to eight rows: 80 bytes apart,
+    // eight different bank groups; the four pieces of a row, one per quarter
+    // warp, are one 64-byte request to L2)
+    const uint32_t piece = (lane >> 3) * 16;
     auto issue = [&](uint32_t st, uint32_t buf) {
 #pragma unroll
       for (uint32_t i = 0; i < 4; ++i) {
-        const uint32_t row = i * 8 + (lane >> 2);
+        const uint32_t row = i * 8 + (lane & 7);
         const uint64_t rc = c0 + row;
         const uint64_t rBegin = rc * chunkBytes;
         const uint64_t rBytes = (rc < nChunks) ? min(static_cast<uint64_t>(chunkBytes), len - rBegin) : 0;
