@@ -477,6 +477,9 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         __threadfence_block();
         const uint32_t total = lds32_volatile(ctlAddr + 4);
         asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctlAddr + 12), "r"(total) : "memory");
+        __threadfence_block();
+        for (uint32_t s = 0; s < R; ++s)  // wake the sleepers
+          mbar_arrive(barsAddr + 8 * (2 * R + s));
       }
     }
     return;
@@ -514,18 +517,24 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        piece wakes whoever waits there (measured: ~50 wake-ups per wait, the
        waiters' instructions a quarter of all the kernel issued).  So only the
        warp with the batch's first tile waits at full[s]; it then arrives at
-       ready[s], where the others sleep through the copy and wake up once. */
-    const uint32_t waitBar = barsAddr + 8 * ((t == 0) ? s : 2 * R + s);
+       ready[s], where the others sleep through the copy.  ready[s] is a place
+       to sleep and no more - the last producer arrives there too, to wake
+       those whose batch will never come: whether the batch is in is always
+       read off full[s] and the slot's sequence number. */
+    const uint32_t par = (qq / R) & 1;
+    const uint32_t fullBar = barsAddr + 8 * s, readyBar = barsAddr + 8 * (2 * R + s);
     for (uint32_t spins = 0;; ++spins) {
-      if (mbar_try_wait(waitBar, (qq / R) & 1)) {
+      const bool woke = (t != 0) && mbar_try_wait(readyBar, par);
+      const bool landed = (t != 0) ? mbar_test_wait(fullBar, par) : mbar_try_wait(fullBar, par);
+      if (landed) {
         if (lds32_volatile(seqAddr) == qq)
           break;
         __nanosleep(200);  // an earlier phase: batch qq - R is still to come
       }
-      // not there yet: is there such a batch at all?  (at full[s] looked at
-      // every so often only: a poll is a shared-memory wavefront the walkers
-      // want; a wait that nothing ends comes back after a few microseconds)
-      if ((t != 0) || ((spins & 7) == 7)) {
+      // not there yet: is there such a batch at all?  (a poll is a
+      // shared-memory wavefront the walkers want: the sleepers look when they
+      // are woken, and every so often)
+      if ((t == 0) || woke || ((spins & 7) == 7)) {
         if (qq >= lds32_volatile(ctlAddr + 12)) {
           ended = true;
           break;
