@@ -1,11 +1,9 @@
-/* nfa.cpp - see nfa.h.  Each combinator states the reference function whose
-   effect on the automaton it reproduces (reference: lib/Nfa.cpp). */
+/* nfa.cpp - see nfa.h. */
 
 #include "nfa.h"
 
-#include <deque>
+#include <algorithm>
 #include <limits>
-#include <unordered_map>
 
 #include "../../../include/red_b200.h"
 
@@ -20,233 +18,228 @@ void fail_api(const std::string &msg) { throw CompileError{RED_B200_EAPI, msg}; 
 void fail_limit(const std::string &msg) { throw CompileError{RED_B200_ELIMIT, msg}; }
 void fail_internal(const std::string &msg) { throw CompileError{RED_B200_EINTERNAL, msg}; }
 
-// reference: NfaObj::newState (lib/Nfa.cpp:95) - id 0 is never a node
+/* How the combinators are put together here.  What a combinator must DO to the
+   automaton is fixed by the reference (nfa.h, parity note; lib/Nfa.cpp:160-262
+   is where its effects were read off); how it is done is this file's:
+
+     survey(x)      one traversal of a fragment: its nodes, and every edge that
+                    enters a node which accepts at this moment;
+     twin(edges, t) each surveyed edge gets a copy that goes to t instead;
+     absorb(a, b)   a takes over b's outgoing edges (duplicates dropped).
+
+   sequence = twin the entering edges to the right operand (+ absorb if the
+   left one accepts at once) and stop the left side from accepting; star = twin
+   them back to the start; alternate = absorb.  repeat() first takes all the
+   copies it needs from the untouched operand and then chains them. */
+
+// (id 0 is never a node; the reference charges its budget for the slot: the
+// limits agree to the state)
 NodeId Nfa::node(int32_t result) {
-  if (nodes_.empty())
+  if (nodes_.empty()) {
     nodes_.resize(1);
+    used_ += 1;
+  }
   if (nodes_.size() >= static_cast<size_t>(std::numeric_limits<NodeId>::max()))
     fail_limit("nfa state id overflow");
-  uint64_t cost = (nodes_.size() == 1) ? 2 : 1;
-  if (used_ + cost > budget_)
+  if (used_ + 1 > budget_)
     fail_limit("state budget exceeded");
-  used_ += cost;
-  nodes_.emplace_back();
-  nodes_.back().result = result;
+  used_ += 1;
+  Node fresh;
+  fresh.result = result;
+  nodes_.push_back(std::move(fresh));
   return static_cast<NodeId>(nodes_.size() - 1);
 }
 
 void Nfa::addEdge(Node &n, const Edge &e) {
-  for (const Edge &have : n.out)
-    if (have == e)
-      return;
-  n.out.push_back(e);
+  if (std::find(n.out.begin(), n.out.end(), e) == n.out.end())
+    n.out.push_back(e);
 }
 
-// nodes reachable from `from` (itself included), ascending ids
-std::vector<NodeId> Nfa::reachable(NodeId from) const {
+Nfa::Survey Nfa::survey(NodeId from) const {
+  Survey sv;
   std::vector<char> seen(nodes_.size(), 0);
-  std::deque<NodeId> todo;
+  std::vector<NodeId> stack(1, from);
   seen[from] = 1;
-  todo.push_back(from);
-  while (!todo.empty()) {
-    NodeId id = todo.front();
-    todo.pop_front();
+  while (!stack.empty()) {
+    const NodeId id = stack.back();
+    stack.pop_back();
     for (const Edge &e : nodes_[id].out)
       if (!seen[e.to]) {
         seen[e.to] = 1;
-        todo.push_back(e.to);
+        stack.push_back(e.to);
       }
   }
-  std::vector<NodeId> out;
-  for (size_t i = 1; i < seen.size(); ++i)
-    if (seen[i])
-      out.push_back(static_cast<NodeId>(i));
-  return out;
+  for (size_t id = 1; id < seen.size(); ++id) {
+    if (!seen[id])
+      continue;
+    sv.nodes.push_back(static_cast<NodeId>(id));
+    const std::vector<Edge> &out = nodes_[id].out;
+    for (size_t k = 0; k < out.size(); ++k)
+      if (nodes_[out[k].to].result > 0)
+        sv.entering.push_back({static_cast<NodeId>(id), out[k]});
+  }
+  return sv;
+}
+
+void Nfa::twin(const Survey &sv, NodeId target) {
+  for (const Survey::Entering &en : sv.entering) {
+    Edge copy = en.edge;
+    copy.to = target;
+    addEdge(nodes_[en.from], copy);
+  }
+}
+
+void Nfa::absorb(NodeId into, NodeId from) {
+  const std::vector<Edge> taken = nodes_[from].out;  // (into may be from)
+  for (const Edge &e : taken)
+    addEdge(nodes_[into], e);
+}
+
+NodeId Nfa::fragment(const Edge &proto) {
+  const NodeId start = node(0);
+  Edge e = proto;
+  e.to = goalNode();
+  nodes_[start].out.push_back(e);
+  return start;
 }
 
 NodeId Nfa::oneOf(const ByteSet &set) {
-  NodeId a = node(0);
-  NodeId b = goalNode();
   Edge e;
-  e.to = b;
   e.on = set;
-  nodes_[a].out.push_back(e);
-  return a;
+  return fragment(e);
 }
 
 NodeId Nfa::anyByte() {
-  ByteSet all;
-  all.fill();
-  return oneOf(all);
+  Edge e;
+  e.on.fill();
+  return fragment(e);
 }
 
 NodeId Nfa::wildcard() { return star(anyByte()); }
 
 NodeId Nfa::endMark(int32_t result) {
-  NodeId a = node(0);
-  NodeId b = goalNode();
   Edge e;
-  e.to = b;
   e.endMark = result;
-  nodes_[a].out.push_back(e);
-  return a;
+  return fragment(e);
 }
 
-// reference: stateUnion (lib/Nfa.cpp:160) - y's initial edges are copied into
-// x's initial node, whatever else points at that node
+// x|y: x's start takes over y's first edges - whatever else points at that
+// start (that is the reference's union, over-approximation included)
 NodeId Nfa::alternate(NodeId x, NodeId y) {
-  if ((nodes_[x].result <= 0) && (nodes_[y].result > 0))
-    nodes_[x].result = nodes_[y].result;
-  const std::vector<Edge> copy = nodes_[y].out;  // x may be y
-  for (const Edge &e : copy)
-    addEdge(nodes_[x], e);
+  Node &left = nodes_[x];
+  if ((left.result <= 0) && (nodes_[y].result > 0))
+    left.result = nodes_[y].result;
+  absorb(x, y);
   return x;
 }
 
-// reference: stateConcat (lib/Nfa.cpp:171) - every edge that enters an
-// accepting node of x gets a twin that enters y; x's accepting nodes stop
-// accepting (x itself keeps accepting only if y accepts too)
+// xy: what entered an accepting node of x may enter y instead; x stops
+// accepting - except that a start that accepted keeps doing so if y's does
 NodeId Nfa::sequence(NodeId x, NodeId y) {
-  if (!x)
-    return y;
-  if (!y)
-    return x;
-  struct Pending { NodeId from; Edge e; };
-  std::vector<NodeId> accepting;
-  std::vector<Pending> entering;
-  for (NodeId id : reachable(x)) {
-    if (nodes_[id].result > 0)
-      accepting.push_back(id);
-    for (const Edge &e : nodes_[id].out)
-      if (nodes_[e.to].result > 0)
-        entering.push_back({id, e});
-  }
-  for (Pending &p : entering) {
-    Edge twin = p.e;
-    twin.to = y;
-    addEdge(nodes_[p.from], twin);
-  }
-  const bool xAccepts = nodes_[x].result > 0;
-  const bool yAccepts = nodes_[y].result > 0;
-  if (xAccepts) {
-    const std::vector<Edge> copy = nodes_[y].out;
-    for (const Edge &e : copy)
-      addEdge(nodes_[x], e);
-  }
-  int32_t keep = (xAccepts && yAccepts) ? nodes_[x].result : 0;
-  for (NodeId id : accepting)
+  if (!x || !y)
+    return x ? x : y;
+  const Survey sv = survey(x);
+  const bool startAccepted = nodes_[x].result > 0;
+  const int32_t kept = (startAccepted && (nodes_[y].result > 0)) ? nodes_[x].result : 0;
+  twin(sv, y);
+  if (startAccepted)
+    absorb(x, y);
+  for (NodeId id : sv.nodes)
     nodes_[id].result = 0;
-  if (keep > 0)
-    nodes_[x].result = keep;
+  nodes_[x].result = kept;
   return x;
 }
 
-// reference: stateOptional (lib/Nfa.cpp:208)
 NodeId Nfa::optional(NodeId x) {
   nodes_[x].result = goal_;
   return x;
 }
 
-// reference: stateKleenStar (lib/Nfa.cpp:214) - edges entering an accepting
-// node get a twin back to the start
+// x*: what entered an accepting node may go back to the start; the start accepts
 NodeId Nfa::star(NodeId x) {
-  struct Pending { NodeId from; Edge e; };
-  std::vector<Pending> entering;
-  for (NodeId id : reachable(x))
-    for (const Edge &e : nodes_[id].out)
-      if (nodes_[e.to].result > 0)
-        entering.push_back({id, e});
-  for (Pending &p : entering) {
-    Edge twin = p.e;
-    twin.to = x;
-    addEdge(nodes_[p.from], twin);
-  }
+  twin(survey(x), x);
   return optional(x);
 }
 
-// reference: stateClosure (lib/Nfa.cpp:224) - x{min,max}; max < 0 = unbounded.
-// All copies are taken from x before x itself is modified.
-NodeId Nfa::repeat(NodeId x, int min, int max) {
-  if (min == 0) {
-    if (max < 0)
-      return star(x);
-    NodeId opt = 0;
-    for (int i = 1; i < max; ++i)
-      opt = sequence(opt, optional(clone(x)));
-    return sequence(optional(x), opt);
-  }
-  if (min < 0)
-    min = max;
-  NodeId tail = 0;
-  if (max < 0)
-    tail = star(clone(x));
-  else
-    for (int i = 0; i < max - min; ++i)
-      tail = sequence(tail, optional(clone(x)));
-  NodeId head = 0;
-  for (int i = 1; i < min; ++i)
-    head = sequence(head, clone(x));
-  head = sequence(x, head);
-  return sequence(head, tail);
+NodeId Nfa::chain(const std::vector<NodeId> &parts) {
+  NodeId all = 0;
+  for (NodeId part : parts)
+    all = sequence(all, part);
+  return all;
 }
 
-// reference: stateIgnoreCase (lib/Nfa.cpp:252)
+// x{min,max}; max < 0: no upper bound; min < 0: exactly max
+NodeId Nfa::repeat(NodeId x, int min, int max) {
+  if ((min == 0) && (max < 0))
+    return star(x);
+  if (min < 0)
+    min = max;
+  // every copy from the operand as it is now: it is the first link of the chain
+  // and changes as soon as something is appended to it
+  const int mandatoryCopies = (min > 0) ? min - 1 : 0;
+  const int optionalCopies = (max < 0) ? 0 : (min > 0 ? max - min : max - 1);
+  std::vector<NodeId> must, may;
+  for (int i = 0; i < optionalCopies; ++i)
+    may.push_back(clone(x));
+  const NodeId loop = ((max < 0) && (min > 0)) ? clone(x) : 0;
+  for (int i = 0; i < mandatoryCopies; ++i)
+    must.push_back(clone(x));
+  for (NodeId &id : may)
+    id = optional(id);
+  const NodeId rest = loop ? star(loop) : chain(may);
+  if (min == 0)
+    return sequence(optional(x), rest);
+  return sequence(sequence(x, chain(must)), rest);
+}
+
+void ByteSet::foldAsciiCase() {
+  // 'A'..'Z' are bits 1..26 of the second word, 'a'..'z' bits 33..58
+  const uint64_t upper = w[1] & 0x0000000007fffffeull;
+  const uint64_t lower = w[1] & 0x07fffffe00000000ull;
+  w[1] |= (upper << 32) | (lower >> 32);
+}
+
 NodeId Nfa::foldCase(NodeId x) {
-  for (NodeId id : reachable(x))
-    for (Edge &e : nodes_[id].out) {
-      for (unsigned c = 'A'; c <= 'Z'; ++c)
-        if (e.on.has(c))
-          e.on.add(c + 32);
-      for (unsigned c = 'a'; c <= 'z'; ++c)
-        if (e.on.has(c))
-          e.on.add(c - 32);
-    }
+  for (NodeId id : survey(x).nodes)
+    for (Edge &e : nodes_[id].out)
+      e.on.foldAsciiCase();
   return x;
 }
 
-// reference: deepCopyState (lib/Nfa.cpp:111) - copy of everything reachable
+// a copy of everything reachable from x (the shape is what matters, not the numbering)
 NodeId Nfa::clone(NodeId x) {
   if (!x)
     return x;
-  std::unordered_map<NodeId, NodeId> twin;
-  // iterative preorder copy; the shape is what matters, not the numbering
-  std::vector<NodeId> order = reachable(x);
-  for (NodeId id : order)
-    twin[id] = node(nodes_[id].result);
-  for (NodeId id : order) {
+  const std::vector<NodeId> members = survey(x).nodes;
+  std::vector<NodeId> copyOf(nodes_.size(), 0);
+  for (NodeId id : members)
+    copyOf[id] = node(nodes_[id].result);
+  for (NodeId id : members) {
     std::vector<Edge> out = nodes_[id].out;
     for (Edge &e : out)
-      e.to = twin[e.to];
-    nodes_[twin[id]].out = std::move(out);
+      e.to = copyOf[e.to];
+    nodes_[copyOf[id]].out.swap(out);
   }
-  return twin[x];
+  return copyOf[x];
 }
 
-// reference: selfUnion (lib/Nfa.cpp:305)
 void Nfa::joinInitial(NodeId x) {
   init_ = init_ ? alternate(init_, x) : x;
 }
 
-// reference: dropUselessTransitions (lib/Nfa.cpp:313) - one pass, as there
+// edges into nodes that neither accept nor lead anywhere go (one pass: a node
+// that only now has no edges left stays, as in the reference), and so do
+// repeated edges
 void Nfa::pruneDeadEdges() {
-  std::vector<char> useless(nodes_.size(), 0);
+  std::vector<char> dead(nodes_.size(), 0);
   for (size_t id = 1; id < nodes_.size(); ++id)
-    if ((nodes_[id].result <= 0) && nodes_[id].out.empty())
-      useless[id] = 1;
+    dead[id] = (nodes_[id].result <= 0) && nodes_[id].out.empty();
   for (Node &n : nodes_) {
     std::vector<Edge> kept;
-    for (const Edge &e : n.out) {
-      if (useless[e.to])
-        continue;
-      bool dup = false;
-      for (const Edge &k : kept)
-        if (k == e) {
-          dup = true;
-          break;
-        }
-      if (!dup)
+    kept.reserve(n.out.size());
+    for (const Edge &e : n.out)
+      if (!dead[e.to] && (std::find(kept.begin(), kept.end(), e) == kept.end()))
         kept.push_back(e);
-    }
     n.out.swap(kept);
   }
 }

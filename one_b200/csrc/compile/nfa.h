@@ -62,6 +62,7 @@ struct ByteSet {
       w[i] |= o.w[i];
   }
   bool empty() const { return !(w[0] | w[1] | w[2] | w[3]); }
+  void foldAsciiCase();  // every ASCII letter in the set brings its other case along
   bool operator==(const ByteSet &o) const {
     return (w[0] == o.w[0]) && (w[1] == o.w[1]) && (w[2] == o.w[2]) && (w[3] == o.w[3]);
   }
@@ -105,20 +106,32 @@ public:
   NodeId wildcard();                  // .*
   NodeId endMark(int32_t result);
 
-  // combinators, with the reference's semantics (see header comment)
-  NodeId alternate(NodeId x, NodeId y);        // stateUnion
-  NodeId sequence(NodeId x, NodeId y);         // stateConcat
-  NodeId optional(NodeId x);                   // stateOptional
-  NodeId star(NodeId x);                       // stateKleenStar
-  NodeId repeat(NodeId x, int min, int max);   // stateClosure
-  NodeId foldCase(NodeId x);                   // stateIgnoreCase
-  NodeId clone(NodeId x);                      // deepCopyState
+  // combinators, with the reference's semantics (see header comment; the
+  // reference's name for the same effect in brackets)
+  NodeId alternate(NodeId x, NodeId y);        // x|y      [stateUnion]
+  NodeId sequence(NodeId x, NodeId y);         // xy       [stateConcat]
+  NodeId optional(NodeId x);                   // x?       [stateOptional]
+  NodeId star(NodeId x);                       // x*       [stateKleenStar]
+  NodeId repeat(NodeId x, int min, int max);   // x{m,n}   [stateClosure]
+  NodeId foldCase(NodeId x);                   // \i       [stateIgnoreCase]
+  NodeId clone(NodeId x);                      //          [deepCopyState]
 
-  void joinInitial(NodeId x);                  // selfUnion
-  void pruneDeadEdges();                       // dropUselessTransitions
+  void joinInitial(NodeId x);                  // one more rule of the union [selfUnion]
+  void pruneDeadEdges();                       // [dropUselessTransitions]
 
 private:
-  std::vector<NodeId> reachable(NodeId from) const;
+  // a fragment at one moment: its nodes (ascending) and the edges that enter
+  // a node which accepts right now
+  struct Survey {
+    struct Entering { NodeId from; Edge edge; };
+    std::vector<NodeId> nodes;
+    std::vector<Entering> entering;
+  };
+  Survey survey(NodeId from) const;
+  void twin(const Survey &sv, NodeId target);
+  void absorb(NodeId into, NodeId from);
+  NodeId fragment(const Edge &proto);            // start --proto--> goal
+  NodeId chain(const std::vector<NodeId> &parts);
   void addEdge(Node &n, const Edge &e);
 
   std::vector<Node> nodes_;
