@@ -85,3 +85,47 @@ def test_fuzz_random_programs(gpu_red, redlib, oracle_cls, seed):
             assert tuple(prog.match_stream_device(dt, "match", sty)) == orc.run(whole, "match", sty, False), \
                 (seed, rules, "stream", sty)
         prog.close()
+
+
+@pytest.mark.parametrize("seed,hot_states", [(11, None), (12, "6"), (13, "3")])
+def test_fuzz_profiled_paths(gpu_red, redlib, oracle_cls, monkeypatch, seed, hot_states):
+    """Batches large enough to be profiled (the staged kernel's hot set then
+    follows the text: with a cap of a few states lanes keep leaving it) and
+    streams long enough to get their own image - random programs, check/match
+    in the styles that kernel serves, and the stream in every style."""
+    import torch
+    if hot_states:
+        monkeypatch.setenv("RED_B200_HOT_STATES", hot_states)
+        monkeypatch.setenv("RED_B200_HOT_FORCE", "1")
+        monkeypatch.setenv("RED_B200_STREAM_HOT", "1")
+    rng = np.random.RandomState(seed)
+    done = 0
+    while done < 8:
+        rules = []
+        for _ in range(rng.randint(1, 5)):
+            flags = [2, 2, 0, 6, 3][rng.randint(5)]
+            rules.append((random_regex(rng).encode(), int(rng.randint(1, 6)), flags))
+        p = redlib.Parser()
+        try:
+            for pat, res, flags in rules:
+                p.add(pat, res, flags)
+            blob = redlib.compileToSerialized(p, 255)
+        except redlib.RedExcept:
+            continue
+        done += 1
+        prog, orc = gpu_red.Program(blob), oracle_cls(blob)
+        alphabet = list(b"abcdx0123 fe\xc3")
+        texts = [bytes(rng.choice(alphabet, size=rng.randint(0, 150)).astype(np.uint8)) for _ in range(9000)]
+        blob_t, starts, lens = pack(texts, lead=b"q" * int(rng.randint(0, 17)))
+        for verb in ("match", "check"):
+            for sty in ("instant", "last", "full"):
+                res, _, me = prog.match_batch_host(blob_t, starts, lens, verb, sty, want_starts=False)
+                eres, _, eme = orc.batch(blob_t, starts, lens, verb, sty)
+                bad = np.nonzero((res != eres) | (me != eme))[0]
+                assert bad.size == 0, (seed, rules, verb, sty, bad[:4], res[bad[:4]], eres[bad[:4]])
+        whole = b"\n".join(texts) + bytes(rng.choice(alphabet, size=300000).astype(np.uint8))
+        dt = torch.frombuffer(bytearray(whole) + bytearray(64), dtype=torch.uint8).cuda()[:len(whole)]
+        for sty in STYLES:
+            assert tuple(prog.match_stream_device(dt, "match", sty)) == orc.run(whole, "match", sty, False), \
+                (seed, rules, "stream", sty)
+        prog.close()
