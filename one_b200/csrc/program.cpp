@@ -148,7 +148,7 @@ bool parse_program(const void *ptr, size_t len, ParsedProgram &out,
 }
 
 void build_image(const ParsedProgram &pp, size_t smemBudget,
-                 DeviceImage &img, bool allowByteRows) {
+                 DeviceImage &img, bool allowByteRows, const uint64_t *visitsByOld) {
   const uint32_t n = pp.stateCount;
   const uint32_t C = pp.classCount;
 
@@ -183,6 +183,12 @@ void build_image(const ParsedProgram &pp, size_t smemBudget,
   for (uint32_t st = 0; st < n; ++st)
     if (pp.pureDead[st])
       order.push_back(st);
+  if (visitsByOld) {
+    auto byVisits = [&](uint32_t a, uint32_t b) { return visitsByOld[a] > visitsByOld[b]; };
+    std::stable_sort(order.begin(), order.begin() + firstAccept, byVisits);
+    std::stable_sort(order.begin() + firstAccept, order.begin() + firstAbsorb, byVisits);
+    std::stable_sort(order.begin() + firstAbsorb, order.begin() + firstPure, byVisits);
+  }
   img.acceptCount = firstPure - firstAccept;
   img.pureCount = n - firstPure;
   std::vector<uint32_t> oldToNew(n);

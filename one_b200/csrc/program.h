@@ -109,8 +109,12 @@ struct DeviceImage {
 };
 
 // smemBudget: bytes of shared memory the table may take
+// visitsByOld (optional, per state of the serialized program): inside each of
+// the four groups the states a profiled walk enters most come first, so that
+// the leading rows of a global table - the ones the kernels mirror in shared
+// memory - are the ones the text actually uses
 void build_image(const ParsedProgram &pp, size_t smemBudget, DeviceImage &img,
-                 bool allowByteRows = true);
+                 bool allowByteRows = true, const uint64_t *visitsByOld = nullptr);
 
 /* The hot image: what kernels_hot.cu keeps in shared memory.  Up to 255 states
    - the ones a walk over real text spends its time in, by measured visit

@@ -48,6 +48,11 @@ struct red_b200_program {
 
   // the hot image of the staged batch kernel (kernels_hot.cu)
   red_b200::HotDev hotDev[2]{};        // [0] style Instant, [1] styles Last and Full
+  red_b200::ProgramDev devBatch{};     // global-table programs: the same DFA with the states a profiled
+                                       // walk enters most in front (the shared-memory mirror's rows);
+                                       // check/match batches only - states handed to callers stay prog->dev's
+  bool haveDevBatch = false;
+  size_t smemBudget = 0;
   uint32_t hotStreamStates = 0;        // cap on that image's states (0: what fits)
   red_b200::HotDev hotStream{};        // the long-stream matcher's (two-byte codes where a byte is too small)
   red_b200::HotTuning hotTune;
