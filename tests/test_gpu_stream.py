@@ -175,12 +175,16 @@ def test_large_dfa_uses_global_table(gpu_red, redlib, oracle_cls):
         k = rng.randint(0, len(lines[i]))
         lines[i] = lines[i][:k] + kw + lines[i][k:]
     text, starts, lens = synth.pack_lines(lines)
+    # (30 000 lines: the first call's profile re-orders the states of the image
+    # the batch kernels use - the visited ones in front, for the shared-memory
+    # mirror; every style sees that image)
     for verb in ("check", "match"):
-        for sty in ("first", "last", "instant"):
+        for sty in ("first", "last", "instant", "tangent", "full"):
             res, ms, me = prog.match_batch_host(text, starts, lens, verb, sty)
             eres, ems, eme = orc.batch(text, starts, lens, verb, sty)
             assert np.array_equal(res, eres) and np.array_equal(ms, ems) and np.array_equal(me, eme), (verb, sty)
-    assert (eres > 0).sum() > 5000
+            if sty == "instant":
+                assert (eres > 0).sum() > 5000
     check_stream(gpu_red, oracle_cls, blob, text.tobytes()[:400000], "keywords2000")
     prog.close()
 
