@@ -65,6 +65,7 @@ constexpr uint32_t kSortBuckets = 256;    // by the line's length in bytes (long
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
 constexpr uint32_t kMaxSlots = 12;
 constexpr uint32_t kMaxProducers = 4;
+constexpr bool kDirectOutcomes = true;     // outcomes go straight to global memory (false: collected per batch, A/B)
 
 struct HotParams {
   // byte offsets into dynamic shared memory (behind its 256-byte alignment)
@@ -726,29 +727,42 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       const bool absorbed = done && wk.absorbed;
       const uint32_t mend = done ? wk.mend : 0;
       const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || absorbed) ? lineLen : mend) : 0;
-      sts32(mA + kMetaRes + 4 * idx, static_cast<uint32_t>(result));
-      sts32(mA + kMetaEnd + 4 * idx, end);
+      if (kDirectOutcomes) {
+        // straight to the line's place: the 256 outcomes of a batch are 1 KB per
+        // array, written within a few microseconds of each other - L2 puts the
+        // sectors together
+        const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
+        args.results[line] = result;
+        if (args.matchEnds)
+          args.matchEnds[line] = end;
+      }
+      else {
+        sts32(mA + kMetaRes + 4 * idx, static_cast<uint32_t>(result));
+        sts32(mA + kMetaEnd + 4 * idx, end);
+      }
     }
-    // the tile that finishes a batch writes the batch's outcomes back, coalesced
     __syncwarp();
     const long long tc2 = hp.dbg ? clock64() : 0;
-    uint32_t last = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      last = (atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaDone), 1u) == TPB - 1) ? 1 : 0;
-      __threadfence_block();
-    }
-    last = __shfl_sync(kFullMask, last, 0);
-    if (last) {
-      const uint64_t first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
-      for (uint32_t i = lane; i < cnt; i += 32) {
-        args.results[first + i] = static_cast<int32_t>(lds32(mA + kMetaRes + 4 * i));
-        if (args.matchEnds)
-          args.matchEnds[first + i] = lds32(mA + kMetaEnd + 4 * i);
+    if (!kDirectOutcomes) {
+      // the tile that finishes a batch writes the batch's outcomes back, coalesced
+      uint32_t last = 0;
+      if (lane == 0) {
+        __threadfence_block();
+        last = (atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaDone), 1u) == TPB - 1) ? 1 : 0;
+        __threadfence_block();
       }
-      if (lane == 0)
-        sts32(mA + kMetaDone, 0);
-      __syncwarp();
+      last = __shfl_sync(kFullMask, last, 0);
+      if (last) {
+        const uint64_t first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
+        for (uint32_t i = lane; i < cnt; i += 32) {
+          args.results[first + i] = static_cast<int32_t>(lds32(mA + kMetaRes + 4 * i));
+          if (args.matchEnds)
+            args.matchEnds[first + i] = lds32(mA + kMetaEnd + 4 * i);
+        }
+        if (lane == 0)
+          sts32(mA + kMetaDone, 0);
+        __syncwarp();
+      }
     }
     if (lane == 0)
       mbar_arrive(barsAddr + 8 * (R + s));
