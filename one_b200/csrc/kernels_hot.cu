@@ -26,8 +26,8 @@
      * the length sort (tiles of 32 lines of equal length in bytes, longest
        first; equal length very often means equal shape) happens inside the
        CTA, per batch, by the producer warp, whose index entries are loaded one
-       batch ahead; outcomes are collected per batch in shared memory and
-       written back coalesced;
+       batch ahead; every lane writes its line's outcome straight to global
+       memory;
      * styles that end at the first state needing a decision (Instant, Full)
        walk on an image in which such a state STICKS: the fast pass keeps no
        running maximum, the code behind a 16-byte chunk says whether anything
@@ -65,7 +65,6 @@ constexpr uint32_t kSortBuckets = 256;    // by the line's length in bytes (long
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
 constexpr uint32_t kMaxSlots = 12;
 constexpr uint32_t kMaxProducers = 4;
-constexpr bool kDirectOutcomes = true;     // outcomes go straight to global memory (false: collected per batch, A/B)
 
 struct HotParams {
   // byte offsets into dynamic shared memory (behind its 256-byte alignment)
@@ -78,12 +77,9 @@ struct HotParams {
 constexpr uint32_t kMetaIdx = 0;                          // u16[256] line (relative to the batch) at sorted position
 constexpr uint32_t kMetaOff = kMetaIdx + 2 * kMaxBatch;   // u16[256] text offset in the slot
 constexpr uint32_t kMetaLen = kMetaOff + 2 * kMaxBatch;   // u16[256]
-constexpr uint32_t kMetaRes = kMetaLen + 2 * kMaxBatch;   // i32[256] by line
-constexpr uint32_t kMetaEnd = kMetaRes + 4 * kMaxBatch;   // u32[256] by line
-constexpr uint32_t kMetaFirst = kMetaEnd + 4 * kMaxBatch; // u64 first line of the batch
+constexpr uint32_t kMetaFirst = kMetaLen + 2 * kMaxBatch; // u64 first line of the batch
 constexpr uint32_t kMetaCnt = kMetaFirst + 8;             // u32 lines in the batch
-constexpr uint32_t kMetaDone = kMetaCnt + 4;              // u32 tiles finished
-constexpr uint32_t kMetaSeq = kMetaDone + 4;              // u32 number of the batch the slot holds
+constexpr uint32_t kMetaSeq = kMetaCnt + 4;               // u32 number of the batch the slot holds
 constexpr uint32_t kMetaBytes = kMetaSeq + 4;
 
 // per-producer scratch
@@ -133,7 +129,6 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         mbar_init(barsAddr + 8 * s, 1);
         mbar_init(barsAddr + 8 * (R + s), TPB);
         mbar_init(barsAddr + 8 * (2 * R + s), 1);
-        sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaDone, 0);
         sts32(sBase + hp.oMeta + s * hp.metaBytes + kMetaSeq, 0xffffffffu);
       }
       sts32(ctlAddr, 0);
@@ -727,43 +722,17 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       const bool absorbed = done && wk.absorbed;
       const uint32_t mend = done ? wk.mend : 0;
       const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || absorbed) ? lineLen : mend) : 0;
-      if (kDirectOutcomes) {
-        // straight to the line's place: the 256 outcomes of a batch are 1 KB per
-        // array, written within a few microseconds of each other - L2 puts the
-        // sectors together
-        const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
-        args.results[line] = result;
-        if (args.matchEnds)
-          args.matchEnds[line] = end;
-      }
-      else {
-        sts32(mA + kMetaRes + 4 * idx, static_cast<uint32_t>(result));
-        sts32(mA + kMetaEnd + 4 * idx, end);
-      }
+      // straight to the line's place: the 256 outcomes of a batch are 1 KB per
+      // array, written within a few microseconds of each other - L2 puts the
+      // sectors together (collecting them per batch in shared memory for a
+      // coalesced copy cost a counter, two fences and 570 cycles per tile)
+      const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
+      args.results[line] = result;
+      if (args.matchEnds)
+        args.matchEnds[line] = end;
     }
     __syncwarp();
     const long long tc2 = hp.dbg ? clock64() : 0;
-    if (!kDirectOutcomes) {
-      // the tile that finishes a batch writes the batch's outcomes back, coalesced
-      uint32_t last = 0;
-      if (lane == 0) {
-        __threadfence_block();
-        last = (atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaDone), 1u) == TPB - 1) ? 1 : 0;
-        __threadfence_block();
-      }
-      last = __shfl_sync(kFullMask, last, 0);
-      if (last) {
-        const uint64_t first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
-        for (uint32_t i = lane; i < cnt; i += 32) {
-          args.results[first + i] = static_cast<int32_t>(lds32(mA + kMetaRes + 4 * i));
-          if (args.matchEnds)
-            args.matchEnds[first + i] = lds32(mA + kMetaEnd + 4 * i);
-        }
-        if (lane == 0)
-          sts32(mA + kMetaDone, 0);
-        __syncwarp();
-      }
-    }
     if (lane == 0)
       mbar_arrive(barsAddr + 8 * (R + s));
     if (hp.dbg) {
