@@ -242,11 +242,17 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
   if (samples && realLines)
     prog->avgLineBytes.store(static_cast<uint32_t>(std::min<uint64_t>(visits[2 * static_cast<size_t>(nStates)] / samples, 1u << 20)));
   {
-    // rows of 128 columns when (nearly) all of the text is ASCII: half the
-    // shared memory for the table, more of it for text
+    /* Rows of 128 columns (when nearly all of the text is ASCII) are half the
+       shared memory - but every 16-byte chunk then has to be looked at for a
+       byte >= 128, and that costs the batch kernel more than a sixth slot of
+       text brings (measured: 256-column rows +2 %).  So the batch images take
+       them only when told to (RED_B200_HOT_ASCII=1); the long-stream matcher's
+       two-byte image, whose size decides how many states it holds, does when
+       the text allows. */
     const uint64_t allBytes = visits[2 * static_cast<size_t>(nStates)];
     const uint64_t highBytes = visits[2 * static_cast<size_t>(nStates) + 1];
-    const bool ascii = prog->hotAsciiRows ? (prog->hotAsciiRows > 0) : (highBytes * 2000 <= allBytes);
+    const bool asciiText = prog->hotAsciiRows ? (prog->hotAsciiRows > 0) : (highBytes * 2000 <= allBytes);
+    const bool ascii = prog->hotAsciiRows > 0;
     HotDev instant, whole;
     if ((upload_hot(prog, visits.data(), ascii, true, instant) == cudaSuccess) &&
         (upload_hot(prog, visits.data() + nStates, ascii, false, whole) == cudaSuccess)) {
@@ -256,13 +262,13 @@ static void profile_hot(red_b200_program *prog, const BatchArgs &args, cudaStrea
       // if a byte cannot name them all (as many as fit beside the text stages)
       prog->hotStream = whole;
       if (whole.coverage < 1000) {
-        const uint32_t rowBytes = (ascii ? 128u : 256u) * 2 + 4;
+        const uint32_t rowBytes = (asciiText ? 128u : 256u) * 2 + 4;
         uint32_t fit = (prog->geo.maxSmemOptin > 140 * 1024) ? (prog->geo.maxSmemOptin - 140 * 1024) / rowBytes : 0;
         if (prog->hotStreamStates)  // RED_B200_STREAM_HOT_STATES (tests: lanes that leave the image)
           fit = std::min(fit, std::max(prog->hotStreamStates, kHotMax + 2) + 1);
         HotDev wide;
         if ((fit > kHotMax + 1) &&
-            (upload_hot(prog, visits.data() + nStates, ascii, false, wide, std::min(fit - 1, kHotMaxWide)) == cudaSuccess))
+            (upload_hot(prog, visits.data() + nStates, asciiText, false, wide, std::min(fit - 1, kHotMaxWide)) == cudaSuccess))
           prog->hotStream = wide;
         else
           cudaGetLastError();

@@ -28,7 +28,7 @@ struct HotDev {
 
 struct HotTuning {
   int consumerWarps = 0;   // 0 = pick (all the warps the ring can feed)
-  int producers = 0;       // 0 = pick (3)
+  int producers = 0;       // 0 = pick (4)
   int defer = 0;           // careful passes at the end of a tile: 0 = pick, 1 = yes, -1 = no
   bool force = false;      // take this kernel even when the hot set leaves out states the profile saw
   int slots = 0;           // 0 = pick (as many as fit)

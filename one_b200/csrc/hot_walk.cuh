@@ -256,40 +256,22 @@ __device__ __forceinline__ bool hot_fast(const HotCtx &hx, const uint4 &w, const
 /* The fast pass where codes that need a decision STICK (style Full: absorbing
    and dead states, the sink; style Instant on an image built with
    acceptSticks): no running maximum - the code behind the chunk tells whether
-   anything happened in it.  Returns that code, or 255 for a chunk of an
-   ASCII-row image that holds a byte >= 128.  hi: bytes of the chunk that
-   belong to the line (FULL16: all 16). */
+   anything happened in it.  Returns that code, or 255 for a chunk of a
+   128-column image that holds a byte >= 128.  hi: bytes of the chunk that
+   belong to the line (FULL16: all 16; the others are not looked up). */
 template <bool FULL16, int STRIDE>
-__device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, uint4 w, const uint32_t hi, uint32_t c) {
-  constexpr bool kAscii = STRIDE == static_cast<int>(kHotStrideAscii);
-  if (kAscii && !FULL16) {
-    /* Rows of 128 columns have four more bytes, and those hold the row's own
-       code: byte 0x80 is a step that changes nothing.  The bytes behind the
-       line's end are replaced by it, and the tail chunk is walked like a whole
-       one - no predicated lookups. */
-    // k_q: the low min(max(hi - 4 q, 0), 4) bytes of word q
-    const int h = static_cast<int>(hi);
-    const uint32_t k0 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h, 0), 4)));
-    const uint32_t k1 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 4, 0), 4)));
-    const uint32_t k2 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 8, 0), 4)));
-    const uint32_t k3 = __funnelshift_lc(0xffffffffu, 0u, 8u * static_cast<uint32_t>(min(max(h - 12, 0), 4)));
-    w.x = (w.x & k0) | (0x80808080u & ~k0);
-    w.y = (w.y & k1) | (0x80808080u & ~k1);
-    w.z = (w.z & k2) | (0x80808080u & ~k2);
-    w.w = (w.w & k3) | (0x80808080u & ~k3);
-    // a byte >= 128 of the line itself (not the filler)
-    if ((((w.x & k0) | (w.y & k1) | (w.z & k2) | (w.w & k3)) & 0x80808080u) != 0)
-      return 255u;
-  }
+__device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, const uint4 &w, const uint32_t hi, uint32_t c) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
-      if (FULL16 || kAscii || (static_cast<uint32_t>(4 * q + jj) < hi))
+      if (FULL16 || (static_cast<uint32_t>(4 * q + jj) < hi))
         c = hot_next<STRIDE>(hx, c, word, jj);
   }
-  if (kAscii && FULL16 && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
+  // (rows of 128 columns: whatever follows the line's end in the chunk is looked
+  // at too - a false alarm costs a careful pass, not an answer)
+  if ((STRIDE == static_cast<int>(kHotStrideAscii)) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
     return 255u;
   return c;
 }

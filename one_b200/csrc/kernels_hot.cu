@@ -34,9 +34,7 @@
        happened, a flagged lane steps aside, and when the tile is through all
        flagged lanes settle their outcome together - the state itself names
        it, and for Instant a second run over the chunk counts out where it was
-       entered.  A line's last chunk is filled up with a byte that changes no
-       state (the four spare bytes of a 128-column row) and walked like a
-       whole one.
+       entered.
 
    Roles in a CTA: warps 0 .. NC-1 are consumers (a tile of 32 lines at a
    time, claimed in order from a shared-memory ticket), the warps behind them
@@ -833,7 +831,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
     at += bytes;
     return o;
   };
-  const uint32_t producers = std::max(1, std::min(tune.producers ? tune.producers : 3, static_cast<int>(kMaxProducers)));
+  const uint32_t producers = std::max(1, std::min(tune.producers ? tune.producers : 4, static_cast<int>(kMaxProducers)));
   hp.nProducers = producers;
   hp.prodBytes = (kProdBytes + 15u) & ~15u;
   hp.oC2v = take(2048, 16);

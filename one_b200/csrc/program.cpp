@@ -466,9 +466,7 @@ void build_hot_image(const ParsedProgram &pp, const DeviceImage &img,
     uint8_t *row = &hot.table[static_cast<size_t>(c) * hot.stride];
     for (uint32_t b = 0; b < columns; ++b)
       put(row + b * E, ((c == hot.nHot) || (acceptSticks && (c >= hot.cAccept))) ? c : codeOf[nextOf(cand[c], b)]);
-    // the four bytes behind a row of 128 one-byte columns: "byte 0x80 .. 0x83"
-    // leaves the state as it is (the staged kernel fills a line's last chunk
-    // with it)
+    // the bytes that pad a row to an odd number of banks hold its own code
     for (uint32_t b = columns * E; b < hot.stride; b += E)
       put(row + b, c);
   }
