@@ -409,6 +409,8 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
   auto cleanup = [&](cudaError_t e, const char *what) {
     cudaFree(prog->dTable); cudaFree(prog->dCls); cudaFree(prog->dResults);
     cudaFree(prog->dLeader);
+    for (void *p : prog->hotBuffers)
+      cudaFree(p);
     delete prog;
     return cuda_fail(e, what);
   };
@@ -451,12 +453,38 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     if ((err = cudaMemcpy(dReset, img.resetStates.data(), statesBytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (err = cudaMemcpy(static_cast<char *>(dReset) + statesBytes, img.resetCount.data(), 256,
                           cudaMemcpyHostToDevice)) != cudaSuccess) {
-      cudaFree(dReset);
-      prog->hotBuffers.clear();
       return cleanup(err, "cudaMemcpy(reset states)");
     }
     prog->dev.resetStates = static_cast<const uint32_t *>(dReset);
     prog->dev.resetCount = reinterpret_cast<const uint8_t *>(dReset) + statesBytes;
+  }
+
+  {
+    // the start-position filter of the sliding verbs (device_program.h)
+    const ParsedProgram &pp = prog->parsed;
+    const uint32_t C = pp.classCount;
+    std::vector<uint32_t> bits(2048 + 8, 0);
+    for (uint32_t b0 = 0; b0 < 256; ++b0) {
+      const uint32_t v1 = pp.next[static_cast<size_t>(pp.initialState) * C + pp.equiv[b0]];
+      const bool acc1 = !pp.pureDead[v1] && (pp.result[v1] > 0);
+      if (acc1)
+        bits[2048 + (b0 >> 5)] |= 1u << (b0 & 31);
+      for (uint32_t b1 = 0; b1 < 256; ++b1) {
+        const uint32_t v2 = pp.next[static_cast<size_t>(v1) * C + pp.equiv[b1]];
+        if (acc1 || (!pp.pureDead[v1] && !pp.pureDead[v2])) {
+          const uint32_t idx = (b0 << 8) | b1;
+          bits[idx >> 5] |= 1u << (idx & 31);
+        }
+      }
+    }
+    void *dFilter = nullptr;
+    if ((err = cudaMalloc(&dFilter, bits.size() * 4)) != cudaSuccess)
+      return cleanup(err, "cudaMalloc(start filter)");
+    prog->hotBuffers.push_back(dFilter);
+    if ((err = cudaMemcpy(dFilter, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      return cleanup(err, "cudaMemcpy(start filter)");
+    }
+    prog->dev.startFilter = static_cast<const uint32_t *>(dFilter);
   }
 
   ProgramDev &pd = prog->dev;
@@ -561,11 +589,8 @@ int red_b200_program_upload(const void *serialized, size_t len, int device,
     prog->hotStreamStates = static_cast<uint32_t>(std::max(0, atoi(env)));
   if (prog->hotEnabled) {
     if (((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, true, prog->hotDev[0])) != cudaSuccess) ||
-        ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, false, prog->hotDev[1])) != cudaSuccess)) {
-      for (void *p : prog->hotBuffers)
-        cudaFree(p);
+        ((err = upload_hot(prog, nullptr, prog->hotAsciiRows > 0, false, prog->hotDev[1])) != cudaSuccess))
       return cleanup(err, "upload of the hot image");
-    }
     prog->hotStream = prog->hotDev[1];
   }
 

@@ -34,6 +34,14 @@ struct ProgramDev {
   const uint32_t *resetStates;  // [256 * 8]
   uint32_t hotBytes;    // global-table mode: leading bytes of the table mirrored in shared
                         // memory by the production kernels (0: none)
+  /* scan/search/replace try an anchored walk at every start position; nearly
+     all of them die within two bytes.  startFilter says which cannot match,
+     from the bytes at the position and behind it (computed at upload):
+     bit (b0 << 8 | b1) of words [0, 2048): the state behind b0 accepts, or
+     the one behind b0 b1 is not a dead end; bit b0 of words [2048, 2056), for
+     a line's last byte: the state behind b0 accepts.  A position whose bit is
+     clear yields no match in any style. */
+  const uint32_t *startFilter;
 };
 
 struct BatchArgs {

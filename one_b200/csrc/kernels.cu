@@ -339,6 +339,8 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
   const Tab tab{SMEM ? smem + kClsBytes
                      : static_cast<const unsigned char *>(pd.table)};
   const uint32_t lane = threadIdx.x & 31;
+  // per warp: up to 63 start positions that wait to be walked
+  uint32_t *surv = reinterpret_cast<uint32_t *>(smem + kClsBytes + (SMEM ? pd.tableBytes : 0)) + (threadIdx.x >> 5) * 64;
   const uint64_t nLines = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   constexpr uint32_t kBatch = 8;  // lines claimed at a time
   for (;;) {
@@ -373,11 +375,20 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
         start = 0;
         end = 0;
       }
-      for (uint32_t base = 0; base < len; base += 32) {
-        const uint32_t pos = base + lane;
+      /* Filter, then walk.  Nearly every start position dies within two
+         bytes (pd.startFilter: one bit per byte pair); a round of 32 positions
+         that walks them all lasts as long as its longest walk with a third of
+         the lanes busy.  So a round only LOOKS at its positions, the ones that
+         may match are collected in order, and whenever 32 of them wait (and at
+         the line's end) they are walked together, one per lane; the lowest
+         lane that matched is the first position that does. */
+      bool found = false;
+      uint32_t nSurv = 0;
+      auto walkSurvivors = [&](uint32_t count) {
         int32_t r = 0;
-        uint32_t s = 0, e = 0;
-        if (pos < len) {
+        uint32_t sPos = 0, e = 0;
+        if (lane < count) {
+          const uint32_t pos = surv[lane];
           Walk<STYLE, SEARCH> wk;
           wk.begin(pd);
           wk.mstart = pos;
@@ -385,17 +396,46 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
           for (uint32_t idx = pos; idx < len; ++idx)
             if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
               break;
-          wk.finish(pd, len, r, s, e);
+          wk.finish(pd, len, r, sPos, e);
         }
         const unsigned hits = __ballot_sync(0xffffffffu, r > 0);
         if (hits) {
           const int w = __ffs(hits) - 1;
           result = __shfl_sync(0xffffffffu, r, w);
-          start = __shfl_sync(0xffffffffu, s, w);
+          start = __shfl_sync(0xffffffffu, sPos, w);
           end = __shfl_sync(0xffffffffu, e, w);
-          break;
+          found = true;
+        }
+      };
+      for (uint32_t base = 0; (base < len) && !found; base += 32) {
+        const uint32_t pos = base + lane;
+        bool alive = false;
+        if (pos < len) {
+          const uint32_t b0 = __ldg(p + pos);
+          const uint32_t bit = (pos + 1 < len) ? ((b0 << 8) | __ldg(p + pos + 1)) : (65536u + b0);
+          alive = (__ldg(pd.startFilter + (bit >> 5)) >> (bit & 31)) & 1u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (alive)
+          surv[nSurv + __popc(m & ((1u << lane) - 1))] = pos;
+        nSurv += __popc(m);
+        __syncwarp();
+        if (nSurv >= 32) {
+          walkSurvivors(32);
+          __syncwarp();
+          // the rest (at most 31) moves to the front
+          const uint32_t left = nSurv - 32;
+          const uint32_t moved = (lane < left) ? surv[32 + lane] : 0;
+          __syncwarp();
+          if (lane < left)
+            surv[lane] = moved;
+          nSurv = left;
+          __syncwarp();
         }
       }
+      if (!found && nSurv)
+        walkSurvivors(nSurv);
+      __syncwarp();
       if (lane == 0) {
         args.results[line] = result;
         if (args.matchStarts)
@@ -419,8 +459,9 @@ cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
     return err;
   if (counter && !simple && (SEARCH || (pd.leaderLen == 0))) {
     auto wkern = batch_sliding_warp_kernel<STYLE, SEARCH, SMEM, K, ClsT>;
+    const size_t wsmem = smem + (kMaxThreads / 32) * 256;  // + the warps' lists of waiting positions
     err = cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem));
+                               static_cast<int>(wsmem));
     if (err != cudaSuccess)
       return err;
     if (args.nLines == 0)
@@ -434,7 +475,7 @@ cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
     const uint64_t warpsNeeded = (args.nLines + 7) / 8;
     const uint64_t wgrid = std::min<uint64_t>(static_cast<uint64_t>(geo.smCount) * perSmW,
                                               (warpsNeeded + wthreads / 32 - 1) / (wthreads / 32));
-    wkern<<<static_cast<unsigned>(wgrid), wthreads, smem, stream>>>(pd, args, counter);
+    wkern<<<static_cast<unsigned>(wgrid), wthreads, wsmem, stream>>>(pd, args, counter);
     return cudaGetLastError();
   }
   const int threads = 256;  // lines differ wildly in cost: smaller tiles

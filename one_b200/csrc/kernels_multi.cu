@@ -238,6 +238,8 @@ batch_replace_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *s
    behind the match.  Most walks die within a byte or two and the byte loads of
    a step are coalesced; copying is done by the whole warp.  Same two passes
    as the lane-per-line kernel (measure, then write). */
+constexpr uint32_t kReplaceBuf = 1024;  // bytes of line text per warp in shared memory
+
 template <bool SMEM, int K, class ClsT, bool WRITE>
 __global__ void __launch_bounds__(512)
 batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *starts,
@@ -256,15 +258,30 @@ batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nWarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  /* A line is read many times over (every start position is a walk of its
+     own), byte by byte, each byte a load the next step waits for: the warp
+     copies the line into shared memory first - all of its loads in flight at
+     once - and walks it from there; the next line's text is asked into L2
+     meanwhile.  A line longer than the buffer is walked from global memory. */
+  uint8_t *wbuf = smem + kClsBytes + (SMEM ? pd.tableBytes : 0) + (threadIdx.x >> 5) * kReplaceBuf;
   for (uint64_t line = warp; line < nLines; line += nWarps) {
     const uint8_t *p = text + __ldg(starts + line);
     const uint32_t len = __ldg(lens + line);
+    if ((line + nWarps < nLines) && (lane < 2))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(text + __ldg(starts + line + nWarps) + 128 * lane));
+    if (len <= kReplaceBuf) {
+      __syncwarp();
+      for (uint32_t ii = lane; ii < len; ii += 32)
+        wbuf[ii] = __ldg(p + ii);
+      __syncwarp();
+      p = wbuf;
+    }
     uint8_t *out = WRITE ? outText + __ldg(outStarts + line) : nullptr;
     uint32_t cnt = 0, o = 0, pos = 0;
     auto copyThrough = [&](uint32_t from, uint32_t to) {  // text[from, to) -> out + o
       if (WRITE)
         for (uint32_t ii = from + lane; ii < to; ii += 32)
-          out[o + ii - from] = __ldg(p + ii);
+          out[o + ii - from] = p[ii];
       o += to - from;
     };
     while (pos < len) {
@@ -276,11 +293,19 @@ batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64
       const uint32_t at = pos + lane;
       bool have = false;
       uint32_t found = 0;
+      // (pd.startFilter: the bytes at a position say whether a walk from it can
+      // match at all; most cannot, and a round without candidates is one load)
+      bool alive = false;
       if (at < len) {
+        const uint32_t b0 = p[at];
+        const uint32_t bit = (at + 1 < len) ? ((b0 << 8) | p[at + 1]) : (65536u + b0);
+        alive = (__ldg(pd.startFilter + (bit >> 5)) >> (bit & 31)) & 1u;
+      }
+      if (alive) {
         uint32_t v = pd.initV;
         int32_t prev = 0;
         for (uint32_t idx = at; idx < len; ++idx) {
-          v = tab.next(v, cls[__ldg(p + idx)]);
+          v = tab.next(v, cls[p[idx]]);
           if ((v >= pd.acceptV) && (v < pd.pureV)) {
             if (style == STY_FIRST) {
               const int32_t r = pd.results[state_index(pd, v)];
@@ -433,7 +458,7 @@ cudaError_t launch_line_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
 template <bool SMEM, int K, class ClsT, class Kern, class... Args>
 cudaError_t launch_warp_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
                                const LaunchGeometry &geo, cudaStream_t stream, Args... args) {
-  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0);
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0) + (512 / 32) * kReplaceBuf;  // + the warps' line buffers
   cudaError_t err = cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess)
