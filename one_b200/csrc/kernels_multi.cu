@@ -238,7 +238,9 @@ batch_replace_kernel(const ProgramDev pd, const uint8_t *text, const uint64_t *s
    behind the match.  Most walks die within a byte or two and the byte loads of
    a step are coalesced; copying is done by the whole warp.  Same two passes
    as the lane-per-line kernel (measure, then write). */
-constexpr uint32_t kReplaceBuf = 1024;  // bytes of line text per warp in shared memory
+constexpr uint32_t kReplaceBuf = 1024;   // bytes of line text per warp in shared memory
+constexpr uint32_t kReplaceList = 256;   // start positions per line that may match (more: the plain loop)
+constexpr uint32_t kReplaceWarpBytes = kReplaceBuf + 4 * kReplaceList;  // text, positions (u16), ends (u16)
 
 template <bool SMEM, int K, class ClsT, bool WRITE>
 __global__ void __launch_bounds__(512)
@@ -263,7 +265,9 @@ batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64
      copies the line into shared memory first - all of its loads in flight at
      once - and walks it from there; the next line's text is asked into L2
      meanwhile.  A line longer than the buffer is walked from global memory. */
-  uint8_t *wbuf = smem + kClsBytes + (SMEM ? pd.tableBytes : 0) + (threadIdx.x >> 5) * kReplaceBuf;
+  uint8_t *wbuf = smem + kClsBytes + (SMEM ? pd.tableBytes : 0) + (threadIdx.x >> 5) * kReplaceWarpBytes;
+  uint16_t *sPos = reinterpret_cast<uint16_t *>(wbuf + kReplaceBuf);
+  uint16_t *sEnd = sPos + kReplaceList;
   for (uint64_t line = warp; line < nLines; line += nWarps) {
     const uint8_t *p = text + __ldg(starts + line);
     const uint32_t len = __ldg(lens + line);
@@ -284,63 +288,115 @@ batch_replace_warp_kernel(const ProgramDev pd, const uint8_t *text, const uint64
           out[o + ii - from] = p[ii];
       o += to - from;
     };
-    while (pos < len) {
+    // the anchored walk from `at` (replaceCore's inner loop): is there a match, and its last byte
+    auto walkFrom = [&](uint32_t at, uint32_t &found) -> bool {
+      bool have = false;
+      uint32_t v = pd.initV;
+      int32_t prev = 0;
+      for (uint32_t idx = at; idx < len; ++idx) {
+        v = tab.next(v, cls[p[idx]]);
+        if ((v >= pd.acceptV) && (v < pd.pureV)) {
+          if (style == STY_FIRST) {
+            const int32_t r = pd.results[state_index(pd, v)];
+            if (prev && (r != prev))
+              break;
+            prev = r;
+          }
+          have = true;
+          found = idx;
+          if (style == STY_INSTANT)
+            break;
+          if (v >= pd.absV) {
+            found = len - 1;
+            break;
+          }
+        }
+        else {
+          if (style == STY_FULL)
+            have = false;
+          if ((((style == STY_FIRST) || (style == STY_TANGENT)) && have) || (v >= pd.pureV))
+            break;
+        }
+      }
+      return have;
+    };
+    // (pd.startFilter: the bytes at a position say whether a walk from it can match at all)
+    auto mayMatch = [&](uint32_t at) -> bool {
+      const uint32_t b0 = p[at];
+      const uint32_t bit = (at + 1 < len) ? ((b0 << 8) | p[at + 1]) : (65536u + b0);
+      return (__ldg(pd.startFilter + (bit >> 5)) >> (bit & 31)) & 1u;
+    };
+    auto substitute = [&](uint32_t at, uint32_t end) {
+      copyThrough(pos, at);
+      if (WRITE)
+        for (uint32_t ii = lane; ii < replLen; ii += 32)
+          out[o + ii] = __ldg(repl + ii);
+      o += replLen;
+      pos = end;
+      ++cnt;
+    };
+
+    /* A staged line in three steps.  (1) Every position is LOOKED at, the few
+       that may match go on a list, in order.  (2) They are walked 32 at a
+       time, one per lane - the walks are independent of each other and of what
+       gets substituted: each starts in the initial state and reads the line as
+       it is.  (3) The substitutions are read off in order: the first listed
+       position at or behind the cursor that has a match, then the first one at
+       or behind that match's end, and so on.  The same result as trying every
+       position in turn, without a round of 32 walks per 32 bytes of text. */
+    bool listed = false;
+    if ((p == wbuf) && (maxRepl > 0)) {
+      uint32_t nSurv = 0;
+      for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t at = base + lane;
+        const bool alive = (at < len) && mayMatch(at);
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        const uint32_t slot = nSurv + __popc(m & ((1u << lane) - 1));
+        if (alive && (slot < kReplaceList))
+          sPos[slot] = static_cast<uint16_t>(at);
+        nSurv += __popc(m);
+      }
+      __syncwarp();
+      if (nSurv <= kReplaceList) {
+        listed = true;
+        for (uint32_t base = 0; base < nSurv; base += 32) {
+          const uint32_t i = base + lane;
+          if (i < nSurv) {
+            uint32_t found = 0;
+            const bool have = walkFrom(sPos[i], found);
+            sEnd[i] = have ? static_cast<uint16_t>(found + 1) : 0;
+          }
+        }
+        __syncwarp();
+        for (uint32_t base = 0; (base < nSurv) && (cnt < maxRepl);) {
+          const uint32_t i = base + lane;
+          const bool cand = (i < nSurv) && (sEnd[i] != 0) && (sPos[i] >= pos);
+          const unsigned m = __ballot_sync(0xffffffffu, cand);
+          if (!m) {
+            base += 32;
+            continue;
+          }
+          const uint32_t w = base + (__ffs(m) - 1);
+          substitute(sPos[w], sEnd[w]);
+          base = w + 1;
+        }
+        copyThrough(pos, len);
+        pos = len;
+      }
+    }
+    while (!listed && (pos < len)) {
       if (cnt >= maxRepl) {
         copyThrough(pos, len);
         break;
       }
       // lane l: is there a match starting at pos + l, and where does it end
       const uint32_t at = pos + lane;
-      bool have = false;
       uint32_t found = 0;
-      // (pd.startFilter: the bytes at a position say whether a walk from it can
-      // match at all; most cannot, and a round without candidates is one load)
-      bool alive = false;
-      if (at < len) {
-        const uint32_t b0 = p[at];
-        const uint32_t bit = (at + 1 < len) ? ((b0 << 8) | p[at + 1]) : (65536u + b0);
-        alive = (__ldg(pd.startFilter + (bit >> 5)) >> (bit & 31)) & 1u;
-      }
-      if (alive) {
-        uint32_t v = pd.initV;
-        int32_t prev = 0;
-        for (uint32_t idx = at; idx < len; ++idx) {
-          v = tab.next(v, cls[p[idx]]);
-          if ((v >= pd.acceptV) && (v < pd.pureV)) {
-            if (style == STY_FIRST) {
-              const int32_t r = pd.results[state_index(pd, v)];
-              if (prev && (r != prev))
-                break;
-              prev = r;
-            }
-            have = true;
-            found = idx;
-            if (style == STY_INSTANT)
-              break;
-            if (v >= pd.absV) {
-              found = len - 1;
-              break;
-            }
-          }
-          else {
-            if (style == STY_FULL)
-              have = false;
-            if ((((style == STY_FIRST) || (style == STY_TANGENT)) && have) || (v >= pd.pureV))
-              break;
-          }
-        }
-      }
+      const bool have = (at < len) && mayMatch(at) && walkFrom(at, found);
       const unsigned hits = __ballot_sync(0xffffffffu, have);
       if (hits) {
         const int w = __ffs(hits) - 1;
-        const uint32_t end = __shfl_sync(0xffffffffu, found, w) + 1;
-        copyThrough(pos, pos + w);
-        if (WRITE)
-          for (uint32_t ii = lane; ii < replLen; ii += 32)
-            out[o + ii] = __ldg(repl + ii);
-        o += replLen;
-        pos = end;
-        ++cnt;
+        substitute(pos + w, __shfl_sync(0xffffffffu, found, w) + 1);
       }
       else {
         const uint32_t to = min(len, pos + 32);
@@ -458,7 +514,7 @@ cudaError_t launch_line_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
 template <bool SMEM, int K, class ClsT, class Kern, class... Args>
 cudaError_t launch_warp_kernel(Kern kern, const ProgramDev &pd, uint64_t nLines,
                                const LaunchGeometry &geo, cudaStream_t stream, Args... args) {
-  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0) + (512 / 32) * kReplaceBuf;  // + the warps' line buffers
+  size_t smem = kClsBytes + (SMEM ? pd.tableBytes : 0) + (512 / 32) * kReplaceWarpBytes;  // + the warps' line buffers and lists
   cudaError_t err = cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess)
