@@ -339,8 +339,9 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
   const Tab tab{SMEM ? smem + kClsBytes
                      : static_cast<const unsigned char *>(pd.table)};
   const uint32_t lane = threadIdx.x & 31;
-  // per warp: up to 63 start positions that wait to be walked
-  uint32_t *surv = reinterpret_cast<uint32_t *>(smem + kClsBytes + (SMEM ? pd.tableBytes : 0)) + (threadIdx.x >> 5) * 64;
+  // per warp: up to 63 start positions that wait to be walked, and whose line they are
+  uint32_t *surv = reinterpret_cast<uint32_t *>(smem + kClsBytes + (SMEM ? pd.tableBytes : 0)) + (threadIdx.x >> 5) * 80;
+  uint8_t *survLine = reinterpret_cast<uint8_t *>(surv + 64);
   const uint64_t nLines = args.nLinesDev ? min(*args.nLinesDev, args.nLines) : args.nLines;
   constexpr uint32_t kBatch = 8;  // lines claimed at a time
   for (;;) {
@@ -362,52 +363,71 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
       if (myLen > 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(args.text + myStart + 128));
     }
-    for (uint64_t line = first; line < last; ++line) {
-      const uint8_t *p = args.text + __shfl_sync(0xffffffffu, myStart, static_cast<int>(line - first));
-      const uint32_t len = __shfl_sync(0xffffffffu, myLen, static_cast<int>(line - first));
-      int32_t result = 0;
-      uint32_t start = 0, end = 0;
+    /* Filter, then walk.  Nearly every start position dies within two bytes
+       (pd.startFilter: one bit per byte pair); a round of 32 positions that
+       walks them all lasts as long as its longest walk with a third of the
+       lanes busy.  So a round only LOOKS at its positions; the ones that may
+       match - of all the lines of the batch, in order - are collected, and
+       whenever 32 of them wait (and at the batch's end) they are walked
+       together, one per lane.  The lowest lane of a line that matched is the
+       first position of that line that does; a line that has its match takes
+       no further part.  (Candidates of several lines in one round: the long
+       walk of a true match then has thirty other walks beside it, not five.) */
+    const uint32_t nb = static_cast<uint32_t>(last - first);
+    int32_t myRes = 0;        // lane j: the outcome of line first + j
+    uint32_t myS = 0, myE = 0;
+    uint32_t foundMask = 0;   // lines that have their match (warp-uniform)
+    uint32_t nSurv = 0;
+    auto walkGroup = [&](uint32_t count) {
+      int32_t r = 0;
+      uint32_t sPos = 0, e = 0, j = 0;
+      if (lane < count) {
+        j = survLine[lane];
+      }
+      const uint64_t st = __shfl_sync(0xffffffffu, myStart, static_cast<int>(j));
+      const uint32_t len = __shfl_sync(0xffffffffu, myLen, static_cast<int>(j));
+      if ((lane < count) && !((foundMask >> j) & 1u)) {
+        const uint8_t *p = args.text + st;
+        const uint32_t pos = surv[lane];
+        Walk<STYLE, SEARCH> wk;
+        wk.begin(pd);
+        wk.mstart = pos;
+        wk.mend = pos;
+        for (uint32_t idx = pos; idx < len; ++idx)
+          if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
+            break;
+        wk.finish(pd, len, r, sPos, e);
+      }
+      for (uint32_t L = 0; L < nb; ++L) {
+        const unsigned hits = __ballot_sync(0xffffffffu, (r > 0) && (j == L) && (lane < count));
+        if (hits && !((foundMask >> L) & 1u)) {
+          const int w = __ffs(hits) - 1;
+          const int32_t rW = __shfl_sync(0xffffffffu, r, w);
+          const uint32_t sW = __shfl_sync(0xffffffffu, sPos, w);
+          const uint32_t eW = __shfl_sync(0xffffffffu, e, w);
+          if (lane == L) {
+            myRes = rW;
+            myS = sW;
+            myE = eW;
+          }
+          foundMask |= 1u << L;
+        }
+      }
+    };
+    for (uint32_t j = 0; j < nb; ++j) {
+      const uint8_t *p = args.text + __shfl_sync(0xffffffffu, myStart, static_cast<int>(j));
+      const uint32_t len = __shfl_sync(0xffffffffu, myLen, static_cast<int>(j));
       if (len == 0) {
         // empty text: the initial state's result, positions 0
         Walk<STYLE, SEARCH> wk;
         wk.begin(pd);
-        wk.finish(pd, 0, result, start, end);
-        start = 0;
-        end = 0;
+        int32_t r0 = 0;
+        uint32_t s0 = 0, e0 = 0;
+        wk.finish(pd, 0, r0, s0, e0);
+        if (lane == j)
+          myRes = r0;
       }
-      /* Filter, then walk.  Nearly every start position dies within two
-         bytes (pd.startFilter: one bit per byte pair); a round of 32 positions
-         that walks them all lasts as long as its longest walk with a third of
-         the lanes busy.  So a round only LOOKS at its positions, the ones that
-         may match are collected in order, and whenever 32 of them wait (and at
-         the line's end) they are walked together, one per lane; the lowest
-         lane that matched is the first position that does. */
-      bool found = false;
-      uint32_t nSurv = 0;
-      auto walkSurvivors = [&](uint32_t count) {
-        int32_t r = 0;
-        uint32_t sPos = 0, e = 0;
-        if (lane < count) {
-          const uint32_t pos = surv[lane];
-          Walk<STYLE, SEARCH> wk;
-          wk.begin(pd);
-          wk.mstart = pos;
-          wk.mend = pos;
-          for (uint32_t idx = pos; idx < len; ++idx)
-            if (wk.step(pd, tab, cls[__ldg(p + idx)], idx))
-              break;
-          wk.finish(pd, len, r, sPos, e);
-        }
-        const unsigned hits = __ballot_sync(0xffffffffu, r > 0);
-        if (hits) {
-          const int w = __ffs(hits) - 1;
-          result = __shfl_sync(0xffffffffu, r, w);
-          start = __shfl_sync(0xffffffffu, sPos, w);
-          end = __shfl_sync(0xffffffffu, e, w);
-          found = true;
-        }
-      };
-      for (uint32_t base = 0; (base < len) && !found; base += 32) {
+      for (uint32_t base = 0; (base < len) && !((foundMask >> j) & 1u); base += 32) {
         const uint32_t pos = base + lane;
         bool alive = false;
         if (pos < len) {
@@ -416,33 +436,40 @@ batch_sliding_warp_kernel(const ProgramDev pd, const BatchArgs args,
           alive = (__ldg(pd.startFilter + (bit >> 5)) >> (bit & 31)) & 1u;
         }
         const unsigned m = __ballot_sync(0xffffffffu, alive);
-        if (alive)
-          surv[nSurv + __popc(m & ((1u << lane) - 1))] = pos;
+        if (alive) {
+          const uint32_t slot = nSurv + __popc(m & ((1u << lane) - 1));
+          surv[slot] = pos;
+          survLine[slot] = static_cast<uint8_t>(j);
+        }
         nSurv += __popc(m);
         __syncwarp();
         if (nSurv >= 32) {
-          walkSurvivors(32);
+          walkGroup(32);
           __syncwarp();
           // the rest (at most 31) moves to the front
           const uint32_t left = nSurv - 32;
-          const uint32_t moved = (lane < left) ? surv[32 + lane] : 0;
+          const uint32_t movedPos = (lane < left) ? surv[32 + lane] : 0;
+          const uint8_t movedLine = (lane < left) ? survLine[32 + lane] : 0;
           __syncwarp();
-          if (lane < left)
-            surv[lane] = moved;
+          if (lane < left) {
+            surv[lane] = movedPos;
+            survLine[lane] = movedLine;
+          }
           nSurv = left;
           __syncwarp();
         }
       }
-      if (!found && nSurv)
-        walkSurvivors(nSurv);
-      __syncwarp();
-      if (lane == 0) {
-        args.results[line] = result;
-        if (args.matchStarts)
-          args.matchStarts[line] = start;
-        if (args.matchEnds)
-          args.matchEnds[line] = end;
-      }
+    }
+    if (nSurv)
+      walkGroup(nSurv);
+    __syncwarp();
+    if (lane < nb) {
+      const uint64_t line = first + lane;
+      args.results[line] = myRes;
+      if (args.matchStarts)
+        args.matchStarts[line] = myS;
+      if (args.matchEnds)
+        args.matchEnds[line] = myE;
     }
   }
 }
@@ -459,7 +486,7 @@ cudaError_t launch_slide(const ProgramDev &pd, const BatchArgs &args,
     return err;
   if (counter && !simple && (SEARCH || (pd.leaderLen == 0))) {
     auto wkern = batch_sliding_warp_kernel<STYLE, SEARCH, SMEM, K, ClsT>;
-    const size_t wsmem = smem + (kMaxThreads / 32) * 256;  // + the warps' lists of waiting positions
+    const size_t wsmem = smem + (kMaxThreads / 32) * 320;  // + the warps' lists of waiting positions
     err = cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(wsmem));
     if (err != cudaSuccess)
