@@ -169,24 +169,24 @@ __device__ __forceinline__ uint32_t hot_next_byte(const HotCtx &hx, uint32_t c, 
    byte offset - 16 ALU operations per 16 bytes, none in the load/store pipe. */
 struct Feed {
   uint32_t blk;   // address of the next aligned block to load
-  uint4 cur;      // the block in front of it
+  uint4 cur;      // the two blocks in front of it: the next chunk's bytes are in these
+  uint4 nxt;
   uint32_t sel;   // PRMT selector of the byte offset: 0x3210 + 0x1111 * (start & 3)
   bool w1, w2;    // bits of the word offset (start >> 2) & 3
 };
 __device__ __forceinline__ void feed_begin(Feed &f, const uint32_t textAddr) {
   f.blk = textAddr & ~15u;
   f.cur = lds128(f.blk);
-  f.blk += 16;
+  f.nxt = lds128(f.blk + 16);
+  f.blk += 32;
   f.sel = 0x3210u + 0x1111u * (textAddr & 3u);
   f.w1 = (textAddr & 4u) != 0;
   f.w2 = (textAddr & 8u) != 0;
 }
-// the next 16 bytes of the line (whatever follows the line's end comes along)
-__device__ __forceinline__ uint4 feed_next(Feed &f) {
-  const uint4 n = lds128(f.blk);
-  f.blk += 16;
-  const uint32_t u0 = f.w1 ? f.cur.y : f.cur.x, u1 = f.w1 ? f.cur.z : f.cur.y, u2 = f.w1 ? f.cur.w : f.cur.z,
-                 u3 = f.w1 ? n.x : f.cur.w, u4 = f.w1 ? n.y : n.x, u5 = f.w1 ? n.z : n.y, u6 = f.w1 ? n.w : n.z;
+// 16 bytes from two aligned blocks, by the word and byte offsets in f
+__device__ __forceinline__ uint4 feed_align(const Feed &f, const uint4 &c, const uint4 &n) {
+  const uint32_t u0 = f.w1 ? c.y : c.x, u1 = f.w1 ? c.z : c.y, u2 = f.w1 ? c.w : c.z,
+                 u3 = f.w1 ? n.x : c.w, u4 = f.w1 ? n.y : n.x, u5 = f.w1 ? n.z : n.y, u6 = f.w1 ? n.w : n.z;
   const uint32_t y0 = f.w2 ? u2 : u0, y1 = f.w2 ? u3 : u1, y2 = f.w2 ? u4 : u2, y3 = f.w2 ? u5 : u3,
                  y4 = f.w2 ? u6 : u4;
   uint4 r;
@@ -194,8 +194,31 @@ __device__ __forceinline__ uint4 feed_next(Feed &f) {
   r.y = __byte_perm(y1, y2, f.sel);
   r.z = __byte_perm(y2, y3, f.sel);
   r.w = __byte_perm(y3, y4, f.sel);
-  f.cur = n;
   return r;
+}
+/* The next 16 bytes of the line (whatever follows the line's end comes along).
+   The block the chunk BEHIND this one will need is asked for first: the loads
+   are volatile asm and keep their order, so a load placed in front of a
+   chunk's sixteen lookups is under way while they run, and the next chunk's
+   first lookup does not wait for its text (it used to: an LDS.128 round trip
+   and the re-alignment in front of every chunk's chain).  A feed therefore
+   reads up to two blocks past its line's last chunk (launch_batch_hot leaves
+   the room behind the last slot). */
+__device__ __forceinline__ uint4 feed_next(Feed &f) {
+  const uint4 ahead = lds128(f.blk);
+  f.blk += 16;
+  const uint4 r = feed_align(f, f.cur, f.nxt);
+  f.cur = f.nxt;
+  f.nxt = ahead;
+  return r;
+}
+// the four bytes at any address (two aligned words; the second may lie behind the text)
+__device__ __forceinline__ uint32_t feed_word(const uint32_t textAddr) {
+  const uint32_t a = textAddr & ~3u;
+  uint32_t lo, hi;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(a + 4));
+  return __byte_perm(lo, hi, 0x3210u + 0x1111u * (textAddr & 3u));
 }
 
 /* The fast pass over one aligned 16-byte chunk of one line per lane: no
@@ -274,6 +297,43 @@ __device__ __forceinline__ uint32_t hot_run(const HotCtx &hx, const uint4 &w, co
   if ((STRIDE == static_cast<int>(kHotStrideAscii)) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
     return 255u;
   return c;
+}
+
+/* hot_run that also hands back the codes behind the chunk's first three
+   quarters (no extra instructions, three registers): where deciding codes
+   stick they tell in which quarter the run met one, and the second look
+   (hot_locate_quarter, or the careful pass) starts there instead of at the
+   chunk's first byte. */
+template <bool FULL16, int STRIDE>
+__device__ __forceinline__ uint32_t hot_run_q(const HotCtx &hx, const uint4 &w, const uint32_t hi, uint32_t c,
+                                              uint32_t &cp0, uint32_t &cp1, uint32_t &cp2) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t word = (q == 0) ? w.x : (q == 1) ? w.y : (q == 2) ? w.z : w.w;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (FULL16 || (static_cast<uint32_t>(4 * q + jj) < hi))
+        c = hot_next<STRIDE>(hx, c, word, jj);
+    if (q == 0) cp0 = c;
+    if (q == 1) cp1 = c;
+    if (q == 2) cp2 = c;
+  }
+  if ((STRIDE == static_cast<int>(kHotStrideAscii)) && (((w.x | w.y | w.z | w.w) & 0x80808080u) != 0))
+    return 255u;
+  return c;
+}
+
+// hot_locate over one quarter of a chunk: word = its four bytes, hi of them in the line
+template <int STRIDE>
+__device__ __forceinline__ uint32_t hot_locate_quarter(const HotCtx &hx, const uint32_t word, const uint32_t hi, uint32_t c) {
+  uint32_t n = 0;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj)
+    if (static_cast<uint32_t>(jj) < hi) {
+      c = hot_next<STRIDE>(hx, c, word, jj);
+      n += (c < hx.cLimit) ? 1u : 0u;
+    }
+  return n;
 }
 
 /* Behind hot_run on an image whose accepting codes stick: how many bytes of

@@ -90,7 +90,7 @@ constexpr uint32_t kProdBytes = kProdHist + 4 * kSortBuckets;
    Instant, Full): a lane whose chunk was flagged steps aside, and the careful
    passes of a tile's flagged lanes run together once the tile is through,
    instead of one after the other with the rest of the warp waiting. */
-template <int STYLE, bool DEFER, int STRIDE>
+template <int STYLE, bool DEFER, int STRIDE, bool DBG>
 __global__ void __launch_bounds__(1024, 1)
 batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, const HotParams hp,
                  unsigned long long *blockCounter) {
@@ -98,6 +98,9 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
   // everything sits behind a 256-byte boundary (hot_next wants the table there)
   unsigned char *smem = smemRaw + ((256u - (smem_addr(smemRaw) & 255u)) & 255u);
   const uint32_t sBase = smem_addr(smem);
+  // cycle counters (RED_B200_HOT_DEBUG) are an instantiation of their own: as a
+  // run-time switch they cost the consumers ten registers of the 64 a thread has
+  const bool dbgOn = DBG && (hp.dbg != nullptr);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t P = hp.nProducers;
@@ -163,7 +166,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        ITS phase complete. */
     unsigned long long tAcq = 0, tIdx = 0, nBatches = 0;
     auto acquire = [&]() -> uint32_t {
-      const long long t0 = hp.dbg ? clock64() : 0;
+      const long long t0 = dbgOn ? clock64() : 0;
       if (lane == 0) {
         q = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl + 4), 1u);
         while (lds32_volatile(ctlAddr + 16) != q)
@@ -176,7 +179,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       __syncwarp();
       if (lane == 0)
         asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ctlAddr + 16), "r"(q + 1) : "memory");
-      if (hp.dbg) {
+      if (dbgOn) {
         tAcq += clock64() - t0;
         ++nBatches;
       }
@@ -367,7 +370,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     if (lane == 0)
       claimed = atomicAdd(blockCounter, 1ull);
     uint64_t block = __shfl_sync(kFullMask, claimed, 0);
-    const long long tStart = hp.dbg ? clock64() : 0;
+    const long long tStart = dbgOn ? clock64() : 0;
     /* The index entries of a sub-block (lane + 32 k: coalesced, all in flight
        at once) are loaded one sub-block ahead - as soon as the registers of the
        current one are free - so that their latency lies behind the wait for a
@@ -388,7 +391,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     };
     loadIndex(block);
     while (block * SUB < n) {
-      const long long tI0 = hp.dbg ? clock64() : 0;
+      const long long tI0 = dbgOn ? clock64() : 0;
       const uint64_t base = block * SUB;
       const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base));
       if (lane == 0)
@@ -402,7 +405,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           lo = min(lo, st[k]);
           hi = max(hi, st[k] + ln[k]);
         }
-      if (hp.dbg)
+      if (dbgOn)
         tIdx += clock64() - tI0;
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) {
@@ -457,7 +460,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         loadIndex(block);
       }
     }
-    if (hp.dbg && (lane == 0)) {
+    if (dbgOn && (lane == 0)) {
       atomicAdd(hp.dbg + 0, static_cast<unsigned long long>(clock64() - tStart));
       atomicAdd(hp.dbg + 1, tIdx);
       atomicAdd(hp.dbg + 2, tAcq);
@@ -490,10 +493,10 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
   hx.wide = hd.wideTable;
   hx.codeOf = hd.codeOf;
   unsigned long long tWait = 0, tWalk = 0, tTail = 0, nTiles = 0;
-  const long long tStartC = hp.dbg ? clock64() : 0;
+  const long long tStartC = dbgOn ? clock64() : 0;
 
   for (;;) {
-    const long long tc0 = hp.dbg ? clock64() : 0;
+    const long long tc0 = dbgOn ? clock64() : 0;
     uint32_t tk = 0;
     if (lane == 0)
       tk = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl), 1u);
@@ -539,7 +542,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       break;
     if ((t == 0) && (lane == 0))
       mbar_arrive(barsAddr + 8 * (2 * R + s));
-    const long long tc1 = hp.dbg ? clock64() : 0;
+    const long long tc1 = dbgOn ? clock64() : 0;
     const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
     const uint32_t cnt = lds32(mA + kMetaCnt);
     const uint32_t pos = t * 32 + lane;
@@ -605,16 +608,39 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
          text feed, the bytes left, the state in front of the chunk; a flagged
          lane freezes them and steps aside. */
       uint32_t fc = 0xffffffffu;  // flagged: the code the chunk's run ended in
+      /* A flagged lane keeps the state in front of the QUARTER of the chunk in
+         which its run met the deciding code (such codes stick, so the codes
+         behind the quarters tell which it was): rem and code move up to that
+         quarter, and the second look is at four bytes, not sixteen. */
+      auto flag = [&](uint32_t c2, uint32_t cp0, uint32_t cp1, uint32_t cp2) {
+        fc = c2;
+        active = false;
+        if (c2 != 255u) {  // (255: possibly a byte >= 128 on 128-column rows - the codes mean nothing)
+          const uint32_t lim = hx.cLimit;
+          if (cp0 < lim) {
+            uint32_t adv = 4, cq = cp0;
+            if (cp1 < lim) {
+              adv = 8;
+              cq = cp1;
+              if (cp2 < lim) {
+                adv = 12;
+                cq = cp2;
+              }
+            }
+            code = cq;
+            rem -= adv;
+          }
+        }
+      };
       if (kFull != 0xffffffffu) {
 #pragma unroll 2
         for (uint32_t k = 0; k < kFull; ++k) {
           if (active) {
             const uint4 w = feed_next(fd);
-            const uint32_t c2 = hot_run<true, STRIDE>(hx, w, 16, code);
-            if (c2 >= hx.cLimit) {
-              fc = c2;
-              active = false;
-            }
+            uint32_t cp0, cp1, cp2;
+            const uint32_t c2 = hot_run_q<true, STRIDE>(hx, w, 16, code, cp0, cp1, cp2);
+            if (c2 >= hx.cLimit)
+              flag(c2, cp0, cp1, cp2);
             else {
               code = c2;
               rem -= 16;
@@ -626,11 +652,10 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       while (__any_sync(kFullMask, active)) {
         if (active) {
           const uint4 w = feed_next(fd);
-          const uint32_t c2 = hot_run<false, STRIDE>(hx, w, min(16u, rem), code);
-          if (c2 >= hx.cLimit) {
-            fc = c2;
-            active = false;
-          }
+          uint32_t cp0, cp1, cp2;
+          const uint32_t c2 = hot_run_q<false, STRIDE>(hx, w, min(16u, rem), code, cp0, cp1, cp2);
+          if (c2 >= hx.cLimit)
+            flag(c2, cp0, cp1, cp2);
           else {
             code = c2;
             if (rem <= 16)
@@ -643,17 +668,15 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       if (__any_sync(kFullMask, fc != 0xffffffffu)) {
         /* Flagged lanes, together.  Nearly always the run ended in a state
            that settles the line: an accepting one (Instant: where it was
-           entered is counted out by a second run over the chunk), an absorbing
-           or a dead one (no position needed).  What is left - the walk left
-           the hot set, a byte >= 128 on 128-column rows - goes byte by byte
-           from the chunk's start, to the line's end if it has to. */
+           entered is counted out by a second run over the quarter), an
+           absorbing or a dead one (no position needed).  What is left - the
+           walk left the hot set, a byte >= 128 on 128-column rows - goes byte
+           by byte from where the lane stopped, to the line's end if it has to. */
         const bool settled = (fc != 0xffffffffu) && (fc != 255u) && (fc != hx.sink);
         if (settled) {
           if ((STYLE == STY_INSTANT) && (fc < hx.cPure)) {
-            Feed f2;
-            feed_begin(f2, tb + (len - rem));
-            const uint4 w = feed_next(f2);
-            wk.mend = (len - rem) + hot_locate<STRIDE>(hx, w, min(16u, rem), code) + 1;
+            const uint32_t word = feed_word(tb + (len - rem));
+            wk.mend = (len - rem) + hot_locate_quarter<STRIDE>(hx, word, min(4u, rem), code) + 1;
             wk.absorbed = false;
             done = true;
           }
@@ -730,10 +753,10 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         args.matchEnds[line] = end;
     }
     __syncwarp();
-    const long long tc2 = hp.dbg ? clock64() : 0;
+    const long long tc2 = dbgOn ? clock64() : 0;
     if (lane == 0)
       mbar_arrive(barsAddr + 8 * (R + s));
-    if (hp.dbg) {
+    if (dbgOn) {
       const long long tc3 = clock64();
       tWait += tc1 - tc0;
       tWalk += tc2 - tc1;
@@ -741,7 +764,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       ++nTiles;
     }
   }
-  if (hp.dbg && (lane == 0)) {
+  if (dbgOn && (lane == 0)) {
     atomicAdd(hp.dbg + 4, static_cast<unsigned long long>(clock64() - tStartC));
     atomicAdd(hp.dbg + 5, tWait);
     atomicAdd(hp.dbg + 6, tWalk);
@@ -831,7 +854,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
     at += bytes;
     return o;
   };
-  const uint32_t producers = std::max(1, std::min(tune.producers ? tune.producers : 4, static_cast<int>(kMaxProducers)));
+  const uint32_t producers = std::max(1, std::min(tune.producers ? tune.producers : 3, static_cast<int>(kMaxProducers)));
   hp.nProducers = producers;
   hp.prodBytes = (kProdBytes + 15u) & ~15u;
   hp.oC2v = take(2048, 16);
@@ -884,7 +907,7 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   hp.tilesPerBatch = batchLines / 32;
   hp.oMeta = take(slots * hp.metaBytes, 16);
   hp.oSlots = take(slots * slotBytes, 128);
-  const size_t smemBytes = at + 256 + 32;  // alignment pad; a feed reads one block past its line's last
+  const size_t smemBytes = at + 256 + 64;  // alignment pad; a feed reads up to two blocks (and a word) past its line's last chunk
   if (smemBytes > static_cast<size_t>(geo.maxSmemOptin))
     return cudaErrorNotSupported;
 
@@ -898,13 +921,16 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
     defer = false;  // the lean walk needs an image whose accepting codes stick
   constexpr int W = kHotStrideWide, A = kHotStrideAscii;
   const bool ascii = hd.stride == kHotStrideAscii;
+  const bool dbg = tune.debug != nullptr;
+#define HOT_K(S, D, ST) (dbg ? batch_hot_kernel<S, D, ST, true> : batch_hot_kernel<S, D, ST, false>)
   auto kern = (style == STY_LAST)
-      ? (ascii ? batch_hot_kernel<STY_LAST, false, A> : batch_hot_kernel<STY_LAST, false, W>)
+      ? (ascii ? HOT_K(STY_LAST, false, A) : HOT_K(STY_LAST, false, W))
       : (style == STY_INSTANT)
-          ? (defer ? (ascii ? batch_hot_kernel<STY_INSTANT, true, A> : batch_hot_kernel<STY_INSTANT, true, W>)
-                   : (ascii ? batch_hot_kernel<STY_INSTANT, false, A> : batch_hot_kernel<STY_INSTANT, false, W>))
-          : (defer ? (ascii ? batch_hot_kernel<STY_FULL, true, A> : batch_hot_kernel<STY_FULL, true, W>)
-                   : (ascii ? batch_hot_kernel<STY_FULL, false, A> : batch_hot_kernel<STY_FULL, false, W>));
+          ? (defer ? (ascii ? HOT_K(STY_INSTANT, true, A) : HOT_K(STY_INSTANT, true, W))
+                   : (ascii ? HOT_K(STY_INSTANT, false, A) : HOT_K(STY_INSTANT, false, W)))
+          : (defer ? (ascii ? HOT_K(STY_FULL, true, A) : HOT_K(STY_FULL, true, W))
+                   : (ascii ? HOT_K(STY_FULL, false, A) : HOT_K(STY_FULL, false, W)));
+#undef HOT_K
   err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
   if (err != cudaSuccess)
     return err;
