@@ -68,6 +68,7 @@ struct HotParams {
   // byte offsets into dynamic shared memory (behind its 256-byte alignment)
   uint32_t oC2v, oBars, oCtl, oProd, oDeal, oMeta, oSlots;
   uint32_t nSlots, slotBytes, batchLines, tilesPerBatch, metaBytes, nProducers, prodBytes;
+  uint32_t tpbMagic, slotsMagic;  // floor(2^32 / d) + 1: x / d = umulhi(x, magic) for x < 2^32 / d (tickets and batch numbers of one CTA are far below)
   unsigned long long *dbg;  // null, or 16 cycle counters (HotTuning::debug)
 };
 
@@ -501,9 +502,12 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     if (lane == 0)
       tk = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl), 1u);
     tk = __shfl_sync(kFullMask, tk, 0);
-    const uint32_t qq = tk / TPB;
+    // (by multiplication: two divisions by run-time values were 40 instructions
+    // and two MUFU round trips in front of every tile)
+    const uint32_t qq = (TPB == 1) ? tk : __umulhi(tk, hp.tpbMagic);  // (d = 1 has no such magic in 32 bits)
     const uint32_t t = tk - qq * TPB;
-    const uint32_t s = qq % R;
+    const uint32_t lap = __umulhi(qq, hp.slotsMagic);  // qq / R
+    const uint32_t s = qq - lap * R;
     /* Wait for batch qq.  A parity wait tells two consecutive phases of
        full[s] apart and no more: with several producers batches are published
        out of order, and this warp may be here before batch qq - R - same slot -
@@ -518,7 +522,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        to sleep and no more - the last producer arrives there too, to wake
        those whose batch will never come: whether the batch is in is always
        read off full[s] and the slot's sequence number. */
-    const uint32_t par = (qq / R) & 1;
+    const uint32_t par = lap & 1;
     const uint32_t fullBar = barsAddr + 8 * s, readyBar = barsAddr + 8 * (2 * R + s);
     for (uint32_t spins = 0;; ++spins) {
       const bool woke = (t != 0) && mbar_try_wait(readyBar, par);
@@ -587,7 +591,14 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     const uint32_t slotA = sBase + hp.oSlots + s * hp.slotBytes;
     Walk<STYLE, false> wk;
     uint32_t code = hd.initCode;
-    bool done = false;  // the outcome is in wk (the walk stopped, or it went on the full table)
+    bool done = false;  // the walk stopped, or it went on the full table
+    /* What the outcome needs of wk, in registers of their own: wk goes through
+       calls by reference (careful passes, the full table) and so lives in local
+       memory, and a tile's lanes nearly never take those paths - but reading
+       the two fields back from there was a round trip to L2 for every tile
+       (ncu: 2 % of all the kernel's stall samples on that one load). */
+    uint32_t oMend = 0;
+    bool oAbsorbed = false;
 
     bool active = has && (off != kUnstaged) && (len != 0);
     const uint32_t tb = slotA + off;  // the line's first byte
@@ -676,8 +687,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         if (settled) {
           if ((STYLE == STY_INSTANT) && (fc < hx.cPure)) {
             const uint32_t word = feed_word(tb + (len - rem));
-            wk.mend = (len - rem) + hot_locate_quarter<STRIDE>(hx, word, min(4u, rem), code) + 1;
-            wk.absorbed = false;
+            oMend = (len - rem) + hot_locate_quarter<STRIDE>(hx, word, min(4u, rem), code) + 1;
             done = true;
           }
           code = fc;
@@ -685,6 +695,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         else if (fc != 0xffffffffu) {
           wk.begin(pd);
           hot_careful<STYLE, STRIDE>(pd, hx, tb, len - rem, len, 0, code, wk);
+          oMend = wk.mend;
+          oAbsorbed = wk.absorbed;
           done = true;
         }
       }
@@ -715,6 +727,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           }
         }
       }
+      oMend = wk.mend;
+      oAbsorbed = wk.absorbed;
     }
 
     if (has) {
@@ -726,6 +740,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         wk.begin(pd);
         done = true;
         cold_bytes<STYLE>(pd, hx.wide, wk, args.text + __ldg(args.starts + line), lineLen, 0);
+        oMend = wk.mend;
+        oAbsorbed = wk.absorbed;
         code = hx.sink;  // the state is in wk.v
       }
       // Walk::finish (Matcher.h:481-493), with the result ids of hot states
@@ -740,8 +756,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
                                           : __ldg(pd.results + state_index(pd, wk.accV));
       const int32_t result = (before > 0) ? before : now;
       // (a walk that ran out without a decision has no accepting position to report)
-      const bool absorbed = done && wk.absorbed;
-      const uint32_t mend = done ? wk.mend : 0;
+      const bool absorbed = done && oAbsorbed;
+      const uint32_t mend = done ? oMend : 0;
       const uint32_t end = (result > 0) ? (((STYLE == STY_FULL) || absorbed) ? lineLen : mend) : 0;
       // straight to the line's place: the 256 outcomes of a batch are 1 KB per
       // array, written within a few microseconds of each other - L2 puts the
@@ -902,6 +918,8 @@ cudaError_t launch_batch_hot(const ProgramDev &pd, const HotDev &hd, const Batch
   }
   hp.dbg = tune.debug;
   hp.nSlots = slots;
+  hp.slotsMagic = static_cast<uint32_t>((1ull << 32) / slots) + 1u;
+  hp.tpbMagic = static_cast<uint32_t>((1ull << 32) / (batchLines / 32)) + 1u;
   hp.slotBytes = slotBytes;
   hp.batchLines = batchLines;
   hp.tilesPerBatch = batchLines / 32;
