@@ -496,12 +496,23 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
   unsigned long long tWait = 0, tWalk = 0, tTail = 0, nTiles = 0;
   const long long tStartC = dbgOn ? clock64() : 0;
 
+  /* A tile's ticket is taken while the tile before it is finished off (the
+     atomic's round trip lies behind the flagged lanes and the outcomes).  PTX
+     with a per-lane addend: atomicAdd() under "lane == 0" becomes the
+     warp-aggregated form, whose shuffle waits for the result on the spot. */
+  auto takeTicket = [&]() -> uint32_t {
+    uint32_t t = 0;
+    if (lane == 0) {
+      uint32_t l0;
+      asm volatile("mov.u32 %0, %%laneid;" : "=r"(l0));
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(t) : "r"(ctlAddr), "r"(l0 + 1u) : "memory");
+    }
+    return t;
+  };
+  uint32_t tkAhead = takeTicket();
   for (;;) {
     const long long tc0 = dbgOn ? clock64() : 0;
-    uint32_t tk = 0;
-    if (lane == 0)
-      tk = atomicAdd(reinterpret_cast<uint32_t *>(smem + hp.oCtl), 1u);
-    tk = __shfl_sync(kFullMask, tk, 0);
+    const uint32_t tk = __shfl_sync(kFullMask, tkAhead, 0);
     // (by multiplication: two divisions by run-time values were 40 instructions
     // and two MUFU round trips in front of every tile)
     const uint32_t qq = (TPB == 1) ? tk : __umulhi(tk, hp.tpbMagic);  // (d = 1 has no such magic in 32 bits)
@@ -566,15 +577,20 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        every run of eight lanes gets every fourth line of that order. */
     {
       const uint32_t g = (off >> 4) & 7;  // (no line: 7, sorts last)
-      uint32_t r = 0;
-#pragma unroll
-      for (uint32_t v = 0; v < 8; ++v) {
-        const unsigned m = __ballot_sync(kFullMask, g == v);
-        if (v < g)
-          r += __popc(m);
-        if (v == g)
-          r += __popc(m & ((1u << lane) - 1));
-      }
+      /* Rank by (group, lane).  How many lanes each group has: a byte per
+         group, four groups to a word, summed over the warp (REDUX; a count is
+         at most 32); the lanes of the groups below g are the bytes below g's,
+         added up by a multiplication.  (Eight ballots with their counts were
+         4 % of the kernel's stall samples.) */
+      const uint32_t sh = (g & 3u) * 8u;
+      const uint32_t one = 1u << sh;
+      const uint32_t tlo = __reduce_add_sync(kFullMask, (g < 4) ? one : 0u);
+      const uint32_t thi = __reduce_add_sync(kFullMask, (g < 4) ? 0u : one);
+      const uint32_t below = one - 1u;
+      const uint32_t part = (((g < 4) ? tlo : thi) & below) * 0x01010101u;
+      const uint32_t whole = (g < 4) ? 0u : tlo * 0x01010101u;
+      const unsigned same = __match_any_sync(kFullMask, g);
+      const uint32_t r = ((part + whole) >> 24) + __popc(same & ((1u << lane) - 1));
       const uint32_t to = ((r & 3) << 3) | (r >> 2);
       const uint32_t dealA = sBase + hp.oDeal + 32 * warp;
       asm volatile("st.shared.u8 [%0], %1;" ::"r"(dealA + to), "r"(lane) : "memory");
@@ -676,6 +692,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           }
         }
       }
+      tkAhead = takeTicket();
       if (__any_sync(kFullMask, fc != 0xffffffffu)) {
         /* Flagged lanes, together.  Nearly always the run ended in a state
            that settles the line: an accepting one (Instant: where it was
@@ -729,6 +746,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       }
       oMend = wk.mend;
       oAbsorbed = wk.absorbed;
+      tkAhead = takeTicket();
     }
 
     if (has) {
