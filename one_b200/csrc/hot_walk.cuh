@@ -212,15 +212,6 @@ __device__ __forceinline__ uint4 feed_next(Feed &f) {
   f.nxt = ahead;
   return r;
 }
-// the four bytes at any address (two aligned words; the second may lie behind the text)
-__device__ __forceinline__ uint32_t feed_word(const uint32_t textAddr) {
-  const uint32_t a = textAddr & ~3u;
-  uint32_t lo, hi;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a));
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(a + 4));
-  return __byte_perm(lo, hi, 0x3210u + 0x1111u * (textAddr & 3u));
-}
-
 /* The fast pass over one aligned 16-byte chunk of one line per lane: no
    decisions, only the largest code per quarter and the code at each quarter's
    end.  [lo, hi): the bytes of the chunk that belong to the line; FULL16: they

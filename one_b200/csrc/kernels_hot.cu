@@ -58,6 +58,10 @@ namespace red_b200 {
 
 namespace {
 
+#ifndef HOT_UNROLL
+#define HOT_UNROLL 2
+#endif
+constexpr int kHotUnroll = HOT_UNROLL;    // whole chunks per trip of the consumers' interior loop
 constexpr uint32_t kMaxBatch = 256;       // lines per batch (and per claimed sub-block)
 constexpr uint32_t kSortBuckets = 256;    // by the line's length in bytes (longer lines share the first bucket)
 constexpr uint32_t kUnstaged = 0xffffu;   // sOff: the line's text is not in the slot
@@ -559,14 +563,18 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       mbar_arrive(barsAddr + 8 * (2 * R + s));
     const long long tc1 = dbgOn ? clock64() : 0;
     const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
-    const uint32_t cnt = lds32(mA + kMetaCnt);
+    // (the entries are read whether the batch has them or not - pos < 256, the
+    // arrays are that long - so that the four loads are under way together)
     const uint32_t pos = t * 32 + lane;
+    uint32_t idx = lds16(mA + kMetaIdx + 2 * pos);
+    uint32_t off = lds16(mA + kMetaOff + 2 * pos);
+    uint32_t len = lds16(mA + kMetaLen + 2 * pos);
+    const uint32_t cnt = lds32(mA + kMetaCnt);
     bool has = pos < cnt;
-    uint32_t idx = 0, off = kUnstaged, len = 0;
-    if (has) {
-      idx = lds16(mA + kMetaIdx + 2 * pos);
-      off = lds16(mA + kMetaOff + 2 * pos);
-      len = lds16(mA + kMetaLen + 2 * pos);
+    if (!has) {
+      idx = 0;
+      off = kUnstaged;
+      len = 0;
     }
     /* Deal the tile's lines out to the lanes by the 16-byte bank group their
        text starts in (every chunk of a line is then in step with its first):
@@ -639,19 +647,24 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
          which its run met the deciding code (such codes stick, so the codes
          behind the quarters tell which it was): rem and code move up to that
          quarter, and the second look is at four bytes, not sixteen. */
-      auto flag = [&](uint32_t c2, uint32_t cp0, uint32_t cp1, uint32_t cp2) {
+      uint32_t fw = 0;  // the four bytes of that quarter (the second look needs no text from shared memory)
+      auto flag = [&](uint32_t c2, uint32_t cp0, uint32_t cp1, uint32_t cp2, const uint4 &w) {
         fc = c2;
         active = false;
+        fw = w.x;
         if (c2 != 255u) {  // (255: possibly a byte >= 128 on 128-column rows - the codes mean nothing)
           const uint32_t lim = hx.cLimit;
           if (cp0 < lim) {
             uint32_t adv = 4, cq = cp0;
+            fw = w.y;
             if (cp1 < lim) {
               adv = 8;
               cq = cp1;
+              fw = w.z;
               if (cp2 < lim) {
                 adv = 12;
                 cq = cp2;
+                fw = w.w;
               }
             }
             code = cq;
@@ -660,14 +673,14 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         }
       };
       if (kFull != 0xffffffffu) {
-#pragma unroll 2
+#pragma unroll kHotUnroll
         for (uint32_t k = 0; k < kFull; ++k) {
           if (active) {
             const uint4 w = feed_next(fd);
             uint32_t cp0, cp1, cp2;
             const uint32_t c2 = hot_run_q<true, STRIDE>(hx, w, 16, code, cp0, cp1, cp2);
             if (c2 >= hx.cLimit)
-              flag(c2, cp0, cp1, cp2);
+              flag(c2, cp0, cp1, cp2, w);
             else {
               code = c2;
               rem -= 16;
@@ -682,7 +695,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
           uint32_t cp0, cp1, cp2;
           const uint32_t c2 = hot_run_q<false, STRIDE>(hx, w, min(16u, rem), code, cp0, cp1, cp2);
           if (c2 >= hx.cLimit)
-            flag(c2, cp0, cp1, cp2);
+            flag(c2, cp0, cp1, cp2, w);
           else {
             code = c2;
             if (rem <= 16)
@@ -703,8 +716,7 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         const bool settled = (fc != 0xffffffffu) && (fc != 255u) && (fc != hx.sink);
         if (settled) {
           if ((STYLE == STY_INSTANT) && (fc < hx.cPure)) {
-            const uint32_t word = feed_word(tb + (len - rem));
-            oMend = (len - rem) + hot_locate_quarter<STRIDE>(hx, word, min(4u, rem), code) + 1;
+            oMend = (len - rem) + hot_locate_quarter<STRIDE>(hx, fw, min(4u, rem), code) + 1;
             done = true;
           }
           code = fc;
