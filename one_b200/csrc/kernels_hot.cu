@@ -77,17 +77,17 @@ struct HotParams {
 };
 
 // per-slot metadata (offsets within the slot's block)
-constexpr uint32_t kMetaIdx = 0;                          // u16[256] line (relative to the batch) at sorted position
-constexpr uint32_t kMetaOff = kMetaIdx + 2 * kMaxBatch;   // u16[256] text offset in the slot
-constexpr uint32_t kMetaLen = kMetaOff + 2 * kMaxBatch;   // u16[256]
-constexpr uint32_t kMetaFirst = kMetaLen + 2 * kMaxBatch; // u64 first line of the batch
+constexpr uint32_t kMetaIdx = 0;                          // u8[256] line (relative to the batch) at sorted position
+constexpr uint32_t kMetaOL = kMetaIdx + kMaxBatch;        // u32[256] text offset in the slot | length << 16
+constexpr uint32_t kMetaArrays = kMetaOL + 4 * kMaxBatch; // (one byte and one word per line: two stores and two loads, not three)
+constexpr uint32_t kMetaFirst = kMetaArrays;              // u64 first line of the batch
 constexpr uint32_t kMetaCnt = kMetaFirst + 8;             // u32 lines in the batch
 constexpr uint32_t kMetaSeq = kMetaCnt + 4;               // u32 number of the batch the slot holds
 constexpr uint32_t kMetaBytes = kMetaSeq + 4;
 
 // per-producer scratch
 constexpr uint32_t kProdMeta = 0;                             // sorted idx/off/len of the batch being prepared
-constexpr uint32_t kProdOff = kProdMeta + 6 * kMaxBatch;      // u16[256] text offsets by line (gather path)
+constexpr uint32_t kProdOff = kProdMeta + kMetaArrays;        // u16[256] text offsets by line (gather path)
 constexpr uint32_t kProdHist = kProdOff + 2 * kMaxBatch;      // u32[kSortBuckets]
 constexpr uint32_t kProdBytes = kProdHist + 4 * kSortBuckets;
 
@@ -273,9 +273,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         for (uint32_t k = 0; k < kPer; ++k) {
           const uint32_t i = i0 + lane + 32 * k;
           if (valid[k]) {
-            sts16(mA + kMetaIdx + 2 * pos[k], i - i0);
-            sts16(mA + kMetaOff + 2 * pos[k], lds16(offA + 2 * i));
-            sts16(mA + kMetaLen + 2 * pos[k], min(lenOf(i), 0xffffu));
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(mA + kMetaIdx + pos[k]), "r"(i - i0) : "memory");
+            sts32(mA + kMetaOL + 4 * pos[k], lds16(offA + 2 * i) | (min(lenOf(i), 0xffffu) << 16));
           }
         }
         finishBatch(s, base + i0, i1 - i0);
@@ -435,9 +434,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k)
           if (valid[k]) {
-            sts16(scrA + 2 * pos[k], lane + 32 * k);
-            sts16(scrA + 2 * kMaxBatch + 2 * pos[k], static_cast<uint32_t>(st[k] - loA));
-            sts16(scrA + 4 * kMaxBatch + 2 * pos[k], min(ln[k], 0xffffu));
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(scrA + kMetaIdx + pos[k]), "r"(lane + 32 * k) : "memory");
+            sts32(scrA + kMetaOL + 4 * pos[k], static_cast<uint32_t>(st[k] - loA) | (min(ln[k], 0xffffu) << 16));
           }
         __syncwarp();
         block = __shfl_sync(kFullMask, claimed, 0);
@@ -450,12 +448,14 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
                    barsAddr + 8 * s);
         }
         const uint32_t mA = sBase + hp.oMeta + s * hp.metaBytes;
-        static_assert((kMetaOff == 2 * kMaxBatch) && (kMetaLen == 4 * kMaxBatch), "scratch mirrors the slot's arrays");
+        static_assert((kMetaArrays % 16 == 0) && (kMetaArrays <= 3 * 32 * 16), "the scratch mirrors the slot's arrays, three 16-byte pieces per lane at most");
 #pragma unroll
-        for (uint32_t k = 0; k < 6 * kMaxBatch / (32 * 16); ++k) {
+        for (uint32_t k = 0; k < 3; ++k) {
           const uint32_t o = 16 * (lane + 32 * k);
-          const uint4 v = lds128(scrA + o);
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mA + o), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+          if (o < kMetaArrays) {
+            const uint4 v = lds128(scrA + o);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(mA + o), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+          }
         }
         finishBatch(s, base, cnt);
       }
@@ -566,9 +566,10 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
     // (the entries are read whether the batch has them or not - pos < 256, the
     // arrays are that long - so that the four loads are under way together)
     const uint32_t pos = t * 32 + lane;
-    uint32_t idx = lds16(mA + kMetaIdx + 2 * pos);
-    uint32_t off = lds16(mA + kMetaOff + 2 * pos);
-    uint32_t len = lds16(mA + kMetaLen + 2 * pos);
+    uint32_t idx = lds8(mA + kMetaIdx + pos);
+    const uint32_t ol = lds32(mA + kMetaOL + 4 * pos);
+    uint32_t off = ol & 0xffffu;
+    uint32_t len = ol >> 16;
     const uint32_t cnt = lds32(mA + kMetaCnt);
     bool has = pos < cnt;
     if (!has) {
