@@ -400,21 +400,35 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       const uint32_t cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(SUB), n - base));
       if (lane == 0)
         claimed = atomicAdd(blockCounter, 1ull);  // the next sub-block; looked at below
-      // the span of the sub-block's text
-      uint64_t lo = ~0ull, hi = 0;
+      /* The span of the sub-block's text, in 32 bits: every line's start
+         relative to the sub-block's first line (lane 0 has it; a sub-block that
+         is taken has one), smallest start and largest end by REDUX.  (In 64
+         bits it was eight wide adds, mins and maxes per lane and five rounds of
+         four shuffles.)  Lines a gigabyte apart go the rare shapes' way. */
+      const uint64_t ref = textA + __shfl_sync(kFullMask, st[0], 0);
+      int32_t rel[kPer];
+      int32_t dlo = 0x7fffffff, dhi = -0x7fffffff - 1;
+      bool near = true;
 #pragma unroll
-      for (uint32_t k = 0; k < kPer; ++k)
+      for (uint32_t k = 0; k < kPer; ++k) {
+        rel[k] = 0;
         if (valid[k]) {
-          st[k] += textA;
-          lo = min(lo, st[k]);
-          hi = max(hi, st[k] + ln[k]);
+          const int64_t d = static_cast<int64_t>(st[k] + textA - ref);
+          near = near && (d > -(1ll << 30)) && (d < (1ll << 30)) && (ln[k] < (1u << 30));
+          rel[k] = static_cast<int32_t>(d);
+          dlo = min(dlo, rel[k]);
+          dhi = max(dhi, rel[k] + static_cast<int32_t>(ln[k]));
         }
+      }
       if (dbgOn)
         tIdx += clock64() - tI0;
-#pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) {
-        lo = min(lo, __shfl_xor_sync(kFullMask, lo, d));
-        hi = max(hi, __shfl_xor_sync(kFullMask, hi, d));
+      near = __all_sync(kFullMask, near);
+      uint64_t lo = ~0ull, hi = 0;  // (hi < lo: not the usual shape)
+      if (near) {
+        dlo = __reduce_min_sync(kFullMask, dlo);
+        dhi = __reduce_max_sync(kFullMask, dhi);
+        lo = ref + static_cast<int64_t>(dlo);
+        hi = ref + static_cast<int64_t>(dhi);
       }
       const uint64_t loA = lo & ~15ull;
       const uint64_t hiA = (hi + 15) & ~15ull;
@@ -426,16 +440,17 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         // takes from there on is time the slot stands empty.
         if ((lane == 0) && (hiA > loA))
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(loA), "r"(static_cast<uint32_t>(hiA - loA)) : "memory");
+        const uint32_t relBias = static_cast<uint32_t>(ref - loA);  // a line's offset in the slot = rel + (ref - loA), mod 2^32
         uint32_t bucket[kPer], pos[kPer];
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k)
-          bucket[k] = valid[k] ? bucketOf(static_cast<uint32_t>(st[k] - loA), ln[k]) : 0;
+          bucket[k] = valid[k] ? bucketOf(static_cast<uint32_t>(rel[k]) + relBias, ln[k]) : 0;
         sortPositions(bucket, valid, pos);
 #pragma unroll
         for (uint32_t k = 0; k < kPer; ++k)
           if (valid[k]) {
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(scrA + kMetaIdx + pos[k]), "r"(lane + 32 * k) : "memory");
-            sts32(scrA + kMetaOL + 4 * pos[k], static_cast<uint32_t>(st[k] - loA) | (min(ln[k], 0xffffu) << 16));
+            sts32(scrA + kMetaOL + 4 * pos[k], (static_cast<uint32_t>(rel[k]) + relBias) | (min(ln[k], 0xffffu) << 16));
           }
         __syncwarp();
         block = __shfl_sync(kFullMask, claimed, 0);
