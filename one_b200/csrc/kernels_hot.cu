@@ -33,8 +33,16 @@
        running maximum, the code behind a 16-byte chunk says whether anything
        happened, a flagged lane steps aside, and when the tile is through all
        flagged lanes settle their outcome together - the state itself names
-       it, and for Instant a second run over the chunk counts out where it was
-       entered.
+       it, and for Instant a second run over the QUARTER of the chunk in
+       which the run met it counts out where it was entered (the codes behind
+       the quarters are kept, the quarter's four bytes too);
+     * what lies around the lookups is kept off a tile's critical path: the
+       next chunk's text is loaded a chunk ahead, the next tile's ticket while
+       the current tile is finished off, ticket arithmetic is by
+       multiplication, the outcome's fields stay in registers, the dealing's
+       ranks come from two warp sums and a match, the producers' span
+       arithmetic is in 32 bits ("What a tile costs besides its
+       chain").
 
    Roles in a CTA: warps 0 .. NC-1 are consumers (a tile of 32 lines at a
    time, claimed in order from a shared-memory ticket), the warps behind them
