@@ -647,6 +647,22 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
        (ncu: 2 % of all the kernel's stall samples on that one load). */
     uint32_t oMend = 0;
     bool oAbsorbed = false;
+    /* The slot is given back as soon as the tile's lanes need nothing of it any
+       more - behind the walk, in front of the flagged lanes' second look (which
+       reads no text) and the outcomes - unless a lane has to go byte by byte
+       through its text: the producers get the slot a few hundred cycles
+       earlier for every tile, and what the consumers wait for is the copy that
+       follows.  The batch's first line number is read before that (the slot's
+       meta block is the next batch's then). */
+    uint64_t first = 0;
+    bool released = false;
+    auto release = [&]() {
+      first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(barsAddr + 8 * (R + s));
+      released = true;
+    };
 
     bool active = has && (off != kUnstaged) && (len != 0);
     const uint32_t tb = slotA + off;  // the line's first byte
@@ -730,6 +746,8 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
         }
       }
       tkAhead = takeTicket();
+      if (!__any_sync(kFullMask, (fc != 0xffffffffu) && ((fc == 255u) || (fc == hx.sink))))
+        release();
       if (__any_sync(kFullMask, fc != 0xffffffffu)) {
         /* Flagged lanes, together.  Nearly always the run ended in a state
            that settles the line: an accepting one (Instant: where it was
@@ -783,13 +801,16 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       oMend = wk.mend;
       oAbsorbed = wk.absorbed;
       tkAhead = takeTicket();
+      release();
     }
+    if (!released)
+      first = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst);
 
     if (has) {
       uint32_t lineLen = len;
       if (off == kUnstaged) {
         // longer than a slot: from global memory, on the full table
-        const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
+        const uint64_t line = first + idx;
         lineLen = __ldg(args.lens + line);
         wk.begin(pd);
         done = true;
@@ -817,14 +838,14 @@ batch_hot_kernel(const ProgramDev pd, const HotDev hd, const BatchArgs args, con
       // array, written within a few microseconds of each other - L2 puts the
       // sectors together (collecting them per batch in shared memory for a
       // coalesced copy cost a counter, two fences and 570 cycles per tile)
-      const uint64_t line = *reinterpret_cast<const uint64_t *>(smem + hp.oMeta + s * hp.metaBytes + kMetaFirst) + idx;
+      const uint64_t line = first + idx;
       args.results[line] = result;
       if (args.matchEnds)
         args.matchEnds[line] = end;
     }
     __syncwarp();
     const long long tc2 = dbgOn ? clock64() : 0;
-    if (lane == 0)
+    if (!released && (lane == 0))
       mbar_arrive(barsAddr + 8 * (R + s));
     if (dbgOn) {
       const long long tc3 = clock64();
